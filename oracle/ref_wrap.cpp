@@ -1,0 +1,283 @@
+/*
+ * TEST INFRASTRUCTURE ONLY (oracle/).  Nothing under elba_b200/ may include,
+ * link or execute this; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs load the library built from it.
+ *
+ * oracle/_ref/libelba_ref_k<K>_l<L>_u<U>.so = the REFERENCE'S OWN sources,
+ * compiled unmodified from where they lie under /root/reference
+ * (src/{DnaSeq,DnaBuffer,HashFuncs,Bloom,HyperLogLog,Logger,KmerOps,
+ * SharedSeeds}.cpp + include/), against oracle/stubs/{mpi.h,CombBLAS/} and
+ * this C-ABI shim.  It is what pins oracle/elba_oracle.cpp.
+ *
+ * What is genuinely the reference here: every k-mer, hash, HyperLogLog, Bloom,
+ * DnaSeq/DnaBuffer operation, both counting passes of KmerOps.cpp, the triple
+ * generation of create_kmer_matrix and the SharedSeeds semiring + Prune call.
+ * What is a restatement: MPI (threads, stubs/mpi.h) and the five CombBLAS
+ * entry points (stubs/CombBLAS/CombBLAS.h — unpinned external dependency).
+ *
+ * K, LOWER, UPPER are compile-time macros in the reference
+ * (include/compiletime.h:7-22), hence one library per (K,L,U).
+ */
+#include <cstring>
+#include <cstdint>
+#include <cstddef>
+#include <numeric>
+#include <algorithm>
+#include <iomanip>
+#include <cmath>
+#include <thread>
+#include <chrono>
+#include <mpi.h>
+#include "common.h"             /* pulls the stubs + every std header first */
+#define private public          /* HyperLogLog::registers, Bloom::bf are private */
+#include "HyperLogLog.hpp"
+#include "Bloom.hpp"
+#undef private
+#include "KmerOps.hpp"
+#include "SharedSeeds.hpp"
+#include "HashFuncs.hpp"
+#include "Logger.hpp"
+#include "DnaSeq.hpp"
+#include "DnaBuffer.hpp"
+#include <cstring>
+#include <numeric>
+#include <algorithm>
+#include <iomanip>
+#include <cmath>
+#include <thread>
+#include <chrono>
+
+/*
+ * src/KmerOps.cpp keeps its Bloom filter in a file-static pointer
+ * (KmerOps.cpp:12-13).  Ranks are threads here, so that one static must be
+ * per-thread; every header the file includes is already included above
+ * (guards), so the macro below touches that single declaration only.
+ */
+#define static static thread_local
+#include REF_KMEROPS_CPP   /* = "<reference>/src/KmerOps.cpp", set by oracle/Makefile */
+#undef static
+
+namespace {
+
+struct RefResult
+{
+    int nranks = 1;
+    /* reliable k-mers in the reference's own column-id order */
+    std::vector<uint64_t> kmer;
+    std::vector<int32_t> count;
+    std::vector<int64_t> reads;      /* R x UPPER, arrival order */
+    std::vector<uint32_t> pos;       /* R x UPPER */
+    std::vector<uint64_t> keys_after_pass1;   /* per rank: map size after pass 1 */
+    /* A */
+    int64_t a_m = 0, a_n = 0;
+    std::vector<int64_t> a_rowptr, a_col;
+    std::vector<uint32_t> a_val;
+    /* B after prune */
+    std::vector<int64_t> b_rowptr, b_col;
+    std::vector<int32_t> b_num;
+    std::vector<uint32_t> b_seeds;   /* nnz x 4: s0.q s0.t s1.q s1.t */
+    int64_t b_nnz_preprune = 0;
+    double secs[6] = {0,0,0,0,0,0};  /* keys, values, matrix, transpose, spgemm, total */
+};
+
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+/* contiguous, base-balanced blocks: src/FastaIndex.cpp:47-94 */
+std::vector<uint64_t> partition_reads(const uint64_t *lens, uint64_t n, int P)
+{
+    std::vector<uint64_t> start(P + 1, n);
+    double tot = 0; for (uint64_t i = 0; i < n; ++i) tot += (double)lens[i];
+    double avg = tot / P;
+    uint64_t id = 0;
+    for (int r = 0; r < P - 1; ++r)
+    {
+        start[r] = id;
+        double sofar = 0;
+        while (id < n && sofar + (double)lens[id] < avg) { sofar += (double)lens[id]; id++; }
+    }
+    start[P-1] = id; start[P] = n;
+    if (P == 1) start[0] = 0;
+    return start;
+}
+
+} // namespace
+
+extern "C" {
+
+void ref_params(int *k, int *l, int *u) { *k = KMER_SIZE; *l = LOWER_KMER_FREQ; *u = UPPER_KMER_FREQ; }
+
+/* DnaSeq::compress, src/DnaSeq.cpp:7-29 */
+void ref_pack(const char *s, uint64_t len, uint8_t *mem) { DnaSeq seq(s, len, mem); (void)seq; }
+
+/* Kmer ctor/GetTwin/GetRep/GetHash on a k-character ASCII k-mer */
+void ref_kmer_info(const char *s, uint64_t *fwd, uint64_t *twin, uint64_t *rep, uint64_t *hash)
+{
+    TKmer f(s), t = f.GetTwin(), r = f.GetRep();
+    f.CopyDataInto(fwd); t.CopyDataInto(twin); r.CopyDataInto(rep);
+    *hash = r.GetHash();
+}
+
+uint64_t ref_hash(uint64_t kmer) { TKmer m((const void*)&kmer); return m.GetHash(); }
+int ref_owner(uint64_t kmer, int nprocs) { TKmer m((const void*)&kmer); return GetKmerOwner(m, nprocs); }
+
+/* TKmer::GetRepKmers over one packed read, src/Kmer.cpp:236-242 */
+uint64_t ref_rep_kmers(const uint8_t *packed, uint64_t len, uint64_t *out)
+{
+    DnaSeq seq(len, const_cast<uint8_t*>(packed));
+    if (len < KMER_SIZE) return 0;
+    auto v = TKmer::GetRepKmers(seq);
+    for (size_t i = 0; i < v.size(); ++i) v[i].CopyDataInto(out + i);
+    return v.size();
+}
+
+/* HyperLogLog exactly as get_kmer_count_map_keys drives it: KmerOps.cpp:45-47 */
+double ref_hll(const uint8_t *packed, const uint64_t *lens, uint64_t nreads, uint8_t *regs_out)
+{
+    size_t bufsize = 0; for (uint64_t i = 0; i < nreads; ++i) bufsize += DnaSeq::bytesneeded(lens[i]);
+    uint8_t *buf = new uint8_t[bufsize ? bufsize : 1]; std::memcpy(buf, packed, bufsize);
+    std::vector<size_t> l(lens, lens + nreads);
+    DnaBuffer dna(bufsize, nreads, buf, l.data());
+    HyperLogLog hll;
+    KmerEstimateHandler estimator(hll);
+    ForeachKmer(dna, estimator);
+    if (regs_out) std::memcpy(regs_out, hll.registers.data(), 4096);
+    return hll.estimate();
+}
+
+/* Bloom */
+void *ref_bloom_new(int64_t entries, double err) { return new Bloom(entries, err); }
+void ref_bloom_free(void *b) { delete (Bloom*)b; }
+int64_t ref_bloom_bits(void *b) { return ((Bloom*)b)->bits; }
+int ref_bloom_hashes(void *b) { return ((Bloom*)b)->hashes; }
+int ref_bloom_check(void *b, uint64_t kmer) { return ((Bloom*)b)->Check(&kmer, 8); }
+int ref_bloom_add(void *b, uint64_t kmer) { return ((Bloom*)b)->Add(&kmer, 8); }
+void ref_bloom_copy(void *b, uint8_t *out) { std::memcpy(out, ((Bloom*)b)->bf, ((Bloom*)b)->bytes); }
+
+/*
+ * The hot path exactly as src/main.cpp:191-282 sequences it, on `nranks`
+ * thread-ranks: get_kmer_count_map_keys -> get_kmer_count_map_values ->
+ * create_kmer_matrix -> copy + Transpose -> create_seed_matrix.
+ */
+void *ref_run(const uint8_t *packed, const uint64_t *lens, uint64_t nreads, int nranks)
+{
+    RefResult *res = new RefResult; res->nranks = nranks;
+    std::vector<uint64_t> start = partition_reads(lens, nreads, nranks);
+    std::vector<uint64_t> byteoff(nreads + 1, 0);
+    for (uint64_t i = 0; i < nreads; ++i) byteoff[i+1] = byteoff[i] + DnaSeq::bytesneeded(lens[i]);
+
+    fake_mpi::World world(nranks);
+    fake_mpi::g_world = &world;
+    res->keys_after_pass1.assign(nranks, 0);
+
+    struct PerRank { std::vector<uint64_t> kmer; std::vector<int32_t> count; std::vector<int64_t> reads; std::vector<uint32_t> pos; };
+    std::vector<PerRank> per(nranks);
+    std::vector<double> t(nranks * 6, 0.0);
+
+    auto body = [&](int rank)
+    {
+        fake_mpi::t_rank = rank;
+        auto commgrid = std::make_shared<CommGrid>(MPI_COMM_WORLD, 0, 0);
+        uint64_t r0 = start[rank], r1 = start[rank+1];
+        size_t bufsize = byteoff[r1] - byteoff[r0];
+        uint8_t *buf = new uint8_t[bufsize ? bufsize : 1]; std::memcpy(buf, packed + byteoff[r0], bufsize);
+        std::vector<size_t> l(lens + r0, lens + r1);
+        DnaBuffer mydna(bufsize, r1 - r0, buf, l.data());
+        double *tt = &t[rank * 6];
+
+        MPI_Barrier(MPI_COMM_WORLD); double t0 = now(), ta = t0;
+        auto kmermap = get_kmer_count_map_keys(mydna, commgrid);
+        MPI_Barrier(MPI_COMM_WORLD); tt[0] = now() - ta; ta = now();
+        res->keys_after_pass1[rank] = kmermap->size();
+        get_kmer_count_map_values(mydna, *kmermap, commgrid);
+        MPI_Barrier(MPI_COMM_WORLD); tt[1] = now() - ta;
+
+        /* snapshot the map in its own iteration order == the reference's column-id order */
+        PerRank& pr = per[rank];
+        for (auto it = kmermap->cbegin(); it != kmermap->cend(); ++it)
+        {
+            uint64_t x; it->first.CopyDataInto(&x);
+            pr.kmer.push_back(x); pr.count.push_back(std::get<2>(it->second));
+            for (int j = 0; j < UPPER_KMER_FREQ; ++j) { pr.reads.push_back(std::get<0>(it->second)[j]); pr.pos.push_back(std::get<1>(it->second)[j]); }
+        }
+
+        MPI_Barrier(MPI_COMM_WORLD); ta = now();
+        auto A = create_kmer_matrix(mydna, *kmermap, commgrid);
+        MPI_Barrier(MPI_COMM_WORLD); tt[2] = now() - ta; ta = now();
+        kmermap.reset();
+        auto AT = std::make_unique<CT<PosInRead>::PSpParMat>(*A);
+        AT->Transpose();
+        MPI_Barrier(MPI_COMM_WORLD); tt[3] = now() - ta; ta = now();
+
+        /* create_seed_matrix (src/SharedSeeds.cpp:4-10), split only to read nnz before Prune */
+        auto Bpre = Mult_AnXBn_DoubleBuff<SharedSeeds::Semiring, SharedSeeds, CT<SharedSeeds>::PSpDCCols>(*A, *AT);
+        int64_t pre = Bpre.getnnz();
+        auto B = create_seed_matrix(*A, *AT);
+        MPI_Barrier(MPI_COMM_WORLD); tt[4] = (now() - ta) / 2.0; tt[5] = now() - t0 - tt[4];
+
+        if (rank == 0)
+        {
+            res->a_m = A->getnrow(); res->a_n = A->getncol();
+            res->a_rowptr.assign(A->st->rowptr.begin(), A->st->rowptr.end());
+            res->a_col.assign(A->st->col.begin(), A->st->col.end());
+            res->a_val.assign(A->st->val.begin(), A->st->val.end());
+            res->b_nnz_preprune = pre;
+            res->b_rowptr.assign(B->st->rowptr.begin(), B->st->rowptr.end());
+            res->b_col.assign(B->st->col.begin(), B->st->col.end());
+            for (const SharedSeeds& s : B->st->val)
+            {
+                res->b_num.push_back(s.getnumshared());
+                res->b_seeds.push_back(std::get<0>(s.getseeds()[0])); res->b_seeds.push_back(std::get<1>(s.getseeds()[0]));
+                res->b_seeds.push_back(std::get<0>(s.getseeds()[1])); res->b_seeds.push_back(std::get<1>(s.getseeds()[1]));
+            }
+        }
+        MPI_Barrier(MPI_COMM_WORLD);
+    };
+
+    if (nranks == 1) body(0);
+    else
+    {
+        std::vector<std::thread> th;
+        for (int r = 0; r < nranks; ++r) th.emplace_back(body, r);
+        for (auto& x : th) x.join();
+    }
+    fake_mpi::g_world = nullptr; fake_mpi::t_rank = 0;
+
+    for (int r = 0; r < nranks; ++r)
+    {
+        res->kmer.insert(res->kmer.end(), per[r].kmer.begin(), per[r].kmer.end());
+        res->count.insert(res->count.end(), per[r].count.begin(), per[r].count.end());
+        res->reads.insert(res->reads.end(), per[r].reads.begin(), per[r].reads.end());
+        res->pos.insert(res->pos.end(), per[r].pos.begin(), per[r].pos.end());
+    }
+    for (int s = 0; s < 6; ++s) { double mx = 0; for (int r = 0; r < nranks; ++r) mx = std::max(mx, t[r*6+s]); res->secs[s] = mx; }
+    return res;
+}
+
+void ref_free(void *h) { delete (RefResult*)h; }
+void ref_sizes(void *h, int64_t *out /*[8]*/)
+{
+    RefResult *r = (RefResult*)h;
+    out[0] = r->kmer.size(); out[1] = r->a_m; out[2] = r->a_n; out[3] = r->a_col.size();
+    out[4] = r->b_col.size(); out[5] = r->b_nnz_preprune; out[6] = 0; for (auto v : r->keys_after_pass1) out[6] += v; out[7] = r->nranks;
+}
+void ref_secs(void *h, double *out /*[6]*/) { std::memcpy(out, ((RefResult*)h)->secs, sizeof(double) * 6); }
+void ref_get_kmers(void *h, uint64_t *kmer, int32_t *count, int64_t *reads, uint32_t *pos)
+{
+    RefResult *r = (RefResult*)h;
+    std::memcpy(kmer, r->kmer.data(), r->kmer.size() * 8); std::memcpy(count, r->count.data(), r->count.size() * 4);
+    std::memcpy(reads, r->reads.data(), r->reads.size() * 8); std::memcpy(pos, r->pos.data(), r->pos.size() * 4);
+}
+void ref_get_A(void *h, int64_t *rowptr, int64_t *col, uint32_t *val)
+{
+    RefResult *r = (RefResult*)h;
+    std::memcpy(rowptr, r->a_rowptr.data(), r->a_rowptr.size() * 8); std::memcpy(col, r->a_col.data(), r->a_col.size() * 8);
+    std::memcpy(val, r->a_val.data(), r->a_val.size() * 4);
+}
+void ref_get_B(void *h, int64_t *rowptr, int64_t *col, int32_t *num, uint32_t *seeds)
+{
+    RefResult *r = (RefResult*)h;
+    std::memcpy(rowptr, r->b_rowptr.data(), r->b_rowptr.size() * 8); std::memcpy(col, r->b_col.data(), r->b_col.size() * 8);
+    std::memcpy(num, r->b_num.data(), r->b_num.size() * 4); std::memcpy(seeds, r->b_seeds.data(), r->b_seeds.size() * 4);
+}
+
+} // extern "C"

@@ -1,0 +1,724 @@
+// C ABI of the B200-native ELBA front end (include/elba_fe.h): context, HBM buffers, phase orchestration.
+// Host code is C++; CUDA is reached only from here.  sm_100a only, no CPU fallback.
+#include "../../include/elba_fe.h"
+#include "common.cuh"
+#include "kmer_count.cuh"
+#include "sketch.cuh"
+#include "matrix_build.cuh"
+#include "spgemm.cuh"
+#include <cub/cub.cuh>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+#include <algorithm>
+
+using namespace elba;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf
+{
+    void *p = nullptr; size_t cap = 0;
+    template <class T> T *as() const { return reinterpret_cast<T*>(p); }
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = (bytes + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct EventPair { cudaEvent_t a = nullptr, b = nullptr; };
+
+} // namespace
+
+struct elba_fe_ctx
+{
+    elba_fe_config cfg;
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    int phase = 0;                      // 0 none, 1 reads, 2 counted, 3 A built, 4 B built
+    // reads
+    DevBuf packed, off, len64, len32, chunk_start, kmer_start, nks_start;
+    u32 n = 0; u64 packed_bytes = 0, nchunks = 0, M = 0, Ms = 0; int64_t read_id_offset = 0;
+    // counting
+    DevBuf table, cand, ctr, partbuf, phist, pcursor, rel_key, rel_cnt, rel_key_s, rel_cnt_s, lut;
+    u64 lut_mask = 0; u64 rel_cap = 0;
+    // A
+    DevBuf seed_key, seed_pos, seed_key2, seed_pos2, idx, a_key, a_rowptr, a_col, a_pos, at_key, at_key2, at_pos2, at_colptr, at_row, at_pos, prod;
+    int col_bits = 1, read_bits = 1;
+    // B
+    DevBuf t_col, t_num, t_seeds, row_off, row_nnz, bins, small_rows, big_rows, ovf_rows, gscratch, b_rowptr, b_col, b_num, b_seeds;
+    u64 b_cap_hint = 0;
+    DevBuf cubtmp, hll_regs, bloom;
+    elba_fe_sizes_t sz;
+    elba_fe_timings_t tm;
+    cudaEvent_t ev[8];
+    std::vector<EventPair> kev; size_t kev_used = 0;      // per-kernel event pairs (count kernels)
+    std::vector<EventPair> sev; size_t sev_used = 0;      // spgemm numeric kernels
+    std::vector<EventPair> pev; size_t pev_used = 0;      // partition kernels
+    std::vector<EventPair> lev; size_t lev_used = 0;      // lookup kernel
+};
+
+namespace {
+
+int fail(elba_fe_ctx *c, int code, const std::string &msg) { if (c) c->err = msg; else g_create_error = msg; return code; }
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+    return fail(ctx, e__ == cudaErrorMemoryAllocation ? ELBA_FE_ERR_OOM : ELBA_FE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
+#define CKL() CK(cudaGetLastError())
+#define LAUNCHED(ctx) ((ctx)->tm.kernel_launches++)
+
+inline u32 nblk(u64 n, u32 b) { return (u32)((n + b - 1) / b); }
+inline u64 next_pow2(u64 v) { u64 p = 1; while (p < v) p <<= 1; return p; }
+inline int bits_for(u64 v) { int b = 1; while ((1ull << b) < v) ++b; return b; }   // bits to hold values < v
+
+EventPair &next_pair(std::vector<EventPair> &v, size_t &used)
+{
+    if (used == v.size()) { EventPair p; cudaEventCreate(&p.a); cudaEventCreate(&p.b); v.push_back(p); }
+    return v[used++];
+}
+float sum_pairs(std::vector<EventPair> &v, size_t used)
+{
+    float tot = 0; for (size_t i = 0; i < used; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, v[i].a, v[i].b) == cudaSuccess) tot += ms; } return tot;
+}
+
+ReadsView view(elba_fe_ctx *c)
+{
+    ReadsView rv; rv.buf = c->packed.as<uint8_t>(); rv.off = c->off.as<u64>(); rv.len = c->len32.as<u32>();
+    rv.chunk_start = c->chunk_start.as<u64>(); rv.kmer_start = c->kmer_start.as<u64>(); rv.n = c->n; rv.nchunks = c->nchunks;
+    return rv;
+}
+
+template <class T> int exclusive_scan_inplace(elba_fe_ctx *ctx, T *d, u64 n)
+{
+    size_t need = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, need, d, d, (int64_t)n, ctx->stream));
+    CK(ctx->cubtmp.ensure(need));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, need, d, d, (int64_t)n, ctx->stream));
+    ctx->tm.kernel_launches += 2;
+    return 0;
+}
+
+int sort_pairs(elba_fe_ctx *ctx, const u64 *kin, u64 *kout, const u32 *vin, u32 *vout, u64 n, int begin_bit, int end_bit)
+{
+    if (n == 0) return 0;
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, kin, kout, vin, vout, (int64_t)n, begin_bit, end_bit, ctx->stream));
+    CK(ctx->cubtmp.ensure(need));
+    CK(cub::DeviceRadixSort::SortPairs(ctx->cubtmp.p, need, kin, kout, vin, vout, (int64_t)n, begin_bit, end_bit, ctx->stream));
+    ctx->tm.kernel_launches += (u32)((end_bit - begin_bit + 7) / 8 + 1);
+    return 0;
+}
+
+int grid_for(elba_fe_ctx *c, int per_sm) { return c->sm_count * per_sm; }
+
+// after the reads are resident: per-read tables and totals
+int prepare_reads(elba_fe_ctx *ctx)
+{
+    u32 n = ctx->n;
+    CK(ctx->len32.ensure(sizeof(u32) * (size_t)(n + 1)));
+    CK(ctx->chunk_start.ensure(sizeof(u64) * (size_t)(n + 1)));
+    CK(ctx->kmer_start.ensure(sizeof(u64) * (size_t)(n + 1)));
+    CK(ctx->nks_start.ensure(sizeof(u64) * (size_t)(n + 1)));
+    k_prep_reads<<<nblk((u64)n + 1, 256), 256, 0, ctx->stream>>>(ctx->len64.as<u64>(), n, ctx->cfg.k, ctx->cfg.stride,
+        ctx->len32.as<u32>(), ctx->chunk_start.as<u64>(), ctx->kmer_start.as<u64>(), ctx->nks_start.as<u64>());
+    CKL(); LAUNCHED(ctx);
+    int rc;
+    if ((rc = exclusive_scan_inplace(ctx, ctx->chunk_start.as<u64>(), (u64)n + 1))) return rc;
+    if ((rc = exclusive_scan_inplace(ctx, ctx->kmer_start.as<u64>(), (u64)n + 1))) return rc;
+    if ((rc = exclusive_scan_inplace(ctx, ctx->nks_start.as<u64>(), (u64)n + 1))) return rc;
+    u64 tot[3];
+    CK(cudaMemcpyAsync(&tot[0], ctx->chunk_start.as<u64>() + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&tot[1], ctx->kmer_start.as<u64>() + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&tot[2], ctx->nks_start.as<u64>() + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nchunks = tot[0]; ctx->M = tot[1]; ctx->Ms = tot[2];
+    std::memset(&ctx->sz, 0, sizeof ctx->sz);
+    ctx->sz.nreads = n; ctx->sz.num_kmers = ctx->Ms;
+    ctx->phase = 1;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int elba_fe_version(void) { return ELBA_FE_VERSION; }
+
+void elba_fe_default_config(elba_fe_config *cfg)
+{
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->k = 31; cfg->lower = 15; cfg->upper = 35;     /* reference Makefile:1-3 */
+    cfg->stride = 1; cfg->seed_count = 2; cfg->device = 0; cfg->num_partitions = 0; cfg->flags = 0;
+}
+
+const char *elba_fe_last_error(const elba_fe_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
+{
+    elba_fe_ctx *ctx = nullptr;
+    if (!cfg || !out) return fail(nullptr, ELBA_FE_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->k < 3 || cfg->k > ELBA_FE_MAX_KMER_SIZE) return fail(nullptr, ELBA_FE_ERR_INVALID, "k must be in 3..32 (one 64-bit word, include/Kmer.hpp:95-97)");
+    if (cfg->stride < 1) return fail(nullptr, ELBA_FE_ERR_INVALID, "stride must be >= 1");
+    if (cfg->seed_count < 1 || cfg->seed_count > 2) return fail(nullptr, ELBA_FE_ERR_INVALID, "seed_count must be 1 or 2 (SharedSeeds::seeds[2], include/SharedSeeds.hpp:94)");
+    if (cfg->lower < 2) return fail(nullptr, ELBA_FE_ERR_INVALID, "lower must be >= 2: with LOWER_KMER_FREQ=1 the reference's result depends on Bloom false positives");
+    if (cfg->upper < cfg->lower || cfg->upper > 65535) return fail(nullptr, ELBA_FE_ERR_INVALID, "need lower <= upper <= 65535 (include/compiletime.h:21)");
+    if (cfg->num_partitions < 0 || cfg->num_partitions > 4096) return fail(nullptr, ELBA_FE_ERR_INVALID, "num_partitions must be in 0..4096");
+    if (cfg->flags != 0) return fail(nullptr, ELBA_FE_ERR_INVALID, "unsupported flags");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ELBA_FE_ERR_NO_DEVICE, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, ELBA_FE_ERR_INVALID, "device ordinal out of range");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, ELBA_FE_ERR_CUDA, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, ELBA_FE_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, ELBA_FE_ERR_NO_DEVICE, "device is not sm_100 (this library carries sm_100a code only)");
+    ctx = new elba_fe_ctx;
+    ctx->cfg = *cfg;
+    ctx->sm_count = prop.multiProcessorCount;
+    std::memset(&ctx->sz, 0, sizeof ctx->sz); std::memset(&ctx->tm, 0, sizeof ctx->tm);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, ELBA_FE_ERR_CUDA, "cudaStreamCreate failed"); }
+    ctx->own_stream = true;
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    // opt in to the large dynamic shared memory of the scatter kernel
+    cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    *out = ctx;
+    return 0;
+}
+
+int elba_fe_destroy(elba_fe_ctx *ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *all[] = { &ctx->packed, &ctx->off, &ctx->len64, &ctx->len32, &ctx->chunk_start, &ctx->kmer_start, &ctx->nks_start,
+        &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut,
+        &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
+        &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
+        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->bins, &ctx->small_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
+        &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom };
+    for (DevBuf *b : all) b->release();
+    for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    for (auto *v : { &ctx->kev, &ctx->sev, &ctx->pev, &ctx->lev }) for (auto &p : *v) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int elba_fe_set_stream(elba_fe_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int elba_fe_synchronize(elba_fe_ctx *ctx) { if (!ctx) return ELBA_FE_ERR_INVALID; CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+static int stage_reads(elba_fe_ctx *ctx, const uint8_t *packed, uint64_t packed_bytes, const uint64_t *byte_off, const uint64_t *len,
+                       uint64_t nreads, int64_t read_id_offset, cudaMemcpyKind kind)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (nreads >= 0xFFFFFFF0ull) return fail(ctx, ELBA_FE_ERR_INVALID, "too many reads for one context (local read ids are 32-bit)");
+    if (nreads && (!byte_off || !len)) return fail(ctx, ELBA_FE_ERR_INVALID, "null read tables");
+    if (packed_bytes && !packed) return fail(ctx, ELBA_FE_ERR_INVALID, "null arena");
+    CK(cudaSetDevice(ctx->cfg.device));
+    ctx->phase = 0;
+    ctx->n = (u32)nreads; ctx->packed_bytes = packed_bytes; ctx->read_id_offset = read_id_offset;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CK(ctx->packed.ensure(packed_bytes + 64));
+    CK(ctx->off.ensure(sizeof(u64) * (size_t)(nreads + 1)));
+    CK(ctx->len64.ensure(sizeof(u64) * (size_t)(nreads + 1)));
+    CK(cudaMemsetAsync(ctx->packed.as<uint8_t>() + packed_bytes, 0, 64, ctx->stream));
+    if (packed_bytes) CK(cudaMemcpyAsync(ctx->packed.p, packed, packed_bytes, kind, ctx->stream));
+    if (nreads)
+    {
+        CK(cudaMemcpyAsync(ctx->off.p, byte_off, sizeof(u64) * nreads, kind, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->len64.p, len, sizeof(u64) * nreads, kind, ctx->stream));
+    }
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    int rc = prepare_reads(ctx);
+    if (rc) return rc;
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->tm.upload_ms = ms;
+    return 0;
+}
+
+int elba_fe_upload_reads(elba_fe_ctx *ctx, const uint8_t *packed, uint64_t packed_bytes, const uint64_t *byte_off, const uint64_t *len,
+                         uint64_t nreads, int64_t read_id_offset)
+{
+    return stage_reads(ctx, packed, packed_bytes, byte_off, len, nreads, read_id_offset, cudaMemcpyHostToDevice);
+}
+
+int elba_fe_set_reads_device(elba_fe_ctx *ctx, const uint8_t *d_packed, uint64_t packed_bytes, const uint64_t *d_byte_off, const uint64_t *d_len,
+                             uint64_t nreads, int64_t read_id_offset)
+{
+    // device-to-device into the context's padded, aligned arena (the parse kernels read whole 32-bit words past a read's last byte)
+    return stage_reads(ctx, d_packed, packed_bytes, d_byte_off, d_len, nreads, read_id_offset, cudaMemcpyDeviceToDevice);
+}
+
+// -------------------------------------------------------------------------------------------------
+int elba_fe_count(elba_fe_ctx *ctx)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 1) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_count: no reads uploaded");
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int k = ctx->cfg.k, stride = ctx->cfg.stride; const u32 lower = ctx->cfg.lower, upper = ctx->cfg.upper;
+    cudaStream_t st = ctx->stream;
+    ReadsView rv = view(ctx);
+    CK(cudaEventRecord(ctx->ev[2], st));
+    ctx->kev_used = 0; ctx->pev_used = 0;
+
+    // counters: [0] R cursor, [1] sum of reliable counts, [2] distinct, [3] (u32) ncand
+    CK(ctx->ctr.ensure(64));
+    CK(cudaMemsetAsync(ctx->ctr.p, 0, 64, st));
+    u64 *d_ctr = ctx->ctr.as<u64>();
+    u32 *d_ncand = reinterpret_cast<u32*>(d_ctr + 3);
+
+    const u64 Ms = ctx->Ms;
+    u32 P = (u32)ctx->cfg.num_partitions;
+    if (P == 0)
+    {
+        // keep one partition's table (16 B/slot, 2 slots per instance) around L2 size: <= 2 Mi instances per partition
+        const u64 target = 2ull << 20;
+        P = (u32)std::min<u64>(1024, std::max<u64>(1, (Ms + target - 1) / target));
+    }
+    if (Ms == 0) P = 1;
+    ctx->sz.partitions = P;
+
+    u64 rel_cap = Ms / lower + 1;
+    if (rel_cap * 12 > (1ull << 30)) rel_cap = std::max<u64>(ctx->rel_cap, std::max<u64>(Ms / 8, (1ull << 30) / 12));
+    u64 R = 0, sumcnt = 0, D = 0;
+
+    for (int attempt = 0; attempt < 2; ++attempt)
+    {
+        CK(ctx->rel_key.ensure(sizeof(u64) * rel_cap)); CK(ctx->rel_cnt.ensure(sizeof(u32) * rel_cap));
+        ctx->rel_cap = rel_cap;
+        CK(cudaMemsetAsync(ctx->ctr.p, 0, 64, st));
+        if (P == 1)
+        {
+            u64 slots = next_pow2(std::max<u64>(2 * Ms, 1024));
+            if (slots > (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "single-partition mode needs <= 2^31 k-mer instances; use num_partitions = 0");
+            u64 cand_cap = Ms / lower + 1;
+            CK(ctx->table.ensure(sizeof(Slot) * slots)); CK(ctx->cand.ensure(sizeof(u32) * cand_cap));
+            ctx->sz.table_slots = slots;
+            k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), slots); CKL(); LAUNCHED(ctx);
+            EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
+            CK(cudaEventRecord(ep.a, st));
+            if (ctx->nchunks)
+            {
+                k_count_direct<<<grid_for(ctx, 8), 256, 0, st>>>(rv, k, stride, ctx->table.as<Slot>(), slots - 1, lower, upper,
+                    ctx->cand.as<u32>(), d_ncand, (u32)std::min<u64>(cand_cap, 0xFFFFFFFFull), d_ctr + 2);
+                CKL(); LAUNCHED(ctx);
+            }
+            CK(cudaEventRecord(ep.b, st));
+            k_collect_reliable<<<std::max(1u, nblk(cand_cap, 256)), 256, 0, st>>>(ctx->table.as<Slot>(), ctx->cand.as<u32>(), d_ncand, upper,
+                ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
+            CKL(); LAUNCHED(ctx);
+        }
+        else
+        {
+            // sweep 0: partition sizes
+            CK(ctx->phist.ensure(sizeof(u64) * (P + 1))); CK(ctx->pcursor.ensure(sizeof(u64) * (P + 1)));
+            CK(cudaMemsetAsync(ctx->phist.p, 0, sizeof(u64) * (P + 1), st));
+            EventPair &pp = next_pair(ctx->pev, ctx->pev_used);
+            CK(cudaEventRecord(pp.a, st));
+            k_part_hist<<<grid_for(ctx, 4), 256, sizeof(u32) * P, st>>>(rv, k, stride, P, ctx->phist.as<u64>()); CKL(); LAUNCHED(ctx);
+            std::vector<u64> hist(P + 1, 0), start(P + 1, 0);
+            CK(cudaMemcpyAsync(hist.data(), ctx->phist.p, sizeof(u64) * P, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            u64 maxcnt = 0;
+            for (u32 p = 0; p < P; ++p) { start[p + 1] = start[p] + hist[p]; maxcnt = std::max(maxcnt, hist[p]); }
+            if (start[P] != Ms) return fail(ctx, ELBA_FE_ERR_CUDA, "partition histogram does not sum to the k-mer count");
+            CK(cudaMemcpyAsync(ctx->pcursor.p, start.data(), sizeof(u64) * P, cudaMemcpyHostToDevice, st));
+            CK(ctx->partbuf.ensure(sizeof(u64) * std::max<u64>(Ms, 1)));
+            // sweep 1: scatter
+            size_t smem = sizeof(u64) * SCATTER_BLOCK * CHUNK + sizeof(u64) * P + sizeof(u32) * (2 * (size_t)P + 2);
+            k_part_scatter<<<grid_for(ctx, 2), SCATTER_BLOCK, smem, st>>>(rv, k, stride, P, ctx->pcursor.as<u64>(), ctx->partbuf.as<u64>());
+            CKL(); LAUNCHED(ctx);
+            CK(cudaEventRecord(pp.b, st));
+            // per-partition counting in one L2-sized table
+            u64 slots = next_pow2(std::max<u64>(2 * maxcnt, 1024));
+            if (slots > (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "partition too large; raise num_partitions");
+            u64 cand_cap = maxcnt / lower + 1;
+            CK(ctx->table.ensure(sizeof(Slot) * slots)); CK(ctx->cand.ensure(sizeof(u32) * cand_cap));
+            ctx->sz.table_slots = slots;
+            for (u32 p = 0; p < P; ++p)
+            {
+                if (hist[p] == 0) continue;
+                // size this partition's table by its own instance count (keeps small partitions cheap to clear)
+                u64 pslots = next_pow2(std::max<u64>(2 * hist[p], 1024));
+                k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), pslots); CKL(); LAUNCHED(ctx);
+                CK(cudaMemsetAsync(d_ncand, 0, sizeof(u32), st));
+                EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
+                CK(cudaEventRecord(ep.a, st));
+                k_count_array<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->partbuf.as<u64>() + start[p], hist[p], ctx->table.as<Slot>(), pslots - 1,
+                    lower, upper, ctx->cand.as<u32>(), d_ncand, (u32)std::min<u64>(cand_cap, 0xFFFFFFFFull), d_ctr + 2);
+                CKL(); LAUNCHED(ctx);
+                CK(cudaEventRecord(ep.b, st));
+                u64 pc = hist[p] / lower + 1;
+                k_collect_reliable<<<std::max(1u, nblk(pc, 256)), 256, 0, st>>>(ctx->table.as<Slot>(), ctx->cand.as<u32>(), d_ncand, upper,
+                    ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
+                CKL(); LAUNCHED(ctx);
+            }
+        }
+        u64 h[3];
+        CK(cudaMemcpyAsync(h, d_ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        R = h[0]; sumcnt = h[1]; D = h[2];
+        if (R <= rel_cap) break;
+        if (attempt == 1) return fail(ctx, ELBA_FE_ERR_CUDA, "reliable list overflow after resize");
+        rel_cap = R;       // exact; redo the count
+    }
+    if (R >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers on one context");
+    ctx->sz.distinct = D; ctx->sz.reliable = R; ctx->sz.nnzA_pre = sumcnt;
+
+    // column ids = rank by k-mer value: sort (key, count) by key
+    CK(ctx->rel_key_s.ensure(sizeof(u64) * std::max<u64>(R, 1))); CK(ctx->rel_cnt_s.ensure(sizeof(u32) * std::max<u64>(R, 1)));
+    int rc = sort_pairs(ctx, ctx->rel_key.as<u64>(), ctx->rel_key_s.as<u64>(), ctx->rel_cnt.as<u32>(), ctx->rel_cnt_s.as<u32>(), R, 64 - 2 * k, 64);
+    if (rc) return rc;
+    // lookup table k-mer -> column id
+    u64 lslots = next_pow2(std::max<u64>(2 * R, 1024));
+    CK(ctx->lut.ensure(sizeof(Slot) * lslots));
+    ctx->lut_mask = lslots - 1;
+    k_table_clear<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->lut.as<Slot>(), lslots); CKL(); LAUNCHED(ctx);
+    if (R) { k_lookup_build<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), (u32)R, ctx->lut.as<Slot>(), ctx->lut_mask); CKL(); LAUNCHED(ctx); }
+    CK(cudaEventRecord(ctx->ev[3], st));
+    ctx->phase = 2;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+int elba_fe_build_A(elba_fe_ctx *ctx)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 2) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_build_A: call elba_fe_count first");
+    CK(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->stream;
+    ReadsView rv = view(ctx);
+    const u64 R = ctx->sz.reliable, npre = ctx->sz.nnzA_pre; const u32 N = ctx->n;
+    CK(cudaEventRecord(ctx->ev[4], st));
+    ctx->lev_used = 0;
+    const int cb = bits_for(std::max<u64>(R, 2)), rb = bits_for(std::max<u64>(N, 2));
+    ctx->col_bits = cb; ctx->read_bits = rb;
+    u64 *d_ctr = ctx->ctr.as<u64>();
+    CK(cudaMemsetAsync(d_ctr, 0, 64, st));
+    const u64 cap = std::max<u64>(npre, 1);
+    CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); CK(ctx->seed_key2.ensure(8 * cap)); CK(ctx->seed_pos2.ensure(4 * cap));
+    // sweep 2: every instance of a reliable k-mer -> (read, column, pos)
+    {
+        EventPair &lp = next_pair(ctx->lev, ctx->lev_used);
+        CK(cudaEventRecord(lp.a, st));
+        if (ctx->nchunks && R)
+        {
+            k_emit_seeds<<<grid_for(ctx, 8), 256, 0, st>>>(rv, ctx->cfg.k, ctx->cfg.stride, ctx->lut.as<Slot>(), ctx->lut_mask,
+                ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, npre, cb);
+            CKL(); LAUNCHED(ctx);
+        }
+        CK(cudaEventRecord(lp.b, st));
+    }
+    u64 emitted = 0;
+    CK(cudaMemcpyAsync(&emitted, d_ctr, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (emitted != npre) { char b[160]; snprintf(b, sizeof b, "seed emission produced %llu triples, counting promised %llu", (unsigned long long)emitted, (unsigned long long)npre); return fail(ctx, ELBA_FE_ERR_CUDA, b); }
+
+    int rc;
+    // sort by (read, column); merge duplicates keeping the largest position
+    if ((rc = sort_pairs(ctx, ctx->seed_key.as<u64>(), ctx->seed_key2.as<u64>(), ctx->seed_pos.as<u32>(), ctx->seed_pos2.as<u32>(), npre, 0, cb + rb))) return rc;
+    CK(ctx->idx.ensure(8 * (npre + 1)));
+    k_mark_run_ends<<<nblk(npre + 1, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), npre, ctx->idx.as<u64>()); CKL(); LAUNCHED(ctx);
+    if ((rc = exclusive_scan_inplace(ctx, ctx->idx.as<u64>(), npre + 1))) return rc;
+    u64 nnzA = 0;
+    CK(cudaMemcpyAsync(&nnzA, ctx->idx.as<u64>() + npre, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->sz.nnzA = nnzA;
+    const u64 na = std::max<u64>(nnzA, 1);
+    CK(ctx->a_key.ensure(8 * na)); CK(ctx->a_pos.ensure(4 * na)); CK(ctx->a_col.ensure(4 * na)); CK(ctx->a_rowptr.ensure(8 * ((size_t)N + 2)));
+    CK(ctx->at_key.ensure(8 * na)); CK(ctx->at_key2.ensure(8 * na)); CK(ctx->at_pos2.ensure(4 * na)); CK(ctx->at_row.ensure(4 * na)); CK(ctx->at_pos.ensure(4 * na));
+    CK(ctx->at_colptr.ensure(8 * (R + 2))); CK(ctx->prod.ensure(8 * ((size_t)N + 1)));
+    if (npre) { k_dedupe_write<<<nblk(npre, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), ctx->seed_pos2.as<u32>(), ctx->idx.as<u64>(), npre, ctx->a_key.as<u64>(), ctx->a_pos.as<u32>()); CKL(); LAUNCHED(ctx); }
+    k_segment_ptr<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, N, cb, ctx->a_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
+    if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, cb, rb, ctx->a_col.as<u32>(), ctx->at_key.as<u64>()); CKL(); LAUNCHED(ctx); }
+    // transpose: the same entries sorted by (column, read)
+    if ((rc = sort_pairs(ctx, ctx->at_key.as<u64>(), ctx->at_key2.as<u64>(), ctx->a_pos.as<u32>(), ctx->at_pos.as<u32>(), nnzA, 0, cb + rb))) return rc;
+    k_segment_ptr<<<nblk(R + 1, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, R, rb, ctx->at_colptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
+    if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, rb, cb, ctx->at_row.as<u32>(), nullptr); CKL(); LAUNCHED(ctx); }
+    // products per row, F
+    CK(cudaMemsetAsync(d_ctr, 0, 64, st));
+    if (N) { k_row_products<<<nblk((u64)N * 32, 256), 256, 0, st>>>(ctx->a_rowptr.as<int64_t>(), ctx->a_col.as<u32>(), ctx->at_colptr.as<int64_t>(), N, ctx->prod.as<u64>(), d_ctr); CKL(); LAUNCHED(ctx); }
+    u64 F = 0;
+    CK(cudaMemcpyAsync(&F, d_ctr, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    ctx->sz.products = F;
+    ctx->phase = 3;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+int elba_fe_spgemm(elba_fe_ctx *ctx)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 3) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_spgemm: call elba_fe_build_A first");
+    CK(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->stream;
+    const u32 N = ctx->n; const u64 nnzA = ctx->sz.nnzA;
+    CK(cudaEventRecord(ctx->ev[6], st));
+    ctx->sev_used = 0;
+    CK(ctx->row_off.ensure(8 * ((size_t)N + 1))); CK(ctx->row_nnz.ensure(4 * ((size_t)N + 1)));
+    CK(ctx->small_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->big_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->ovf_rows.ensure(4 * ((size_t)N + 1)));
+    CK(ctx->bins.ensure(64)); CK(ctx->b_rowptr.ensure(8 * ((size_t)N + 2)));
+    u64 cap = std::max<u64>(ctx->b_cap_hint, std::max<u64>(nnzA + N, 1024));
+    u64 *d_ctr = ctx->ctr.as<u64>();
+    u64 h[4] = {0, 0, 0, 0};
+    for (int attempt = 0; attempt < 2; ++attempt)
+    {
+        CK(ctx->t_col.ensure(4 * cap)); CK(ctx->t_num.ensure(4 * cap)); CK(ctx->t_seeds.ensure(16 * cap));
+        CK(cudaMemsetAsync(d_ctr, 0, 64, st)); CK(cudaMemsetAsync(ctx->bins.p, 0, 64, st));
+        u32 *d_bins = ctx->bins.as<u32>(); u64 *d_maxprod = reinterpret_cast<u64*>(d_bins + 4);
+        SpgemmArgs A;
+        A.a_rowptr = ctx->a_rowptr.as<int64_t>(); A.a_col = ctx->a_col.as<u32>(); A.a_pos = ctx->a_pos.as<u32>();
+        A.at_colptr = ctx->at_colptr.as<int64_t>(); A.at_row = ctx->at_row.as<u32>(); A.at_pos = ctx->at_pos.as<u32>();
+        A.nrows = N; A.seed_count = ctx->cfg.seed_count;
+        A.t_col = ctx->t_col.as<u32>(); A.t_num = ctx->t_num.as<int32_t>(); A.t_seeds = ctx->t_seeds.as<u32>(); A.cap = cap;
+        A.counters = d_ctr; A.row_off = ctx->row_off.as<u64>(); A.row_nnz = ctx->row_nnz.as<u32>();
+        if (N)
+        {
+            k_spgemm_bin<<<nblk(N, 256), 256, 0, st>>>(ctx->prod.as<u64>(), N, ctx->small_rows.as<u32>(), ctx->big_rows.as<u32>(), d_bins, A.row_off, A.row_nnz, d_maxprod);
+            CKL(); LAUNCHED(ctx);
+            EventPair &sp = next_pair(ctx->sev, ctx->sev_used);
+            CK(cudaEventRecord(sp.a, st));
+            k_spgemm_warp<<<grid_for(ctx, 4), 32 * SPG_WARPS_PER_CTA, 0, st>>>(A, ctx->small_rows.as<u32>(), d_bins); CKL(); LAUNCHED(ctx);
+            k_spgemm_block<<<grid_for(ctx, 4), SPG_BLOCK_THREADS, 0, st>>>(A, ctx->big_rows.as<u32>(), d_bins + 1, ctx->ovf_rows.as<u32>()); CKL(); LAUNCHED(ctx);
+            CK(cudaEventRecord(sp.b, st));
+        }
+        u64 hb[6];
+        CK(cudaMemcpyAsync(h, d_ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hb, ctx->bins.p, sizeof hb, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        u64 novf = h[2];
+        if (novf)
+        {
+            // rows with more distinct columns than the shared-memory table holds: global-memory tables
+            u64 maxprod = hb[2];
+            u64 TS = next_pow2(2 * std::min<u64>(maxprod, (u64)N) + 2);
+            if (TS < 2 * SPG_BLOCK_TS) TS = 2 * SPG_BLOCK_TS;
+            u32 grid = (u32)std::min<u64>(novf, 64);
+            CK(ctx->gscratch.ensure(sizeof(u32) * 5 * TS * grid));
+            EventPair &sp = next_pair(ctx->sev, ctx->sev_used);
+            CK(cudaEventRecord(sp.a, st));
+            k_spgemm_global<<<grid, SPG_BLOCK_THREADS, 0, st>>>(A, ctx->ovf_rows.as<u32>(), (u32)novf, ctx->gscratch.as<u32>(), (u32)TS); CKL(); LAUNCHED(ctx);
+            CK(cudaEventRecord(sp.b, st));
+            CK(cudaMemcpyAsync(h, d_ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (h[0] <= cap) break;
+        if (attempt == 1) return fail(ctx, ELBA_FE_ERR_CUDA, "B storage overflow after resize");
+        cap = h[0];
+    }
+    ctx->b_cap_hint = cap;
+    const u64 nnzB = h[0];
+    ctx->sz.nnzB = nnzB; ctx->sz.nnzB_pre = h[1];
+    // CSR order
+    CK(ctx->b_col.ensure(4 * std::max<u64>(nnzB, 1))); CK(ctx->b_num.ensure(4 * std::max<u64>(nnzB, 1))); CK(ctx->b_seeds.ensure(16 * std::max<u64>(nnzB, 1)));
+    k_u32_to_u64<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->row_nnz.as<u32>(), N, reinterpret_cast<u64*>(ctx->b_rowptr.p)); CKL(); LAUNCHED(ctx);
+    int rc = exclusive_scan_inplace(ctx, reinterpret_cast<u64*>(ctx->b_rowptr.p), (u64)N + 1);
+    if (rc) return rc;
+    if (N)
+    {
+        k_gather_B<<<nblk((u64)N * 32, 256), 256, 0, st>>>(ctx->row_off.as<u64>(), ctx->row_nnz.as<u32>(), ctx->b_rowptr.as<int64_t>(), N,
+            ctx->t_col.as<u32>(), ctx->t_num.as<int32_t>(), ctx->t_seeds.as<u32>(), ctx->b_col.as<u32>(), ctx->b_num.as<int32_t>(), ctx->b_seeds.as<u32>());
+        CKL(); LAUNCHED(ctx);
+    }
+    CK(cudaEventRecord(ctx->ev[7], st));
+    ctx->phase = 4;
+    return 0;
+}
+
+int elba_fe_run(elba_fe_ctx *ctx)
+{
+    int rc;
+    if ((rc = elba_fe_count(ctx))) return rc;
+    if ((rc = elba_fe_build_A(ctx))) return rc;
+    if ((rc = elba_fe_spgemm(ctx))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int elba_fe_sizes(elba_fe_ctx *ctx, elba_fe_sizes_t *out)
+{
+    if (!ctx || !out) return ELBA_FE_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = ctx->sz;
+    return 0;
+}
+
+int elba_fe_timings(elba_fe_ctx *ctx, elba_fe_timings_t *out)
+{
+    if (!ctx || !out) return ELBA_FE_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms;
+    if (ctx->phase >= 2 && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->tm.count_ms = ms;
+    if (ctx->phase >= 3 && cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->tm.build_ms = ms;
+    if (ctx->phase >= 4 && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->tm.spgemm_ms = ms;
+    if (ctx->phase >= 2) { ctx->tm.count_kernel_ms = sum_pairs(ctx->kev, ctx->kev_used); ctx->tm.partition_ms = sum_pairs(ctx->pev, ctx->pev_used); }
+    if (ctx->phase >= 3) ctx->tm.lookup_ms = sum_pairs(ctx->lev, ctx->lev_used);
+    if (ctx->phase >= 4) ctx->tm.spgemm_kernel_ms = sum_pairs(ctx->sev, ctx->sev_used);
+    *out = ctx->tm;
+    return 0;
+}
+
+int elba_fe_reset_timings(elba_fe_ctx *ctx) { if (!ctx) return ELBA_FE_ERR_INVALID; std::memset(&ctx->tm, 0, sizeof ctx->tm); return 0; }
+
+// ---- results ---------------------------------------------------------------------------------------
+#define D2H(dst, src, bytes) do { if ((bytes) && (dst)) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream)); } while (0)
+
+int elba_fe_get_kmers(elba_fe_ctx *ctx, uint64_t *kmer, uint32_t *count)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 2) return fail(ctx, ELBA_FE_ERR_STATE, "no counts yet");
+    u64 R = ctx->sz.reliable;
+    D2H(kmer, ctx->rel_key_s.p, 8 * R); D2H(count, ctx->rel_cnt_s.p, 4 * R);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int elba_fe_get_A(elba_fe_ctx *ctx, int64_t *rowptr, uint32_t *col, uint32_t *pos)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 3) return fail(ctx, ELBA_FE_ERR_STATE, "A not built");
+    D2H(rowptr, ctx->a_rowptr.p, 8 * ((size_t)ctx->n + 1)); D2H(col, ctx->a_col.p, 4 * ctx->sz.nnzA); D2H(pos, ctx->a_pos.p, 4 * ctx->sz.nnzA);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int elba_fe_get_AT(elba_fe_ctx *ctx, int64_t *colptr, uint32_t *row, uint32_t *pos)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 3) return fail(ctx, ELBA_FE_ERR_STATE, "A not built");
+    D2H(colptr, ctx->at_colptr.p, 8 * (ctx->sz.reliable + 1)); D2H(row, ctx->at_row.p, 4 * ctx->sz.nnzA); D2H(pos, ctx->at_pos.p, 4 * ctx->sz.nnzA);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int elba_fe_get_B(elba_fe_ctx *ctx, int64_t *rowptr, uint32_t *col, int32_t *numshared, uint32_t *seeds)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 4) return fail(ctx, ELBA_FE_ERR_STATE, "B not built");
+    cudaEvent_t a = ctx->ev[0], b = ctx->ev[1];
+    CK(cudaEventRecord(a, ctx->stream));
+    D2H(rowptr, ctx->b_rowptr.p, 8 * ((size_t)ctx->n + 1)); D2H(col, ctx->b_col.p, 4 * ctx->sz.nnzB);
+    D2H(numshared, ctx->b_num.p, 4 * ctx->sz.nnzB); D2H(seeds, ctx->b_seeds.p, 16 * ctx->sz.nnzB);
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, a, b); ctx->tm.download_ms = ms;
+    return 0;
+}
+
+int elba_fe_get_B_triples(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t *numshared, uint32_t *seeds)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 4) return fail(ctx, ELBA_FE_ERR_STATE, "B not built");
+    u64 nnz = ctx->sz.nnzB; u32 N = ctx->n;
+    std::vector<int64_t> rp((size_t)N + 1); std::vector<u32> c32(nnz);
+    int rc = elba_fe_get_B(ctx, rp.data(), c32.data(), numshared, seeds);
+    if (rc) return rc;
+    // global ids: rows by the caller's read offset; columns are global already on one GPU (= local + offset)
+    for (u32 r = 0; r < N; ++r) for (int64_t p = rp[r]; p < rp[r + 1]; ++p) { if (row) row[p] = (int64_t)r + ctx->read_id_offset; if (col) col[p] = (int64_t)c32[p] + ctx->read_id_offset; }
+    return 0;
+}
+
+int elba_fe_device_B(elba_fe_ctx *ctx, const int64_t **rowptr, const uint32_t **col, const int32_t **numshared, const uint32_t **seeds)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 4) return fail(ctx, ELBA_FE_ERR_STATE, "B not built");
+    if (rowptr) *rowptr = ctx->b_rowptr.as<int64_t>(); if (col) *col = ctx->b_col.as<u32>();
+    if (numshared) *numshared = ctx->b_num.as<int32_t>(); if (seeds) *seeds = ctx->b_seeds.as<u32>();
+    return 0;
+}
+
+int elba_fe_device_A(elba_fe_ctx *ctx, const int64_t **rowptr, const uint32_t **col, const uint32_t **pos)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 3) return fail(ctx, ELBA_FE_ERR_STATE, "A not built");
+    if (rowptr) *rowptr = ctx->a_rowptr.as<int64_t>(); if (col) *col = ctx->a_col.as<u32>(); if (pos) *pos = ctx->a_pos.as<u32>();
+    return 0;
+}
+
+// ---- sketches ---------------------------------------------------------------------------------------
+int elba_fe_hll(elba_fe_ctx *ctx, uint8_t *registers, double *estimate)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 1) return fail(ctx, ELBA_FE_ERR_STATE, "no reads uploaded");
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(ctx->hll_regs.ensure(4 * ELBA_FE_HLL_REGISTERS));
+    CK(cudaMemsetAsync(ctx->hll_regs.p, 0, 4 * ELBA_FE_HLL_REGISTERS, ctx->stream));
+    if (ctx->nchunks) { k_hll<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(view(ctx), ctx->cfg.k, ctx->cfg.stride, ctx->hll_regs.as<u32>()); CKL(); LAUNCHED(ctx); }
+    std::vector<u32> regs(ELBA_FE_HLL_REGISTERS);
+    CK(cudaMemcpyAsync(regs.data(), ctx->hll_regs.p, 4 * ELBA_FE_HLL_REGISTERS, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // estimate(): src/HyperLogLog.cpp:52-76, same double arithmetic in the same order
+    const double size = 4096.0;
+    const double alpha_mm = (0.7213 / (1.0 + (1.079 / size))) * size * size;
+    double sum = 0.0; uint32_t zeros = 0;
+    for (int i = 0; i < ELBA_FE_HLL_REGISTERS; ++i) { sum += 1.0 / (double)(1 << regs[i]); zeros += (regs[i] == 0); if (registers) registers[i] = (uint8_t)regs[i]; }
+    double est = alpha_mm / sum;
+    if (est <= 2.5 * size && zeros) est = size * std::log(size / zeros);
+    if (estimate) *estimate = est;
+    return 0;
+}
+
+int elba_fe_bloom(elba_fe_ctx *ctx, int64_t entries, double error, int64_t *bits_out, int32_t *hashes_out, int64_t *bytes_out, uint8_t *bf)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (entries < 1 || !(error > 0 && error < 1)) return fail(ctx, ELBA_FE_ERR_INVALID, "Bloom needs entries >= 1 and 0 < error < 1 (src/Bloom.cpp:8)");
+    // sizing: src/Bloom.cpp:10-22
+    double bpe = -(std::log(error) / 0.480453013918201);
+    int64_t bits = (int64_t)((double)entries * bpe);
+    int64_t bytes = (bits / 8) + !!(bits % 8);
+    int hashes = (int)std::ceil(0.693147180559945 * bpe);
+    if (bits_out) *bits_out = bits; if (hashes_out) *hashes_out = hashes; if (bytes_out) *bytes_out = bytes;
+    if (!bf) return 0;
+    if (ctx->phase < 1) return fail(ctx, ELBA_FE_ERR_STATE, "no reads uploaded");
+    if (bits < 1) return fail(ctx, ELBA_FE_ERR_INVALID, "Bloom filter has no bits");
+    CK(cudaSetDevice(ctx->cfg.device));
+    size_t words = (size_t)(bytes + 3) / 4;
+    CK(ctx->bloom.ensure(4 * words));
+    CK(cudaMemsetAsync(ctx->bloom.p, 0, 4 * words, ctx->stream));
+    if (ctx->nchunks) { k_bloom_add<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(view(ctx), ctx->cfg.k, ctx->cfg.stride, ctx->bloom.as<u32>(), (u64)bits, hashes); CKL(); LAUNCHED(ctx); }
+    CK(cudaMemcpyAsync(bf, ctx->bloom.p, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int elba_fe_get_kmer_stream(elba_fe_ctx *ctx, uint64_t *out)
+{
+    if (!ctx || !out) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 1) return fail(ctx, ELBA_FE_ERR_STATE, "no reads uploaded");
+    CK(cudaSetDevice(ctx->cfg.device));
+    DevBuf tmp;
+    CK(tmp.ensure(8 * std::max<u64>(ctx->M, 1)));
+    if (ctx->nchunks) { k_kmer_stream<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(view(ctx), ctx->cfg.k, tmp.as<u64>()); LAUNCHED(ctx); }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp.p, 8 * ctx->M, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    tmp.release();
+    if (e != cudaSuccess) return fail(ctx, ELBA_FE_ERR_CUDA, cudaGetErrorString(e));
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,173 @@
+/*
+ * elba_fe.h — C ABI of the B200-native ELBA overlap-detection front end.
+ *
+ * Drop-in boundary for ONE path of PASSIONLab/ELBA (reference commit 4b75895a):
+ *
+ *     get_kmer_count_map_keys  ->  get_kmer_count_map_values  ->  create_kmer_matrix
+ *       ->  Transpose  ->  create_seed_matrix          (reference src/main.cpp:191-282)
+ *
+ * The reference has no FFI layer; its interface for this path is five C++ free
+ * functions (include/KmerOps.hpp:24-31, include/SharedSeeds.hpp:98-99).  The
+ * C++ shim include/elba_fe_shim.hpp keeps those five signatures and implements
+ * them on top of the symbols below, so src/main.cpp compiles unchanged (see
+ * INTEGRATION.md).  Everything here is plain C: pointers and sizes, no C++/torch
+ * types.  Every function returns 0 on success or a negative elba_fe_status;
+ * elba_fe_last_error() gives the message.  There is NO CPU fallback: without a
+ * CUDA device (sm_100a) elba_fe_create fails with ELBA_FE_ERR_NO_DEVICE.
+ *
+ * Results are bit-exact against the reference on the same inputs and
+ * parameters for everything the reference's own code defines (k-mer stream,
+ * reliable k-mer set and counts, A after max-position dedupe, pattern of B,
+ * shared-seed counts, prune); which two seed pairs a nonzero retains is decided
+ * inside CombBLAS in the reference (unpinned external dependency) and follows
+ * the documented canonical rule here (DESIGN.md §"Seed rule").
+ *
+ * Threading: a context is not thread-safe; all work is enqueued on the
+ * context's stream.  Multi-GPU: one context per GPU/process; see
+ * elba_fe_comm_* (the calls are collective across the participating contexts).
+ */
+#ifndef ELBA_FE_H
+#define ELBA_FE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELBA_FE_VERSION 1
+#define ELBA_FE_MAX_KMER_SIZE 32      /* README.md:55-57 MAX_KMER_SIZE; one 64-bit word, Kmer<1> (include/Kmer.hpp:95-97) */
+#define ELBA_FE_HLL_REGISTERS 4096    /* HyperLogLog(bits=12), include/HyperLogLog.hpp:17 */
+
+typedef enum {
+    ELBA_FE_OK = 0,
+    ELBA_FE_ERR_INVALID = -1,      /* bad argument / parameter out of contract */
+    ELBA_FE_ERR_NO_DEVICE = -2,    /* no usable CUDA device: there is no CPU fallback */
+    ELBA_FE_ERR_CUDA = -3,         /* a CUDA call failed */
+    ELBA_FE_ERR_OOM = -4,          /* device allocation failed */
+    ELBA_FE_ERR_STATE = -5,        /* call sequence violated (e.g. spgemm before build_A) */
+    ELBA_FE_ERR_COMM = -6          /* NCCL / multi-GPU failure */
+} elba_fe_status;
+
+/*
+ * Run-time parameters.  In the reference k / LOWER / UPPER are compile-time
+ * macros (Makefile:1-6, include/compiletime.h:7-22), stride is hard-wired to 1
+ * (include/KmerOps.hpp:106-136) and the seed count to 2 (include/SharedSeeds.hpp:94).
+ */
+typedef struct {
+    int32_t k;              /* KMER_SIZE, 3..32; parity pinned for odd k <= 31 */
+    int32_t stride;         /* visit window starts p with p % stride == 0; reference == 1 */
+    int32_t seed_count;     /* seed pairs kept per read pair, 1..2; reference == 2 */
+    int32_t lower;          /* LOWER_KMER_FREQ, >= 2 (with 1 the reference depends on Bloom false positives) */
+    int32_t upper;          /* UPPER_KMER_FREQ, lower..65535 (include/compiletime.h:21) */
+    int32_t device;         /* CUDA device ordinal */
+    int32_t num_partitions; /* 0 = choose (count table of one partition kept L2-sized); 1 = direct, no partition pass */
+    int32_t flags;          /* ELBA_FE_FLAG_* */
+} elba_fe_config;
+
+#define ELBA_FE_FLAG_UPPER_TRIANGLE 1   /* keep only B(i,j), i <= j ... reserved, not implemented: rejected */
+
+typedef struct elba_fe_ctx elba_fe_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+void        elba_fe_default_config(elba_fe_config *cfg);     /* k=31 L=15 U=35 (Makefile:1-3), stride 1, seeds 2 */
+int         elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out);
+int         elba_fe_destroy(elba_fe_ctx *ctx);
+const char *elba_fe_last_error(const elba_fe_ctx *ctx);      /* ctx may be NULL: error of the last failed create */
+int         elba_fe_version(void);
+/* Use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int         elba_fe_set_stream(elba_fe_ctx *ctx, void *cuda_stream);
+
+/* ---- input: the reference's DnaBuffer (include/DnaBuffer.hpp, src/DnaBuffer.cpp:5-29) ---------
+ * packed:   the arena, 4 bases/byte, base i of a read at bits 6-2*(i%4) of its byte i/4,
+ *           A=0 C=1 G=2 T=3 (N was already folded to A by DnaSeq::compress, src/DnaSeq.cpp:7-29)
+ * byte_off: offset of read i's first byte in the arena (DnaBuffer::getbufoffset(i) - getbufoffset(0))
+ * len:      bases in read i (DnaSeq::size())
+ * read_id_offset: global id of local read 0 (the MPI_Exscan of src/KmerOps.cpp:215-216)
+ * _host copies from host memory (pinned or pageable) on the context's stream;
+ * _device adopts pointers already resident in HBM (no copy; caller keeps them alive).
+ */
+int elba_fe_upload_reads(elba_fe_ctx *ctx, const uint8_t *packed, uint64_t packed_bytes,
+                         const uint64_t *byte_off, const uint64_t *len, uint64_t nreads, int64_t read_id_offset);
+int elba_fe_set_reads_device(elba_fe_ctx *ctx, const uint8_t *d_packed, uint64_t packed_bytes,
+                             const uint64_t *d_byte_off, const uint64_t *d_len, uint64_t nreads, int64_t read_id_offset);
+
+/* ---- the path ------------------------------------------------------------------------------- */
+/* get_kmer_count_map_keys + get_kmer_count_map_values (src/KmerOps.cpp:18-350):
+ * reliable k-mers {x : lower <= count(x) <= upper}, exact instance counts, column id = rank of x. */
+int elba_fe_count(elba_fe_ctx *ctx);
+/* create_kmer_matrix + Transpose (src/KmerOps.cpp:361-401, src/main.cpp:272-273):
+ * A (reads x reliable k-mers, value = position, duplicates keep the largest position) in device CSR and CSC. */
+int elba_fe_build_A(elba_fe_ctx *ctx);
+/* create_seed_matrix (src/SharedSeeds.cpp:4-10): B = A (x) A^T under SharedSeeds::Semiring, pruned numshared <= 1. */
+int elba_fe_spgemm(elba_fe_ctx *ctx);
+/* all three, then a stream synchronize */
+int elba_fe_run(elba_fe_ctx *ctx);
+int elba_fe_synchronize(elba_fe_ctx *ctx);
+
+/* ---- sizes (valid after the phase that produces them; synchronizes the stream) ----------------------- */
+typedef struct {
+    uint64_t nreads;        /* N (local) */
+    uint64_t num_kmers;     /* M: k-mer instances visited */
+    uint64_t distinct;      /* D: distinct canonical k-mers */
+    uint64_t reliable;      /* R */
+    uint64_t nnzA_pre;      /* instances of reliable k-mers (triples before dedupe) */
+    uint64_t nnzA;          /* after (read,column) dedupe */
+    uint64_t products;      /* F = sum over columns of count^2 (semiring multiplies) */
+    uint64_t nnzB_pre;      /* nonzeros of A*A^T before Prune */
+    uint64_t nnzB;          /* after Prune(numshared <= 1) */
+    uint64_t partitions;    /* k-mer partitions actually used */
+    uint64_t table_slots;   /* slots of one count table */
+    uint64_t reserved[5];
+} elba_fe_sizes_t;
+int elba_fe_sizes(elba_fe_ctx *ctx, elba_fe_sizes_t *out);
+
+/* ---- results to host (caller allocates from elba_fe_sizes) ------------------------------------------- */
+/* reliable k-mers ascending by 64-bit value (== column id order) and their counts */
+int elba_fe_get_kmers(elba_fe_ctx *ctx, uint64_t *kmer /*R*/, uint32_t *count /*R*/);
+/* A in CSR: rowptr[N+1], col[nnzA] ascending within a row, pos[nnzA] */
+int elba_fe_get_A(elba_fe_ctx *ctx, int64_t *rowptr, uint32_t *col, uint32_t *pos);
+/* A^T (= A in CSC): colptr[R+1], row[nnzA] (local read ids ascending within a column), pos[nnzA] */
+int elba_fe_get_AT(elba_fe_ctx *ctx, int64_t *colptr, uint32_t *row, uint32_t *pos);
+/* B in CSR: rowptr[N+1], col[nnzB] ascending, numshared[nnzB], seeds[nnzB*4] = {s0.q, s0.t, s1.q, s1.t}
+ * (SharedSeeds::seeds[2] + numshared, include/SharedSeeds.hpp:94-95; q = position in the row read, t = in the column read) */
+int elba_fe_get_B(elba_fe_ctx *ctx, int64_t *rowptr, uint32_t *col, int32_t *numshared, uint32_t *seeds);
+/* the same as (row, col, ...) triples with GLOBAL ids, the layout the SpParMat triple constructor takes */
+int elba_fe_get_B_triples(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t *numshared, uint32_t *seeds);
+
+/* device pointers of the same arrays (zero-copy hand-off to a device consumer); any may be NULL */
+int elba_fe_device_B(elba_fe_ctx *ctx, const int64_t **rowptr, const uint32_t **col, const int32_t **numshared, const uint32_t **seeds);
+int elba_fe_device_A(elba_fe_ctx *ctx, const int64_t **rowptr, const uint32_t **col, const uint32_t **pos);
+
+/* ---- the reference's sizing sketches, bit-exact (not needed for the result when lower >= 2) ----------- */
+/* HyperLogLog over the canonical k-mers of the uploaded reads exactly as KmerEstimateHandler drives it
+ * (include/KmerOps.hpp:58-69, src/HyperLogLog.cpp:40-76): registers[4096] and estimate(). */
+int elba_fe_hll(elba_fe_ctx *ctx, uint8_t *registers /*4096 or NULL*/, double *estimate);
+/* Bloom sized as Bloom(entries, error) (src/Bloom.cpp:6-27) with every canonical k-mer of the uploaded reads
+ * added (src/Bloom.cpp:44-73).  bits/hashes/bytes are outputs; bf (bytes long) may be NULL to size only. */
+int elba_fe_bloom(elba_fe_ctx *ctx, int64_t entries, double error, int64_t *bits, int32_t *hashes, int64_t *bytes, uint8_t *bf);
+/* the canonical k-mer stream itself (ForeachKmer, include/KmerOps.hpp:106-136): out[M], read order then position order */
+int elba_fe_get_kmer_stream(elba_fe_ctx *ctx, uint64_t *out /*M*/);
+
+/* ---- measurement ---------------------------------------------------------------------------------------- */
+typedef struct {
+    float upload_ms;        /* H2D of the reads (upload_reads) */
+    float count_ms;         /* elba_fe_count, device time */
+    float build_ms;         /* elba_fe_build_A */
+    float spgemm_ms;        /* elba_fe_spgemm */
+    float download_ms;      /* last get_* */
+    float count_kernel_ms;  /* the dominant counting kernel(s) only (sum over partitions) */
+    float spgemm_kernel_ms; /* the numeric SpGEMM kernel(s) only */
+    uint32_t kernel_launches; /* kernels of this library launched since create/reset */
+    float partition_ms;     /* histogram + scatter kernels */
+    float lookup_ms;        /* second sweep (seed emission) kernel */
+    float reserved[6];
+} elba_fe_timings_t;
+int elba_fe_timings(elba_fe_ctx *ctx, elba_fe_timings_t *out);
+int elba_fe_reset_timings(elba_fe_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELBA_FE_H */

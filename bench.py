@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the ELBA overlap-detection front end (k-mer count -> A -> A*A^T SpGEMM) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic reads:
+  value  reads/s with the packed reads already resident in HBM when the timed region starts
+  e2e    reads/s through the C ABI with HOST (pinned) buffers: H2D of the reads and D2H of B inside the timed region
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the roofline accounting.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# BASELINE.json configs: 2 = example_medium (fixture), 3 = E. coli 30X CLR, 4 = C. elegans 40X HiFi, 5 = human 10X CLR
+WORKLOADS = {
+    "example_medium_k17": dict(fixture="example_medium", k=17, lower=2, upper=8, desc="BASELINE configs[1]: example_medium/reads.fa k=17 L=2 U=8"),
+    "ecoli30x_clr": dict(shape="ecoli30x_clr", desc="BASELINE configs[2]: synthetic E. coli 30X CLR, 16,890 reads, k=17 U=8"),
+    "celegans40x_hifi": dict(shape="celegans40x_hifi", desc="BASELINE configs[3]: synthetic C. elegans 40X HiFi shape, 275,699 reads, k=31 U=4"),
+    "human10x_clr": dict(shape="human10x_clr", desc="BASELINE configs[4]: synthetic human 10X CLR shape, 4,421,593 reads, k=17 U=4"),
+}
+DEFAULT_WORKLOAD = "celegans40x_hifi"     # the config BASELINE.json quotes at 1/2/4/8 GPUs; fits one B200
+METRIC = "reads/s through k-mer count + A*A^T SpGEMM"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def load_workload(name: str, rank: int, world: int, device, scale: float = 1.0):
+    """Returns (buf uint8, off int64, lens int64) torch tensors on `device` for THIS rank's contiguous block of reads
+    plus (k, lower, upper, total_reads, read_id_offset)."""
+    from elba_b200.dnabuffer import DnaBuffer
+    from elba_b200 import synth
+    w = WORKLOADS[name]
+    if "fixture" in w:
+        dna = DnaBuffer.load(os.path.join(ROOT, "tests", "golden", w["fixture"] + ".npz"))
+        k, lo, up = w["k"], w["lower"], w["upper"]
+        total = dna.size()
+        r0, r1 = total * rank // world, total * (rank + 1) // world
+        d = dna.slice(r0, r1)
+        return (torch.from_numpy(d.buf).to(device), torch.from_numpy(d.offsets.astype(np.int64)).to(device),
+                torch.from_numpy(d.lengths.astype(np.int64)).to(device), k, lo, up, total, r0)
+    s = synth.SHAPES[w["shape"]]
+    genome, reads = int(s["genome"] * scale), int(s["reads"] * scale)
+    r0, r1 = reads * rank // world, reads * (rank + 1) // world
+    # every rank draws from the SAME genome (seed) and its own block of reads
+    g = synth.random_genome(genome, 313, device)
+    bufs, offs, lens_all, base = [], [], [], 0
+    batch = 16384
+    for b0 in range(r0, r1, batch):
+        nb = min(batch, r1 - b0)
+        codes, lens = synth.sample_reads(g, nb, s["mean"], s["sd"], s["err"], 313 * 1000003 + b0 + 1)
+        buf, off, lens = synth.pack_reads(codes, lens)
+        del codes
+        bufs.append(buf); offs.append(off + base); lens_all.append(lens)
+        base += buf.numel()
+    del g
+    return torch.cat(bufs), torch.cat(offs), torch.cat(lens_all), s["k"], s["lower"], s["upper"], reads, r0
+
+
+def cpu_reference_sample(name: str):
+    """A bounded sample of the same workload shape for the CPU leg: (DnaBuffer, k, lower, upper, description)."""
+    from elba_b200.dnabuffer import DnaBuffer
+    from elba_b200 import synth
+    w = WORKLOADS[name]
+    if "fixture" in w:
+        dna = DnaBuffer.load(os.path.join(ROOT, "tests", "golden", w["fixture"] + ".npz"))
+        return dna, w["k"], w["lower"], w["upper"], f"all {dna.size()} reads of {w['fixture']}"
+    s = synth.SHAPES[w["shape"]]
+    target_bases = 40_000_000
+    scale = min(1.0, target_bases / (s["reads"] * s["mean"]))
+    genome, reads = max(int(s["genome"] * scale), 100_000), max(int(s["reads"] * scale), 64)
+    dna = synth.make_dnabuffer(genome, reads, s["mean"], s["sd"], s["err"], seed=313)
+    return dna, s["k"], s["lower"], s["upper"], f"{reads} reads over a {genome} bp genome: the {w['shape']} shape (same coverage, read length, error rate) scaled by {scale:.4g}"
+
+
+def run_cpu_reference(dna, k, lo, up, ranks: int):
+    """One pass of the reference's own CPU implementation (oracle/_ref when built for this (k,L,U), else the oracle port)."""
+    from oracle import oracle as O
+    t = time.perf_counter()
+    if O.ref_available(k, lo, up):
+        r = O.ref_run(dna, k, lo, up, nranks=ranks, fetch=False)
+        kind, cores, secs = "reference", ranks, r.secs
+    else:
+        r = O.run(dna, k, lo, up, threads=ranks)
+        kind, cores, secs = "port", 1, r.secs
+    dt = time.perf_counter() - t
+    return dna.size() / dt, kind, cores, {a: float(b) for a, b in secs.items()}
+
+
+def square_ranks():
+    cores = os.cpu_count() or 1
+    q = int(np.floor(np.sqrt(min(cores, 64))))
+    return max(1, q * q), cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--partitions", type=int, default=0)
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink a synthetic workload (debug only; the JSON says so)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dna, k, lo, up, sample = cpu_reference_sample(args.workload)
+        ranks, cores = square_ranks()
+        times = []
+        for i in range(args.warmup + args.steps):
+            rps, kind, used, secs = run_cpu_reference(dna, k, lo, up, ranks)
+            if i >= args.warmup:
+                times.append(dna.size() / rps)
+        ms = 1000.0 * float(np.mean(times)) if times else float("nan")
+        val = dna.size() / (ms / 1000.0)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": args.workload, "desc": w["desc"], "k": k, "lower": lo, "upper": up},
+                "cpu_baseline": {"value": val, "unit": "reads/s", "cores": used, "kind": kind, "host_cores": cores,
+                                 "sample": sample + "; reference KmerOps.cpp/SharedSeeds.cpp compiled unmodified, MPI ranks emulated as threads, CombBLAS restated (oracle/stubs)",
+                                 "stage_secs": secs},
+                "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ our arm (B200)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from elba_b200 import frontend
+
+    buf, off, lens, k, lo, up, total_reads, r0 = load_workload(args.workload, rank, world, dev, args.scale)
+    nreads = lens.numel()
+    M = int((lens - k + 1).clamp(min=0).sum().item())
+    # host (pinned) copies for the end-to-end leg
+    hbuf, hoff, hlen = (t.cpu().pin_memory() for t in (buf, off, lens))
+    torch.cuda.synchronize()
+
+    ctx = frontend.Context(frontend.Params(k=k, lower=lo, upper=up, device=local, num_partitions=args.partitions))
+    # run the library on torch's current stream so that torch CUDA events bracket its kernels
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.set_reads_device(buf.data_ptr(), buf.numel(), off.data_ptr(), lens.data_ptr(), nreads, r0)
+        ctx.run()
+
+    out_host = {}
+
+    def step_e2e():
+        ctx.upload_raw(hbuf.data_ptr(), hbuf.numel(), hoff.data_ptr(), hlen.data_ptr(), nreads, r0)
+        ctx.run()
+        s = ctx.sizes()
+        n = s["nnzB"]
+        if out_host.get("cap", -1) < n:
+            out_host["rp"] = torch.empty(nreads + 1, dtype=torch.int64).pin_memory()
+            out_host["col"] = torch.empty(max(n, 1), dtype=torch.int32).pin_memory()
+            out_host["num"] = torch.empty(max(n, 1), dtype=torch.int32).pin_memory()
+            out_host["seeds"] = torch.empty(max(n, 1) * 4, dtype=torch.int32).pin_memory()
+            out_host["cap"] = n
+        import ctypes as C
+        ctx._ck(ctx.L.elba_fe_get_B(ctx.h, C.c_void_p(out_host["rp"].data_ptr()), C.c_void_p(out_host["col"].data_ptr()),
+                                    C.c_void_p(out_host["num"].data_ptr()), C.c_void_p(out_host["seeds"].data_ptr())))
+        return s
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.reset_timings()
+        acc = {}
+        e0.record()
+        for _ in range(steps):
+            fn()
+            for a, b in ctx.timings().items():
+                acc[a] = acc.get(a, 0.0) + b
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)   # device time, CUDA events on the launching stream
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), {a: b / steps for a, b in acc.items()}
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_res, tm = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop()
+    sizes = ctx.sizes()
+    ms_e2e, tm_e2e = timed(step_e2e, max(2, args.steps // 2), 1)
+    sizes_e2e = ctx.sizes()
+
+    # whole-job totals
+    tot = torch.tensor([nreads, M, sizes["nnzA"], sizes["products"], sizes["nnzB_pre"], sizes["nnzB"], sizes["reliable"]], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tot)
+    tot_reads, tot_M, tot_nnzA, tot_F, tot_nnzB_pre, tot_nnzB, tot_R = [float(x) for x in tot.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        # counting = everything the reference does in get_kmer_count_map_keys/values: our count phase + the seed-emission sweep
+        t_count = (tm["count_ms"] + tm["lookup_ms"]) / 1000.0
+        bytes_count = 28.5 * M                      # 8 + 20 + 2*0.25 bytes per k-mer instance
+        ach = bytes_count / t_count / 1e9 if t_count > 0 else 0.0
+        t_sp = tm["spgemm_kernel_ms"] / 1000.0
+        bytes_sp = 8.0 * sizes["products"] + 8.0 * sizes["nnzA"] + 28.0 * sizes["nnzB_pre"]
+        ach_sp = bytes_sp / t_sp / 1e9 if t_sp > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": tot_reads / (ms_res / 1000.0), "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic" if "shape" in w else "reference fixture",
+            "config": {"workload": args.workload, "desc": w["desc"] + (f" (scaled x{args.scale})" if args.scale != 1.0 else ""), "k": k, "lower": lo, "upper": up,
+                       "reads": int(tot_reads), "kmer_instances": int(tot_M), "reliable_kmers": int(tot_R), "nnzA": int(tot_nnzA), "products": int(tot_F),
+                       "nnzB": int(tot_nnzB), "partitions": sizes["partitions"], "l2_policy": "inputs larger than L2 / every step rewrites count tables and partition buffers",
+                       "timing": "CUDA events on the launching stream around K steps, max over ranks; per-phase numbers from the library's own CUDA events on the same stream"},
+            "phases_ms": {a: round(b, 4) for a, b in tm.items() if a.endswith("_ms")},
+            "roofline": {"bound": "hbm", "kernel": "counting phase (k_part_hist + k_part_scatter + k_count_array + k_emit_seeds)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": bytes_count, "seconds": t_count},
+            "roofline_spgemm": {"bound": "hbm", "kernel": "k_spgemm_warp + k_spgemm_block", "achieved": ach_sp, "peak": peak, "unit": "GB/s", "frac": ach_sp / peak,
+                                "algorithmic_bytes": bytes_sp, "seconds": t_sp},
+            "e2e": {"value": tot_reads / (ms_e2e / 1000.0), "unit": "reads/s", "h2d_bytes_per_step": int(hbuf.numel() + 16 * nreads),
+                    "d2h_bytes_per_step": int(8 * (nreads + 1) + 24 * sizes_e2e["nnzB"]), "ms_per_step": ms_e2e},
+            "gpu_launches": int(tm["kernel_launches"]), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            dna, ck, cl, cu, sample = cpu_reference_sample(args.workload)
+            ranks, cores = square_ranks()
+            rps, kind, used, secs = run_cpu_reference(dna, ck, cl, cu, ranks)
+            line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": used, "kind": kind, "host_cores": cores,
+                                    "sample": sample + "; reference KmerOps.cpp/SharedSeeds.cpp compiled unmodified, MPI ranks emulated as threads, CombBLAS restated (oracle/stubs)",
+                                    "stage_secs": secs}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -51,8 +51,8 @@ struct elba_fe_ctx
     DevBuf packed, off, len64, len32, chunk_start, kmer_start, nks_start;
     u32 n = 0; u64 packed_bytes = 0, nchunks = 0, M = 0, Ms = 0; int64_t read_id_offset = 0;
     // counting
-    DevBuf table, cand, ctr, partbuf, phist, pcursor, rel_key, rel_cnt, rel_key_s, rel_cnt_s, lut;
-    u64 lut_mask = 0; u64 rel_cap = 0;
+    DevBuf table, cand, ctr, partbuf, phist, pcursor, rel_key, rel_cnt, rel_key_s, rel_cnt_s, lut, filter;
+    u64 lut_mask = 0; u64 rel_cap = 0; u32 filter_mask = 0;
     // A
     DevBuf seed_key, seed_pos, seed_key2, seed_pos2, idx, a_key, a_rowptr, a_col, a_pos, at_key, at_key2, at_pos2, at_colptr, at_row, at_pos, prod;
     int col_bits = 1, read_bits = 1;
@@ -194,6 +194,8 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, ELBA_FE_ERR_CUDA, "cudaStreamCreate failed"); }
     ctx->own_stream = true;
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    // random 16-byte table probes: do not let L2 pull whole 128-byte lines from HBM for them (profiles/r1_count_v0.md)
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     // opt in to the large dynamic shared memory of the scatter kernel
     cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     *out = ctx;
@@ -206,7 +208,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = { &ctx->packed, &ctx->off, &ctx->len64, &ctx->len32, &ctx->chunk_start, &ctx->kmer_start, &ctx->nks_start,
-        &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut,
+        &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut, &ctx->filter,
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
         &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->bins, &ctx->small_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
@@ -281,21 +283,24 @@ int elba_fe_count(elba_fe_ctx *ctx)
     cudaStream_t st = ctx->stream;
     ReadsView rv = view(ctx);
     CK(cudaEventRecord(ctx->ev[2], st));
-    ctx->kev_used = 0; ctx->pev_used = 0;
 
-    // counters: [0] R cursor, [1] sum of reliable counts, [2] distinct, [3] (u32) ncand
+    // counters: [0] R cursor, [1] sum of reliable counts, [2] distinct, [3] (u32) table-overflow flag
     CK(ctx->ctr.ensure(64));
-    CK(cudaMemsetAsync(ctx->ctr.p, 0, 64, st));
     u64 *d_ctr = ctx->ctr.as<u64>();
-    u32 *d_ncand = reinterpret_cast<u32*>(d_ctr + 3);
+    u32 *d_err = reinterpret_cast<u32*>(d_ctr + 3);
 
     const u64 Ms = ctx->Ms;
+    // One partition's count table must stay L2-resident (a DRAM-resident table costs > 130 B of traffic per k-mer,
+    // profiles/r1_count_v0.md): at most TABLE_BYTES per table, 16 B slots, load <= 0.5 of the distinct k-mers.
+    const u64 TABLE_BYTES = 48ull << 20;
+    const u64 max_slots = TABLE_BYTES / sizeof(Slot);
+    const double SLOTS_PER_DISTINCT = 2.2;
     u32 P = (u32)ctx->cfg.num_partitions;
     if (P == 0)
     {
-        // keep one partition's table (16 B/slot, 2 slots per instance) around L2 size: <= 2 Mi instances per partition
-        const u64 target = 2ull << 20;
-        P = (u32)std::min<u64>(1024, std::max<u64>(1, (Ms + target - 1) / target));
+        // worst case every instance is distinct
+        u64 per_part = (u64)((double)max_slots / SLOTS_PER_DISTINCT);
+        P = (u32)std::min<u64>(4096, std::max<u64>(1, (Ms + per_part - 1) / per_part));
     }
     if (Ms == 0) P = 1;
     ctx->sz.partitions = P;
@@ -303,31 +308,27 @@ int elba_fe_count(elba_fe_ctx *ctx)
     u64 rel_cap = Ms / lower + 1;
     if (rel_cap * 12 > (1ull << 30)) rel_cap = std::max<u64>(ctx->rel_cap, std::max<u64>(Ms / 8, (1ull << 30) / 12));
     u64 R = 0, sumcnt = 0, D = 0;
+    bool force_full = false;
 
-    for (int attempt = 0; attempt < 2; ++attempt)
+    for (int attempt = 0; attempt < 3; ++attempt)
     {
         CK(ctx->rel_key.ensure(sizeof(u64) * rel_cap)); CK(ctx->rel_cnt.ensure(sizeof(u32) * rel_cap));
         ctx->rel_cap = rel_cap;
         CK(cudaMemsetAsync(ctx->ctr.p, 0, 64, st));
+        ctx->kev_used = 0; ctx->pev_used = 0;
         if (P == 1)
         {
-            u64 slots = next_pow2(std::max<u64>(2 * Ms, 1024));
-            if (slots > (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "single-partition mode needs <= 2^31 k-mer instances; use num_partitions = 0");
-            u64 cand_cap = Ms / lower + 1;
-            CK(ctx->table.ensure(sizeof(Slot) * slots)); CK(ctx->cand.ensure(sizeof(u32) * cand_cap));
+            u64 slots = std::max<u64>(2 * Ms + 64, 1024);
+            if (slots >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "single-partition mode needs < 2^31 k-mer instances; use num_partitions = 0");
+            CK(ctx->table.ensure(sizeof(Slot) * slots));
             ctx->sz.table_slots = slots;
             k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), slots); CKL(); LAUNCHED(ctx);
+            TableRef T{ctx->table.as<Slot>(), (u32)slots};
             EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
             CK(cudaEventRecord(ep.a, st));
-            if (ctx->nchunks)
-            {
-                k_count_direct<<<grid_for(ctx, 8), 256, 0, st>>>(rv, k, stride, ctx->table.as<Slot>(), slots - 1, lower, upper,
-                    ctx->cand.as<u32>(), d_ncand, (u32)std::min<u64>(cand_cap, 0xFFFFFFFFull), d_ctr + 2);
-                CKL(); LAUNCHED(ctx);
-            }
+            if (ctx->nchunks) { k_count_direct<<<grid_for(ctx, 8), 256, 0, st>>>(rv, k, stride, T, d_err, d_ctr + 2); CKL(); LAUNCHED(ctx); }
             CK(cudaEventRecord(ep.b, st));
-            k_collect_reliable<<<std::max(1u, nblk(cand_cap, 256)), 256, 0, st>>>(ctx->table.as<Slot>(), ctx->cand.as<u32>(), d_ncand, upper,
-                ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
+            k_table_collect<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
             CKL(); LAUNCHED(ctx);
         }
         else
@@ -351,37 +352,57 @@ int elba_fe_count(elba_fe_ctx *ctx)
             k_part_scatter<<<grid_for(ctx, 2), SCATTER_BLOCK, smem, st>>>(rv, k, stride, P, ctx->pcursor.as<u64>(), ctx->partbuf.as<u64>());
             CKL(); LAUNCHED(ctx);
             CK(cudaEventRecord(pp.b, st));
-            // per-partition counting in one L2-sized table
-            u64 slots = next_pow2(std::max<u64>(2 * maxcnt, 1024));
-            if (slots > (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "partition too large; raise num_partitions");
-            u64 cand_cap = maxcnt / lower + 1;
-            CK(ctx->table.ensure(sizeof(Slot) * slots)); CK(ctx->cand.ensure(sizeof(u32) * cand_cap));
-            ctx->sz.table_slots = slots;
-            for (u32 p = 0; p < P; ++p)
+
+            // table capacity: the first partition is counted with a table sized for "all distinct"; its measured
+            // distinct ratio rho sizes the rest (hash partitions are statistically alike), and consecutive partitions are
+            // merged into groups while the group's table still fits TABLE_BYTES.
+            auto slots_for = [&](u64 cnt, double rho) { return (u64)std::max<double>(1024.0, std::ceil(SLOTS_PER_DISTINCT * rho * (double)cnt) + 64.0); };
+            u64 cap_slots = std::max<u64>(max_slots, slots_for(maxcnt, 1.0));
+            if (cap_slots >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "partition too large; raise num_partitions");
+            CK(ctx->table.ensure(sizeof(Slot) * cap_slots));
+            ctx->sz.table_slots = cap_slots;
+            k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), cap_slots); CKL(); LAUNCHED(ctx);
+            double rho = 1.0;
+            u32 p = 0;
+            bool have_rho = force_full;
+            while (p < P)
             {
-                if (hist[p] == 0) continue;
-                // size this partition's table by its own instance count (keeps small partitions cheap to clear)
-                u64 pslots = next_pow2(std::max<u64>(2 * hist[p], 1024));
-                k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), pslots); CKL(); LAUNCHED(ctx);
-                CK(cudaMemsetAsync(d_ncand, 0, sizeof(u32), st));
-                EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
-                CK(cudaEventRecord(ep.a, st));
-                k_count_array<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->partbuf.as<u64>() + start[p], hist[p], ctx->table.as<Slot>(), pslots - 1,
-                    lower, upper, ctx->cand.as<u32>(), d_ncand, (u32)std::min<u64>(cand_cap, 0xFFFFFFFFull), d_ctr + 2);
-                CKL(); LAUNCHED(ctx);
-                CK(cudaEventRecord(ep.b, st));
-                u64 pc = hist[p] / lower + 1;
-                k_collect_reliable<<<std::max(1u, nblk(pc, 256)), 256, 0, st>>>(ctx->table.as<Slot>(), ctx->cand.as<u32>(), d_ncand, upper,
-                    ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
-                CKL(); LAUNCHED(ctx);
+                u32 q = p + 1; u64 cnt = hist[p];
+                if (have_rho) while (q < P && slots_for(cnt + hist[q], rho) <= max_slots) { cnt += hist[q]; ++q; }
+                if (cnt)
+                {
+                    TableRef T{ctx->table.as<Slot>(), (u32)std::min<u64>(slots_for(cnt, rho), cap_slots)};
+                    EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
+                    CK(cudaEventRecord(ep.a, st));
+                    k_count_array<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->partbuf.as<u64>() + start[p], cnt, T, d_err, d_ctr + 2); CKL(); LAUNCHED(ctx);
+                    CK(cudaEventRecord(ep.b, st));
+                    k_table_collect<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
+                    CKL(); LAUNCHED(ctx);
+                    if (!have_rho && cnt >= 4096)
+                    {
+                        u64 d0 = 0;
+                        CK(cudaMemcpyAsync(&d0, d_ctr + 2, 8, cudaMemcpyDeviceToHost, st));
+                        CK(cudaStreamSynchronize(st));
+                        rho = std::min(1.0, 1.1 * (double)d0 / (double)cnt + 0.01);
+                        have_rho = true;
+                    }
+                }
+                p = q;
             }
         }
-        u64 h[3];
+        u64 h[4];
         CK(cudaMemcpyAsync(h, d_ctr, sizeof h, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         R = h[0]; sumcnt = h[1]; D = h[2];
+        bool table_overflow = (u32)h[3] != 0;
+        if (table_overflow)
+        {
+            if (force_full) return fail(ctx, ELBA_FE_ERR_CUDA, "count table overflow with full-size tables");
+            force_full = true;          // distinct-ratio estimate was too optimistic: size every table for "all distinct"
+            continue;
+        }
         if (R <= rel_cap) break;
-        if (attempt == 1) return fail(ctx, ELBA_FE_ERR_CUDA, "reliable list overflow after resize");
+        if (attempt == 2) return fail(ctx, ELBA_FE_ERR_CUDA, "reliable list overflow after resize");
         rel_cap = R;       // exact; redo the count
     }
     if (R >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers on one context");
@@ -391,12 +412,18 @@ int elba_fe_count(elba_fe_ctx *ctx)
     CK(ctx->rel_key_s.ensure(sizeof(u64) * std::max<u64>(R, 1))); CK(ctx->rel_cnt_s.ensure(sizeof(u32) * std::max<u64>(R, 1)));
     int rc = sort_pairs(ctx, ctx->rel_key.as<u64>(), ctx->rel_key_s.as<u64>(), ctx->rel_cnt.as<u32>(), ctx->rel_cnt_s.as<u32>(), R, 64 - 2 * k, 64);
     if (rc) return rc;
-    // lookup table k-mer -> column id
+    // lookup table k-mer -> column id, fronted by a blocked Bloom filter small enough to live in L2
     u64 lslots = next_pow2(std::max<u64>(2 * R, 1024));
     CK(ctx->lut.ensure(sizeof(Slot) * lslots));
     ctx->lut_mask = lslots - 1;
+    u64 bits_per_key = (R * 2 <= (32ull << 20)) ? 16 : 8;
+    u64 fwords = next_pow2(std::max<u64>(R * bits_per_key / 64, 1024));
+    CK(ctx->filter.ensure(8 * fwords));
+    ctx->filter_mask = (u32)(fwords - 1);
+    CK(cudaMemsetAsync(ctx->filter.p, 0, 8 * fwords, st));
     k_table_clear<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->lut.as<Slot>(), lslots); CKL(); LAUNCHED(ctx);
-    if (R) { k_lookup_build<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), (u32)R, ctx->lut.as<Slot>(), ctx->lut_mask); CKL(); LAUNCHED(ctx); }
+    if (R) { k_lookup_build<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), (u32)R, ctx->lut.as<Slot>(), ctx->lut_mask,
+                                                       ctx->filter.as<u64>(), ctx->filter_mask); CKL(); LAUNCHED(ctx); }
     CK(cudaEventRecord(ctx->ev[3], st));
     ctx->phase = 2;
     return 0;
@@ -426,7 +453,7 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
         if (ctx->nchunks && R)
         {
             k_emit_seeds<<<grid_for(ctx, 8), 256, 0, st>>>(rv, ctx->cfg.k, ctx->cfg.stride, ctx->lut.as<Slot>(), ctx->lut_mask,
-                ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, npre, cb);
+                ctx->filter.as<u64>(), ctx->filter_mask, ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, npre, cb);
             CKL(); LAUNCHED(ctx);
         }
         CK(cudaEventRecord(lp.b, st));

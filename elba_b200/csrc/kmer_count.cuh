@@ -34,46 +34,41 @@ __global__ void k_prep_reads(const u64 *__restrict__ len64, u32 n, int k, int st
 }
 
 // ------------------------------------------------------------------------------------------
-// count table
-__device__ __forceinline__ Slot ld_slot(const Slot *p)
+// count table: open addressing, linear probing, 16-byte slots {key, count, aux}, `slots` arbitrary (< 2^32).
+//
+// ncu (profiles/r1_count_v0.md) showed the first version latency-bound on a 4-deep dependent chain
+// (stream load -> slot load -> CAS -> atomicAdd-with-return), each link a full L2/DRAM round trip, with
+// warps half diverged in the probe loop.  This version has ONE waited round trip per k-mer:
+//   prev = CAS(slot.key, EMPTY, kmer)   -> claims an empty slot or returns the resident key
+//   RED.ADD slot.count                  -> fire-and-forget, nothing waits on it
+// ILP k-mers per thread are in flight at once, the next k-mers are loaded before the atomics are waited on,
+// and equal k-mers inside a warp (poly-A runs land next to each other) are merged with match.any first.
+// Reliable k-mers are found afterwards by one scan of the table that also resets it (k_table_collect).
+struct TableRef { Slot *tab; u32 slots; };
+
+__device__ __forceinline__ u32 slot_of(u64 h, u32 slots) { return __umulhi((u32)h, slots); }
+
+static constexpr u32 MAX_PROBES = 1u << 14;      // a table this full means the distinct-ratio estimate was wrong: flag, host retries
+
+// returns 1 if this call claimed a new slot (a new distinct k-mer)
+__device__ __forceinline__ u32 table_insert_resume(const TableRef &T, u64 kmer, u32 s, u64 prev, u32 mult, u32 *__restrict__ err)
 {
-    // one 16-byte L2 load (L1 is useless for random table probes)
-    ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(p));
-    Slot s; s.key = v.x; s.cnt = (u32)v.y; s.aux = (u32)(v.y >> 32); return s;
+    u32 probes = 0;
+    while (prev != EMPTY_KEY && prev != kmer)
+    {
+        if (++probes > MAX_PROBES) { atomicOr(err, 1u); return 0; }
+        s = (s + 1 == T.slots) ? 0 : s + 1;
+        prev = atomicCAS(&T.tab[s].key, EMPTY_KEY, kmer);
+    }
+    atomicAdd(&T.tab[s].cnt, mult);               // result unused -> RED
+    return prev == EMPTY_KEY;
 }
 
-// Insert/increment.  cand/ncand: slots whose count just reached `lower` are appended (exactly once per key).
-__device__ __forceinline__ u32 table_add(Slot *__restrict__ tab, u64 mask, u64 kmer, u32 lower, u32 upper,
-                                         u32 *__restrict__ cand, u32 *__restrict__ ncand, u32 cand_cap)
+__device__ __forceinline__ u32 table_insert(const TableRef &T, u64 kmer, u32 mult, u32 *__restrict__ err)
 {
-    u64 s = slot_hash(kmer) & mask;
-    u32 claimed = 0;
-    while (true)
-    {
-        Slot v = ld_slot(tab + s);
-        if (v.key == EMPTY_KEY)
-        {
-            u64 prev = atomicCAS(&tab[s].key, EMPTY_KEY, kmer);
-            claimed = (prev == EMPTY_KEY);
-            v.key = claimed ? kmer : prev;
-            v.cnt = 0;
-        }
-        if (v.key == kmer)
-        {
-            // counts only matter up to upper+1: stop hammering hot keys (poly-A) once saturated
-            if (v.cnt <= upper)
-            {
-                u32 old = atomicAdd(&tab[s].cnt, 1u);
-                if (old + 1 == lower)
-                {
-                    u32 i = atomicAdd(ncand, 1u);
-                    if (i < cand_cap) cand[i] = (u32)s;
-                }
-            }
-            return claimed;
-        }
-        s = (s + 1) & mask;
-    }
+    u32 s = slot_of(slot_hash(kmer), T.slots);
+    u64 prev = atomicCAS(&T.tab[s].key, EMPTY_KEY, kmer);
+    return table_insert_resume(T, kmer, s, prev, mult, err);
 }
 
 // warp-reduce a per-thread tally into one global counter
@@ -91,9 +86,8 @@ __global__ void k_table_clear(Slot *__restrict__ tab, u64 slots)
     for (; i < slots; i += step) reinterpret_cast<ulonglong2*>(tab)[i] = e;
 }
 
-__global__ void __launch_bounds__(256) k_count_direct(ReadsView rv, int k, int stride, Slot *__restrict__ tab, u64 mask,
-                                                      u32 lower, u32 upper, u32 *__restrict__ cand, u32 *__restrict__ ncand, u32 cand_cap,
-                                                      u64 *__restrict__ distinct)
+// single-partition mode: straight from the reads (small inputs)
+__global__ void __launch_bounds__(256) k_count_direct(ReadsView rv, int k, int stride, TableRef T, u32 *__restrict__ err, u64 *__restrict__ distinct)
 {
     u64 step = (u64)gridDim.x * blockDim.x;
     u64 rounds = (rv.nchunks + step - 1) / step;
@@ -103,47 +97,85 @@ __global__ void __launch_bounds__(256) k_count_direct(ReadsView rv, int k, int s
         u64 g = it * step + (u64)blockIdx.x * blockDim.x + threadIdx.x;
         ChunkInfo ci;
         if (locate_chunk(rv, g, k, ci))
-            foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32, int) { nd += table_add(tab, mask, x, lower, upper, cand, ncand, cand_cap); });
+            foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32, int) { nd += table_insert(T, x, 1u, err); });
     }
     tally(distinct, nd);
 }
 
-__global__ void __launch_bounds__(256) k_count_array(const u64 *__restrict__ kmers, u64 n, Slot *__restrict__ tab, u64 mask,
-                                                     u32 lower, u32 upper, u32 *__restrict__ cand, u32 *__restrict__ ncand, u32 cand_cap,
-                                                     u64 *__restrict__ distinct)
+static constexpr int COUNT_ILP = 4;
+__global__ void __launch_bounds__(256) k_count_array(const u64 *__restrict__ kmers, u64 n, TableRef T, u32 *__restrict__ err, u64 *__restrict__ distinct)
 {
-    u64 step = (u64)gridDim.x * blockDim.x;
-    u64 rounds = (n + step - 1) / step;
+    const u64 tile = (u64)blockDim.x * COUNT_ILP;
+    const u64 ntiles = (n + tile - 1) / tile;
+    const int lane = threadIdx.x & 31;
     u32 nd = 0;
-    for (u64 it = 0; it < rounds; ++it)
+    u64 x[COUNT_ILP]; bool valid[COUNT_ILP];
+    u64 t = blockIdx.x;
+    if (t < ntiles)
     {
-        u64 i = it * step + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < n)
+#pragma unroll
+        for (int j = 0; j < COUNT_ILP; ++j) { u64 i = t * tile + (u64)j * blockDim.x + threadIdx.x; valid[j] = i < n; x[j] = valid[j] ? __ldcs(kmers + i) : 0; }
+    }
+    for (; t < ntiles; t += gridDim.x)
+    {
+        u32 mult[COUNT_ILP], s[COUNT_ILP]; u64 prev[COUNT_ILP], cur[COUNT_ILP];
+#pragma unroll
+        for (int j = 0; j < COUNT_ILP; ++j)
         {
-            u64 x = __ldcs(kmers + i);        // streaming: do not displace the table from L2
-            nd += table_add(tab, mask, x, lower, upper, cand, ncand, cand_cap);
+            cur[j] = x[j];
+            unsigned act = __ballot_sync(0xffffffffu, valid[j]);
+            mult[j] = 0;
+            if (valid[j])
+            {
+                unsigned m = __match_any_sync(act, cur[j]);
+                if (lane == __ffs(m) - 1) mult[j] = __popc(m);
+            }
         }
+#pragma unroll
+        for (int j = 0; j < COUNT_ILP; ++j)
+            if (mult[j]) { s[j] = slot_of(slot_hash(cur[j]), T.slots); prev[j] = atomicCAS(&T.tab[s[j]].key, EMPTY_KEY, cur[j]); }
+        // next tile's k-mers are requested before the atomics above are waited on
+        u64 tn = t + gridDim.x;
+        if (tn < ntiles)
+        {
+#pragma unroll
+            for (int j = 0; j < COUNT_ILP; ++j) { u64 i = tn * tile + (u64)j * blockDim.x + threadIdx.x; valid[j] = i < n; x[j] = valid[j] ? __ldcs(kmers + i) : 0; }
+        }
+#pragma unroll
+        for (int j = 0; j < COUNT_ILP; ++j)
+            if (mult[j]) nd += table_insert_resume(T, cur[j], s[j], prev[j], mult[j], err);
     }
     tally(distinct, nd);
 }
 
-// candidates -> reliable (count <= upper); also accumulates the instance total of the reliable k-mers
-__global__ void k_collect_reliable(const Slot *__restrict__ tab, const u32 *__restrict__ cand, const u32 *__restrict__ ncand_p, u32 upper,
-                                   u64 *__restrict__ out_key, u32 *__restrict__ out_cnt, u64 *__restrict__ counters /*[0]=R cursor, [1]=sum cnt*/, u64 cap)
+// One scan of a table: reliable k-mers (lower <= count <= upper) are appended to the output, every occupied slot is
+// reset for the next partition.  counters: [0] R cursor, [1] sum of the reliable counts.
+__global__ void __launch_bounds__(256) k_table_collect(Slot *__restrict__ tab, u32 slots, u32 lower, u32 upper,
+                                                       u64 *__restrict__ out_key, u32 *__restrict__ out_cnt, u64 *__restrict__ counters, u64 cap)
 {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    u32 ncand = *ncand_p;
-    bool ok = false; Slot v; v.key = 0; v.cnt = 0;
-    if (i < ncand) { v = ld_slot(tab + cand[i]); ok = v.cnt <= upper; }
-    unsigned m = __ballot_sync(0xffffffffu, ok);
-    if (!m) return;
-    int lane = threadIdx.x & 31;
-    u32 sum = ok ? v.cnt : 0;
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    u64 base = 0;
-    if (lane == 0) { base = atomicAdd(&counters[0], (u64)__popc(m)); atomicAdd(&counters[1], (u64)sum); }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (ok) { u64 o = base + __popc(m & ((1u << lane) - 1)); if (o < cap) { out_key[o] = v.key; out_cnt[o] = v.cnt; } }
+    const u32 step = gridDim.x * blockDim.x;
+    const u32 rounds = (slots + step - 1) / step;
+    const int lane = threadIdx.x & 31;
+    ulonglong2 e; e.x = EMPTY_KEY; e.y = 0;
+    for (u32 it = 0; it < rounds; ++it)
+    {
+        u32 i = it * step + blockIdx.x * blockDim.x + threadIdx.x;
+        bool ok = false; u64 key = EMPTY_KEY; u32 cnt = 0;
+        if (i < slots)
+        {
+            ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(tab + i));
+            key = v.x; cnt = (u32)v.y;
+            if (key != EMPTY_KEY) { reinterpret_cast<ulonglong2*>(tab)[i] = e; ok = cnt >= lower && cnt <= upper; }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (!m) continue;
+        u32 sum = ok ? cnt : 0;
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        u64 base = 0;
+        if (lane == 0) { base = atomicAdd(&counters[0], (u64)__popc(m)); atomicAdd(&counters[1], (u64)sum); }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (ok) { u64 o = base + __popc(m & ((1u << lane) - 1)); if (o < cap) { out_key[o] = key; out_cnt[o] = cnt; } }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -245,13 +277,25 @@ __global__ void __launch_bounds__(SCATTER_BLOCK) k_part_scatter(ReadsView rv, in
 }
 
 // ------------------------------------------------------------------------------------------
-// reliable k-mer -> column id
-__global__ void k_lookup_build(const u64 *__restrict__ keys, const u32 *__restrict__ cnts, u32 R, Slot *__restrict__ tab, u64 mask)
+// reliable k-mer -> column id: a hash table in HBM fronted by an L2-resident blocked Bloom filter (two bits of
+// one 64-bit word per k-mer).  In sweep 2 almost every k-mer instance is NOT reliable; the filter answers those
+// from L2 and only ~2-5 % false positives plus the true hits touch the table in DRAM.
+__device__ __forceinline__ void filter_bits(u64 h, u32 fmask, u32 &word, u64 &bits)
+{
+    word = (u32)(h >> 32) & fmask;
+    bits = (1ull << (h & 63)) | (1ull << ((h >> 6) & 63));
+}
+
+__global__ void k_lookup_build(const u64 *__restrict__ keys, const u32 *__restrict__ cnts, u32 R, Slot *__restrict__ tab, u64 mask,
+                               u64 *__restrict__ filter, u32 fmask)
 {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
     u64 x = keys[i];
-    u64 s = slot_hash(x) & mask;
+    u64 h = slot_hash(x);
+    u32 w; u64 bits; filter_bits(h, fmask, w, bits);
+    atomicOr(&filter[w], bits);
+    u64 s = h & mask;
     while (true)
     {
         u64 prev = atomicCAS(&tab[s].key, EMPTY_KEY, x);
@@ -260,9 +304,12 @@ __global__ void k_lookup_build(const u64 *__restrict__ keys, const u32 *__restri
     }
 }
 
-__device__ __forceinline__ bool lookup(const Slot *__restrict__ tab, u64 mask, u64 x, u32 &col)
+__device__ __forceinline__ bool lookup(const Slot *__restrict__ tab, u64 mask, const u64 *__restrict__ filter, u32 fmask, u64 x, u32 &col)
 {
-    u64 s = slot_hash(x) & mask;
+    u64 h = slot_hash(x);
+    u32 w; u64 bits; filter_bits(h, fmask, w, bits);
+    if ((__ldg(filter + w) & bits) != bits) return false;
+    u64 s = h & mask;
     while (true)
     {
         ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tab + s));
@@ -276,6 +323,7 @@ __device__ __forceinline__ bool lookup(const Slot *__restrict__ tab, u64 mask, u
 // A thread first marks its hits (bitmask over its chunk), the warp reserves output space with ONE atomic,
 // then the hits are recomputed from the staged bases and written.
 __global__ void __launch_bounds__(256) k_emit_seeds(ReadsView rv, int k, int stride, const Slot *__restrict__ tab, u64 mask,
+                                                    const u64 *__restrict__ filter, u32 fmask,
                                                     u64 *__restrict__ out_key, u32 *__restrict__ out_pos, u64 *__restrict__ cursor, u64 cap, int col_bits)
 {
     u64 step = (u64)gridDim.x * blockDim.x;
@@ -286,7 +334,7 @@ __global__ void __launch_bounds__(256) k_emit_seeds(ReadsView rv, int k, int str
         u64 g = it * step + (u64)blockIdx.x * blockDim.x + threadIdx.x;
         ChunkInfo ci; bool have = locate_chunk(rv, g, k, ci);
         u32 hits = 0;
-        if (have) foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32, int s) { u32 c; if (lookup(tab, mask, x, c)) hits |= 1u << s; });
+        if (have) foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32, int s) { u32 c; if (lookup(tab, mask, filter, fmask, x, c)) hits |= 1u << s; });
         u32 n = __popc(hits);
         u32 incl = n;
         for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -300,7 +348,7 @@ __global__ void __launch_bounds__(256) k_emit_seeds(ReadsView rv, int k, int str
             foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32 p, int s) {
                 if (hits & (1u << s))
                 {
-                    u32 c = 0; lookup(tab, mask, x, c);
+                    u32 c = 0; lookup(tab, mask, filter, fmask, x, c);
                     if (base < cap) { out_key[base] = ((u64)ci.read << col_bits) | c; out_pos[base] = p; }
                     base++;
                 }

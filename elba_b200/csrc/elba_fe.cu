@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 #include <cstdio>
 #include <cmath>
 #include <algorithm>
@@ -52,6 +53,9 @@ struct elba_fe_ctx
     u32 n = 0; u64 packed_bytes = 0, nchunks = 0, M = 0, Ms = 0; int64_t read_id_offset = 0;
     // counting
     DevBuf table, cand, ctr, partbuf, phist, pcursor, rel_key, rel_cnt, rel_key_s, rel_cnt_s, lut, filter;
+    DevBuf plan, bfill, pflags, scratch[2];
+    cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    u64 scratch_mb = 64;
     u64 lut_mask = 0; u64 rel_cap = 0; u32 filter_mask = 0;
     // A
     DevBuf seed_key, seed_pos, seed_key2, seed_pos2, idx, a_key, a_rowptr, a_col, a_pos, at_key, at_key2, at_pos2, at_colptr, at_row, at_pos, prod;
@@ -196,8 +200,12 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     // random 16-byte table probes: do not let L2 pull whole 128-byte lines from HBM for them (profiles/r1_count_v0.md)
     cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-    // opt in to the large dynamic shared memory of the scatter kernel
-    cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    if (const char *e = getenv("ELBA_FE_SCRATCH_MB")) { long v = atol(e); if (v >= 8 && v <= 65536) ctx->scratch_mb = (u64)v; }
+    // opt in to large dynamic shared memory
+    cudaFuncSetAttribute(k_scatter1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S1_TILE + 2 * sizeof(u32) * MAX_P1));
+    cudaFuncSetAttribute(k_count_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS));
     *out = ctx;
     return 0;
 }
@@ -212,11 +220,15 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
         &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->bins, &ctx->small_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
-        &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom };
+        &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
+        &ctx->plan, &ctx->bfill, &ctx->pflags, &ctx->scratch[0], &ctx->scratch[1] };
     for (DevBuf *b : all) b->release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     for (auto *v : { &ctx->kev, &ctx->sev, &ctx->pev, &ctx->lev }) for (auto &p : *v) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
     return 0;
 }
@@ -274,6 +286,23 @@ int elba_fe_set_reads_device(elba_fe_ctx *ctx, const uint8_t *d_packed, uint64_t
 }
 
 // -------------------------------------------------------------------------------------------------
+// Slow, always-correct counting of one set of h slabs with a global table (heavy-hitter partitions, direct mode).
+static int count_with_global_table(elba_fe_ctx *ctx, const std::vector<std::pair<const u64*, u64>> &slabs, u64 total, u64 rel_cap)
+{
+    cudaStream_t st = ctx->stream;
+    u64 *d_ctr = ctx->ctr.as<u64>(); u32 *d_err = reinterpret_cast<u32*>(d_ctr + 3);
+    u64 slots = std::max<u64>(2 * total + 64, 1024);
+    if (slots >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "a k-mer partition needs a count table of more than 2^32 slots");
+    CK(ctx->table.ensure(sizeof(Slot) * slots));
+    k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), slots, EMPTY_H); CKL(); LAUNCHED(ctx);
+    TableRef T{ctx->table.as<Slot>(), (u32)slots};
+    for (auto &sl : slabs)
+        if (sl.second) { k_count_array<<<grid_for(ctx, 4), 256, 0, st>>>(sl.first, sl.second, T, d_err, d_ctr + 2); CKL(); LAUNCHED(ctx); }
+    k_table_collect<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, (u32)ctx->cfg.lower, (u32)ctx->cfg.upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
+    CKL(); LAUNCHED(ctx);
+    return 0;
+}
+
 int elba_fe_count(elba_fe_ctx *ctx)
 {
     if (!ctx) return ELBA_FE_ERR_INVALID;
@@ -284,45 +313,38 @@ int elba_fe_count(elba_fe_ctx *ctx)
     ReadsView rv = view(ctx);
     CK(cudaEventRecord(ctx->ev[2], st));
 
-    // counters: [0] R cursor, [1] sum of reliable counts, [2] distinct, [3] (u32) table-overflow flag
+    // counters: [0] R cursor, [1] sum of reliable counts, [2] distinct, [3] (u32) table-overflow flag, [4] (u32) level-1 overflow flag
     CK(ctx->ctr.ensure(64));
     u64 *d_ctr = ctx->ctr.as<u64>();
     u32 *d_err = reinterpret_cast<u32*>(d_ctr + 3);
+    u32 *d_flag1 = reinterpret_cast<u32*>(d_ctr + 4);
 
     const u64 Ms = ctx->Ms;
-    // One partition's count table must stay L2-resident (a DRAM-resident table costs > 130 B of traffic per k-mer,
-    // profiles/r1_count_v0.md): at most TABLE_BYTES per table, 16 B slots, load <= 0.5 of the distinct k-mers.
-    const u64 TABLE_BYTES = 48ull << 20;
-    const u64 max_slots = TABLE_BYTES / sizeof(Slot);
-    const double SLOTS_PER_DISTINCT = 2.2;
-    u32 P = (u32)ctx->cfg.num_partitions;
-    if (P == 0)
-    {
-        // worst case every instance is distinct
-        u64 per_part = (u64)((double)max_slots / SLOTS_PER_DISTINCT);
-        P = (u32)std::min<u64>(4096, std::max<u64>(1, (Ms + per_part - 1) / per_part));
-    }
-    if (Ms == 0) P = 1;
-    ctx->sz.partitions = P;
+    // level-1 partitions of about PART_TARGET instances (8 MB of h values each)
+    const u64 PART_TARGET = 1ull << 20;
+    u32 P1 = (u32)ctx->cfg.num_partitions;
+    const bool direct = (P1 == 1) || (P1 == 0 && Ms <= 65536);
+    if (P1 == 0) P1 = (u32)std::min<u64>(MAX_P1, std::max<u64>(1, (Ms + PART_TARGET - 1) / PART_TARGET));
+    if (direct) P1 = 1;
+    ctx->sz.partitions = P1;
 
     u64 rel_cap = Ms / lower + 1;
     if (rel_cap * 12 > (1ull << 30)) rel_cap = std::max<u64>(ctx->rel_cap, std::max<u64>(Ms / 8, (1ull << 30) / 12));
     u64 R = 0, sumcnt = 0, D = 0;
-    bool force_full = false;
 
-    for (int attempt = 0; attempt < 3; ++attempt)
+    for (int attempt = 0; attempt < 2; ++attempt)
     {
         CK(ctx->rel_key.ensure(sizeof(u64) * rel_cap)); CK(ctx->rel_cnt.ensure(sizeof(u32) * rel_cap));
         ctx->rel_cap = rel_cap;
         CK(cudaMemsetAsync(ctx->ctr.p, 0, 64, st));
         ctx->kev_used = 0; ctx->pev_used = 0;
-        if (P == 1)
+        if (direct)
         {
             u64 slots = std::max<u64>(2 * Ms + 64, 1024);
             if (slots >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "single-partition mode needs < 2^31 k-mer instances; use num_partitions = 0");
             CK(ctx->table.ensure(sizeof(Slot) * slots));
             ctx->sz.table_slots = slots;
-            k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), slots); CKL(); LAUNCHED(ctx);
+            k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), slots, EMPTY_H); CKL(); LAUNCHED(ctx);
             TableRef T{ctx->table.as<Slot>(), (u32)slots};
             EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
             CK(cudaEventRecord(ep.a, st));
@@ -333,82 +355,121 @@ int elba_fe_count(elba_fe_ctx *ctx)
         }
         else
         {
-            // sweep 0: partition sizes
-            CK(ctx->phist.ensure(sizeof(u64) * (P + 1))); CK(ctx->pcursor.ensure(sizeof(u64) * (P + 1)));
-            CK(cudaMemsetAsync(ctx->phist.p, 0, sizeof(u64) * (P + 1), st));
+            ctx->sz.table_slots = BUCKET_SLOTS;
+            // ---- level 1: optimistic uniform regions; exact regions from a histogram if one overflows
+            const u64 mean = (Ms + P1 - 1) / P1;
+            u64 cap1 = (u64)((double)mean * 1.03) + 4096; cap1 = (cap1 + 15) & ~15ull;
+            if (cap1 >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "level-1 partition exceeds 2^32 instances");
+            std::vector<u64> start(P1 + 1);
+            for (u32 p = 0; p <= P1; ++p) start[p] = (u64)p * cap1;
+            std::vector<u32> cnt(P1, 0);
+            CK(ctx->phist.ensure(sizeof(u64) * (P1 + 1))); CK(ctx->pcursor.ensure(sizeof(u32) * (P1 + 1)));
+            const size_t smem1 = sizeof(u64) * S1_TILE + 2 * sizeof(u32) * P1;
             EventPair &pp = next_pair(ctx->pev, ctx->pev_used);
             CK(cudaEventRecord(pp.a, st));
-            k_part_hist<<<grid_for(ctx, 4), 256, sizeof(u32) * P, st>>>(rv, k, stride, P, ctx->phist.as<u64>()); CKL(); LAUNCHED(ctx);
-            std::vector<u64> hist(P + 1, 0), start(P + 1, 0);
-            CK(cudaMemcpyAsync(hist.data(), ctx->phist.p, sizeof(u64) * P, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            u64 maxcnt = 0;
-            for (u32 p = 0; p < P; ++p) { start[p + 1] = start[p] + hist[p]; maxcnt = std::max(maxcnt, hist[p]); }
-            if (start[P] != Ms) return fail(ctx, ELBA_FE_ERR_CUDA, "partition histogram does not sum to the k-mer count");
-            CK(cudaMemcpyAsync(ctx->pcursor.p, start.data(), sizeof(u64) * P, cudaMemcpyHostToDevice, st));
-            CK(ctx->partbuf.ensure(sizeof(u64) * std::max<u64>(Ms, 1)));
-            // sweep 1: scatter
-            size_t smem = sizeof(u64) * SCATTER_BLOCK * CHUNK + sizeof(u64) * P + sizeof(u32) * (2 * (size_t)P + 2);
-            k_part_scatter<<<grid_for(ctx, 2), SCATTER_BLOCK, smem, st>>>(rv, k, stride, P, ctx->pcursor.as<u64>(), ctx->partbuf.as<u64>());
-            CKL(); LAUNCHED(ctx);
+            for (int lay = 0; lay < 2; ++lay)
+            {
+                CK(ctx->partbuf.ensure(sizeof(u64) * std::max<u64>(start[P1], 1)));
+                CK(cudaMemcpyAsync(ctx->phist.p, start.data(), sizeof(u64) * (P1 + 1), cudaMemcpyHostToDevice, st));
+                CK(cudaMemsetAsync(ctx->pcursor.p, 0, sizeof(u32) * (P1 + 1), st));
+                CK(cudaMemsetAsync(d_flag1, 0, 4, st));
+                k_scatter1<<<grid_for(ctx, 2), S1_THREADS, smem1, st>>>(rv, k, stride, P1, ctx->phist.as<u64>(), ctx->pcursor.as<u32>(), ctx->partbuf.as<u64>(), d_flag1);
+                CKL(); LAUNCHED(ctx);
+                u32 flag = 0;
+                CK(cudaMemcpyAsync(cnt.data(), ctx->pcursor.p, sizeof(u32) * P1, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(&flag, d_flag1, 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (!flag) break;
+                if (lay == 1) return fail(ctx, ELBA_FE_ERR_CUDA, "level-1 scatter overflowed an exact layout");
+                // skewed partition sizes (heavy hitters): exact histogram, exact regions
+                CK(ctx->lut.ensure(sizeof(u64) * (P1 + 1)));
+                CK(cudaMemsetAsync(ctx->lut.p, 0, sizeof(u64) * (P1 + 1), st));
+                k_hist1<<<grid_for(ctx, 4), 256, sizeof(u32) * P1, st>>>(rv, k, stride, P1, ctx->lut.as<u64>()); CKL(); LAUNCHED(ctx);
+                std::vector<u64> hist(P1);
+                CK(cudaMemcpyAsync(hist.data(), ctx->lut.p, sizeof(u64) * P1, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                for (u32 p = 0; p < P1; ++p) { if (hist[p] >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "level-1 partition exceeds 2^32 instances"); start[p + 1] = start[p] + ((hist[p] + 15) & ~15ull); }
+            }
             CK(cudaEventRecord(pp.b, st));
 
-            // table capacity: the first partition is counted with a table sized for "all distinct"; its measured
-            // distinct ratio rho sizes the rest (hash partitions are statistically alike), and consecutive partitions are
-            // merged into groups while the group's table still fits TABLE_BYTES.
-            auto slots_for = [&](u64 cnt, double rho) { return (u64)std::max<double>(1024.0, std::ceil(SLOTS_PER_DISTINCT * rho * (double)cnt) + 64.0); };
-            u64 cap_slots = std::max<u64>(max_slots, slots_for(maxcnt, 1.0));
-            if (cap_slots >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "partition too large; raise num_partitions");
-            CK(ctx->table.ensure(sizeof(Slot) * cap_slots));
-            ctx->sz.table_slots = cap_slots;
-            k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), cap_slots); CKL(); LAUNCHED(ctx);
-            double rho = 1.0;
-            u32 p = 0;
-            bool have_rho = force_full;
-            while (p < P)
+            // ---- plan of level 2
+            std::vector<u32> plan(4 * (size_t)P1 + 2, 0);
+            u32 *pn = plan.data(), *pp2 = pn + P1, *ptile = pp2 + P1, *pbucket = ptile + P1 + 1;
+            std::vector<u32> slow;
+            for (u32 p = 0; p < P1; ++p)
             {
-                u32 q = p + 1; u64 cnt = hist[p];
-                if (have_rho) while (q < P && slots_for(cnt + hist[q], rho) <= max_slots) { cnt += hist[q]; ++q; }
-                if (cnt)
+                u64 n = cnt[p];
+                u64 p2 = n ? std::max<u64>(1, (n * 5 / 4 + BUCKET_CAP - 1) / BUCKET_CAP) : 0;
+                if (p2 > MAX_P2) { slow.push_back(p); n = 0; p2 = 0; }
+                pn[p] = (u32)n; pp2[p] = (u32)p2;
+                ptile[p + 1] = ptile[p] + (u32)((n + S2_TILE - 1) / S2_TILE);
+                pbucket[p + 1] = pbucket[p] + (u32)p2;
+            }
+            const u32 nbuckets = pbucket[P1];
+            CK(ctx->plan.ensure(sizeof(u32) * plan.size()));
+            CK(cudaMemcpyAsync(ctx->plan.p, plan.data(), sizeof(u32) * plan.size(), cudaMemcpyHostToDevice, st));
+            CK(ctx->bfill.ensure(sizeof(u32) * ((size_t)nbuckets + 1))); CK(ctx->pflags.ensure(sizeof(u32) * ((size_t)P1 + 1)));
+            CK(cudaMemsetAsync(ctx->bfill.p, 0, sizeof(u32) * ((size_t)nbuckets + 1), st));
+            CK(cudaMemsetAsync(ctx->pflags.p, 0, sizeof(u32) * ((size_t)P1 + 1), st));
+            PartPlan pl; pl.n = ctx->plan.as<u32>(); pl.p2 = pl.n + P1; pl.tile_start = pl.p2 + P1; pl.bucket_start = pl.tile_start + P1 + 1;
+            PartInput pi; pi.in = ctx->partbuf.as<u64>(); pi.W = 1; pi.slab_stride = 0; pi.part_start = ctx->phist.as<u64>(); pi.cnt = ctx->pcursor.as<u32>(); pi.P = P1;
+
+            // ---- groups of partitions whose sub-buckets fit one scratch buffer; two buffers, two streams
+            const u64 group_buckets = std::max<u64>(MAX_P2, (ctx->scratch_mb << 20) / (sizeof(u64) * BUCKET_CAP));
+            for (int b = 0; b < 2; ++b) CK(ctx->scratch[b].ensure(sizeof(u64) * BUCKET_CAP * std::min<u64>(group_buckets, std::max<u32>(nbuckets, 1))));
+            const size_t smemc = (sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS;
+            EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
+            CK(cudaEventRecord(ep.a, st));
+            CK(cudaEventRecord(ctx->ev_fork, st));
+            CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+            int which = 0; bool used_aux = false;
+            for (u32 g0 = 0; g0 < P1;)
+            {
+                u32 g1 = g0 + 1;
+                while (g1 < P1 && (u64)(pbucket[g1 + 1] - pbucket[g0]) <= group_buckets) ++g1;
+                const u32 nt = ptile[g1] - ptile[g0], nb = pbucket[g1] - pbucket[g0];
+                if (nt)
                 {
-                    TableRef T{ctx->table.as<Slot>(), (u32)std::min<u64>(slots_for(cnt, rho), cap_slots)};
-                    EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
-                    CK(cudaEventRecord(ep.a, st));
-                    k_count_array<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->partbuf.as<u64>() + start[p], cnt, T, d_err, d_ctr + 2); CKL(); LAUNCHED(ctx);
-                    CK(cudaEventRecord(ep.b, st));
-                    k_table_collect<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
+                    cudaStream_t s2 = which ? ctx->aux : st; used_aux |= which != 0;
+                    k_scatter2<<<std::min<u32>(nt, grid_for(ctx, 5)), S2_THREADS, 0, s2>>>(pi, pl, P1, 0, g0, g1, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ctx->pflags.as<u32>());
                     CKL(); LAUNCHED(ctx);
-                    if (!have_rho && cnt >= 4096)
-                    {
-                        u64 d0 = 0;
-                        CK(cudaMemcpyAsync(&d0, d_ctr + 2, 8, cudaMemcpyDeviceToHost, st));
-                        CK(cudaStreamSynchronize(st));
-                        rho = std::min(1.0, 1.1 * (double)d0 / (double)cnt + 0.01);
-                        have_rho = true;
-                    }
+                    k_count_buckets<<<std::min<u32>(nb, grid_for(ctx, 2)), CB_THREADS, smemc, s2>>>(pl, g0, g1, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ctx->pflags.as<u32>(),
+                        lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
+                    CKL(); LAUNCHED(ctx);
+                    which ^= 1;
                 }
-                p = q;
+                g0 = g1;
+            }
+            if (used_aux) { CK(cudaEventRecord(ctx->ev_join, ctx->aux)); CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); }
+            CK(cudaEventRecord(ep.b, st));
+
+            // ---- partitions the fast path gave up on (a sub-bucket overflowed: heavy hitters): exact global-table count
+            std::vector<u32> pf(P1);
+            CK(cudaMemcpyAsync(pf.data(), ctx->pflags.p, sizeof(u32) * P1, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (u32 p = 0; p < P1; ++p) if (pf[p]) slow.push_back(p);
+            ctx->sz.slow_partitions = slow.size();
+            for (u32 p : slow)
+            {
+                std::vector<std::pair<const u64*, u64>> slabs{{ctx->partbuf.as<u64>() + start[p], (u64)cnt[p]}};
+                int rc = count_with_global_table(ctx, slabs, cnt[p], rel_cap);
+                if (rc) return rc;
             }
         }
         u64 h[4];
         CK(cudaMemcpyAsync(h, d_ctr, sizeof h, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         R = h[0]; sumcnt = h[1]; D = h[2];
-        bool table_overflow = (u32)h[3] != 0;
-        if (table_overflow)
-        {
-            if (force_full) return fail(ctx, ELBA_FE_ERR_CUDA, "count table overflow with full-size tables");
-            force_full = true;          // distinct-ratio estimate was too optimistic: size every table for "all distinct"
-            continue;
-        }
+        if ((u32)h[3] != 0) return fail(ctx, ELBA_FE_ERR_CUDA, "count table overflow");
         if (R <= rel_cap) break;
-        if (attempt == 2) return fail(ctx, ELBA_FE_ERR_CUDA, "reliable list overflow after resize");
+        if (attempt == 1) return fail(ctx, ELBA_FE_ERR_CUDA, "reliable list overflow after resize");
         rel_cap = R;       // exact; redo the count
     }
     if (R >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers on one context");
     ctx->sz.distinct = D; ctx->sz.reliable = R; ctx->sz.nnzA_pre = sumcnt;
 
-    // column ids = rank by k-mer value: sort (key, count) by key
+    // the lists hold h = mix64(k-mer): back to k-mers, then column ids = rank by k-mer value: sort (key, count) by key
+    if (R) { k_unmix<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_key.as<u64>(), R); CKL(); LAUNCHED(ctx); }
     CK(ctx->rel_key_s.ensure(sizeof(u64) * std::max<u64>(R, 1))); CK(ctx->rel_cnt_s.ensure(sizeof(u32) * std::max<u64>(R, 1)));
     int rc = sort_pairs(ctx, ctx->rel_key.as<u64>(), ctx->rel_key_s.as<u64>(), ctx->rel_cnt.as<u32>(), ctx->rel_cnt_s.as<u32>(), R, 64 - 2 * k, 64);
     if (rc) return rc;
@@ -421,7 +482,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
     CK(ctx->filter.ensure(8 * fwords));
     ctx->filter_mask = (u32)(fwords - 1);
     CK(cudaMemsetAsync(ctx->filter.p, 0, 8 * fwords, st));
-    k_table_clear<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->lut.as<Slot>(), lslots); CKL(); LAUNCHED(ctx);
+    k_table_clear<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->lut.as<Slot>(), lslots, EMPTY_KEY); CKL(); LAUNCHED(ctx);
     if (R) { k_lookup_build<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), (u32)R, ctx->lut.as<Slot>(), ctx->lut_mask,
                                                        ctx->filter.as<u64>(), ctx->filter_mask); CKL(); LAUNCHED(ctx); }
     CK(cudaEventRecord(ctx->ev[3], st));

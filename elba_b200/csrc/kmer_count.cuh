@@ -1,18 +1,17 @@
 // K-mer counting kernels (reference: src/KmerOps.cpp:18-350, include/KmerOps.hpp:58-136).
 //
 //   k_prep_reads        per-read chunk / k-mer counts (then exclusive scans)
-//   k_part_hist         sweep 0: canonical k-mers -> partition histogram          (partitioned mode)
-//   k_part_scatter      sweep 1: canonical k-mers -> partition buffers, tile-sorted in shared memory,
-//                       written in coalesced runs (the reference's per-owner buckets + Alltoallv pack,
-//                       KmerOps.cpp:99-151, as one kernel)
-//   k_count_array       open-addressing count table in HBM/L2 over one partition buffer
-//   k_count_direct      the same, fed straight from the reads (single-partition mode)
-//   k_collect_reliable  candidates (count reached LOWER) -> reliable list filtered by UPPER
+//   (count_smem.cuh)    the fast path: two-level partition + shared-memory counting
+//   k_count_array       open-addressing count table in HBM/L2 over one partition buffer: the exact fallback for a
+//                       partition whose sub-buckets overflow (heavy hitters), profiles/r1_count_v0.md
+//   k_count_direct      the same, fed straight from the reads (single-partition mode, small inputs)
+//   k_table_collect     one table scan: reliable k-mers out, table reset
 //   k_lookup_build      reliable k-mer -> column id table
 //   k_emit_seeds        sweep 2: (read, column, pos) of every instance of a reliable k-mer
 //                       (get_kmer_count_map_values + create_kmer_matrix triples, KmerOps.cpp:283-394)
 #pragma once
 #include "common.cuh"
+#include "count_smem.cuh"
 
 namespace elba {
 
@@ -46,29 +45,31 @@ __global__ void k_prep_reads(const u64 *__restrict__ len64, u32 n, int k, int st
 // Reliable k-mers are found afterwards by one scan of the table that also resets it (k_table_collect).
 struct TableRef { Slot *tab; u32 slots; };
 
+// The count tables hold h = mix64(canonical k-mer) (count_smem.cuh): the slot comes from the LOW word of h, the
+// partition digits from the high word.
 __device__ __forceinline__ u32 slot_of(u64 h, u32 slots) { return __umulhi((u32)h, slots); }
 
 static constexpr u32 MAX_PROBES = 1u << 14;      // a table this full means the distinct-ratio estimate was wrong: flag, host retries
 
 // returns 1 if this call claimed a new slot (a new distinct k-mer)
-__device__ __forceinline__ u32 table_insert_resume(const TableRef &T, u64 kmer, u32 s, u64 prev, u32 mult, u32 *__restrict__ err)
+__device__ __forceinline__ u32 table_insert_resume(const TableRef &T, u64 h, u32 s, u64 prev, u32 mult, u32 *__restrict__ err)
 {
     u32 probes = 0;
-    while (prev != EMPTY_KEY && prev != kmer)
+    while (prev != EMPTY_H && prev != h)
     {
         if (++probes > MAX_PROBES) { atomicOr(err, 1u); return 0; }
         s = (s + 1 == T.slots) ? 0 : s + 1;
-        prev = atomicCAS(&T.tab[s].key, EMPTY_KEY, kmer);
+        prev = atomicCAS(&T.tab[s].key, EMPTY_H, h);
     }
     atomicAdd(&T.tab[s].cnt, mult);               // result unused -> RED
-    return prev == EMPTY_KEY;
+    return prev == EMPTY_H;
 }
 
-__device__ __forceinline__ u32 table_insert(const TableRef &T, u64 kmer, u32 mult, u32 *__restrict__ err)
+__device__ __forceinline__ u32 table_insert(const TableRef &T, u64 h, u32 mult, u32 *__restrict__ err)
 {
-    u32 s = slot_of(slot_hash(kmer), T.slots);
-    u64 prev = atomicCAS(&T.tab[s].key, EMPTY_KEY, kmer);
-    return table_insert_resume(T, kmer, s, prev, mult, err);
+    u32 s = slot_of(h, T.slots);
+    u64 prev = atomicCAS(&T.tab[s].key, EMPTY_H, h);
+    return table_insert_resume(T, h, s, prev, mult, err);
 }
 
 // warp-reduce a per-thread tally into one global counter
@@ -78,11 +79,11 @@ __device__ __forceinline__ void tally(u64 *__restrict__ g, u32 v)
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(g, (u64)v);
 }
 
-__global__ void k_table_clear(Slot *__restrict__ tab, u64 slots)
+__global__ void k_table_clear(Slot *__restrict__ tab, u64 slots, u64 empty)
 {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u64 step = (u64)gridDim.x * blockDim.x;
-    ulonglong2 e; e.x = EMPTY_KEY; e.y = 0;
+    ulonglong2 e; e.x = empty; e.y = 0;
     for (; i < slots; i += step) reinterpret_cast<ulonglong2*>(tab)[i] = e;
 }
 
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) k_count_direct(ReadsView rv, int k, int s
         u64 g = it * step + (u64)blockIdx.x * blockDim.x + threadIdx.x;
         ChunkInfo ci;
         if (locate_chunk(rv, g, k, ci))
-            foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32, int) { nd += table_insert(T, x, 1u, err); });
+            foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32, int) { nd += table_insert(T, mix64(x), 1u, err); });
     }
     tally(distinct, nd);
 }
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256) k_count_array(const u64 *__restrict__ kme
         }
 #pragma unroll
         for (int j = 0; j < COUNT_ILP; ++j)
-            if (mult[j]) { s[j] = slot_of(slot_hash(cur[j]), T.slots); prev[j] = atomicCAS(&T.tab[s[j]].key, EMPTY_KEY, cur[j]); }
+            if (mult[j]) { s[j] = slot_of(cur[j], T.slots); prev[j] = atomicCAS(&T.tab[s[j]].key, EMPTY_H, cur[j]); }
         // next tile's k-mers are requested before the atomics above are waited on
         u64 tn = t + gridDim.x;
         if (tn < ntiles)
@@ -156,16 +157,16 @@ __global__ void __launch_bounds__(256) k_table_collect(Slot *__restrict__ tab, u
     const u32 step = gridDim.x * blockDim.x;
     const u32 rounds = (slots + step - 1) / step;
     const int lane = threadIdx.x & 31;
-    ulonglong2 e; e.x = EMPTY_KEY; e.y = 0;
+    ulonglong2 e; e.x = EMPTY_H; e.y = 0;
     for (u32 it = 0; it < rounds; ++it)
     {
         u32 i = it * step + blockIdx.x * blockDim.x + threadIdx.x;
-        bool ok = false; u64 key = EMPTY_KEY; u32 cnt = 0;
+        bool ok = false; u64 key = EMPTY_H; u32 cnt = 0;
         if (i < slots)
         {
             ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(tab + i));
             key = v.x; cnt = (u32)v.y;
-            if (key != EMPTY_KEY) { reinterpret_cast<ulonglong2*>(tab)[i] = e; ok = cnt >= lower && cnt <= upper; }
+            if (key != EMPTY_H) { reinterpret_cast<ulonglong2*>(tab)[i] = e; ok = cnt >= lower && cnt <= upper; }
         }
         unsigned m = __ballot_sync(0xffffffffu, ok);
         if (!m) continue;
@@ -175,104 +176,6 @@ __global__ void __launch_bounds__(256) k_table_collect(Slot *__restrict__ tab, u
         if (lane == 0) { base = atomicAdd(&counters[0], (u64)__popc(m)); atomicAdd(&counters[1], (u64)sum); }
         base = __shfl_sync(0xffffffffu, base, 0);
         if (ok) { u64 o = base + __popc(m & ((1u << lane) - 1)); if (o < cap) { out_key[o] = key; out_cnt[o] = cnt; } }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// partitioning
-// partition = high bits of the hash (the table slot uses the low bits)
-__device__ __forceinline__ u32 part_of(u64 x, u32 P) { return (u32)__umul64hi(slot_hash(x), (u64)P); }
-
-__global__ void __launch_bounds__(256) k_part_hist(ReadsView rv, int k, int stride, u32 P, u64 *__restrict__ ghist)
-{
-    extern __shared__ u32 s_hist[];
-    for (u32 i = threadIdx.x; i < P; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    u64 step = (u64)gridDim.x * blockDim.x;
-    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < rv.nchunks; g += step)
-    {
-        ChunkInfo ci;
-        if (!locate_chunk(rv, g, k, ci)) continue;
-        foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32, int) { atomicAdd(&s_hist[part_of(x, P)], 1u); });
-    }
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < P; i += blockDim.x) if (s_hist[i]) atomicAdd(&ghist[i], (u64)s_hist[i]);
-}
-
-// One tile = SCATTER_BLOCK chunks (SCATTER_BLOCK*32 k-mers).  Shared memory: sorted[tile k-mers] | gbase[P] | cnt[P] | off[P+1]
-static constexpr int SCATTER_BLOCK = 256;
-__global__ void __launch_bounds__(SCATTER_BLOCK) k_part_scatter(ReadsView rv, int k, int stride, u32 P,
-                                                                u64 *__restrict__ gcursor /*[P] running write cursors, pre-set to partition starts*/,
-                                                                u64 *__restrict__ out)
-{
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    u64 *s_sorted = reinterpret_cast<u64*>(s_raw);            // [SCATTER_BLOCK*CHUNK]
-    u64 *s_gbase = s_sorted + SCATTER_BLOCK * CHUNK;          // [P]
-    u32 *s_cnt = reinterpret_cast<u32*>(s_gbase + P);         // [P]
-    u32 *s_off = s_cnt + P;                                   // [P+1]
-    __shared__ u32 s_total;
-
-    u64 ntiles = (rv.nchunks + SCATTER_BLOCK - 1) / SCATTER_BLOCK;
-    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-    {
-        for (u32 i = threadIdx.x; i < P; i += blockDim.x) s_cnt[i] = 0;
-        __syncthreads();
-        u64 g = tile * SCATTER_BLOCK + threadIdx.x;
-        ChunkInfo ci; bool have = locate_chunk(rv, g, k, ci);
-        // phase A: tile histogram
-        if (have) foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32, int) { atomicAdd(&s_cnt[part_of(x, P)], 1u); });
-        __syncthreads();
-        // exclusive scan of s_cnt -> s_off (P <= 4096: serial per-thread blocks + warp 0 scan)
-        {
-            // each thread scans a contiguous strip of ceil(P/blockDim) entries
-            u32 per = (P + blockDim.x - 1) / blockDim.x;
-            u32 b = threadIdx.x * per, e = min(b + per, P);
-            u32 sum = 0;
-            for (u32 i = b; i < e; ++i) sum += s_cnt[i];
-            // block exclusive scan of `sum` via shared memory (reuse s_off[0..blockDim) temporarily is unsafe; use warp shuffles)
-            __shared__ u32 s_warp[SCATTER_BLOCK / 32];
-            u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-            u32 incl = sum;
-            for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += t; }
-            if (lane == 31) s_warp[w] = incl;
-            __syncthreads();
-            if (w == 0)
-            {
-                u32 v = lane < SCATTER_BLOCK / 32 ? s_warp[lane] : 0;
-                u32 iv = v;
-                for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= (u32)o) iv += t; }
-                if (lane < SCATTER_BLOCK / 32) s_warp[lane] = iv - v;
-                if (lane == SCATTER_BLOCK / 32 - 1) s_total = iv;
-            }
-            __syncthreads();
-            u32 run = s_warp[w] + incl - sum;
-            for (u32 i = b; i < e; ++i) { s_off[i] = run; run += s_cnt[i]; }
-            if (threadIdx.x == 0) s_off[P] = s_total;
-        }
-        __syncthreads();
-        // reserve global space per partition; reset s_cnt as fill cursors
-        for (u32 i = threadIdx.x; i < P; i += blockDim.x)
-        {
-            u32 c = s_cnt[i];
-            s_gbase[i] = c ? atomicAdd(&gcursor[i], (u64)c) : 0;
-            s_cnt[i] = 0;
-        }
-        __syncthreads();
-        // phase B: place k-mers sorted by partition
-        if (have) foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32, int) {
-            u32 p = part_of(x, P); u32 r = atomicAdd(&s_cnt[p], 1u); s_sorted[s_off[p] + r] = x; });
-        __syncthreads();
-        // phase C: coalesced runs, one warp per partition
-        {
-            u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-            for (u32 p = w; p < P; p += nw)
-            {
-                u32 b = s_off[p], e = s_off[p + 1];
-                u64 dst = s_gbase[p];
-                for (u32 i = b + lane; i < e; i += 32) out[dst + (i - b)] = s_sorted[i];
-            }
-        }
-        __syncthreads();
     }
 }
 

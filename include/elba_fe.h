@@ -62,7 +62,7 @@ typedef struct {
     int32_t lower;          /* LOWER_KMER_FREQ, >= 2 (with 1 the reference depends on Bloom false positives) */
     int32_t upper;          /* UPPER_KMER_FREQ, lower..65535 (include/compiletime.h:21) */
     int32_t device;         /* CUDA device ordinal */
-    int32_t num_partitions; /* 0 = choose (count table of one partition kept L2-sized); 1 = direct, no partition pass */
+    int32_t num_partitions; /* level-1 k-mer partitions: 0 = choose (~1 M instances each); 1 = direct (one global table, no partition pass); 2..4096 */
     int32_t flags;          /* ELBA_FE_FLAG_* */
 } elba_fe_config;
 
@@ -119,7 +119,8 @@ typedef struct {
     uint64_t nnzB;          /* after Prune(numshared <= 1) */
     uint64_t partitions;    /* k-mer partitions actually used */
     uint64_t table_slots;   /* slots of one count table */
-    uint64_t reserved[5];
+    uint64_t slow_partitions; /* partitions recounted with the global-table kernel (sub-bucket overflow: heavy hitters) */
+    uint64_t reserved[4];
 } elba_fe_sizes_t;
 int elba_fe_sizes(elba_fe_ctx *ctx, elba_fe_sizes_t *out);
 

@@ -155,6 +155,23 @@ def test_heavy_rows_and_hot_kmers():
     assert ref.nnzB > 1800 * 1600, "test must overflow the 2048-slot table"
 
 
+def test_skewed_partitions():
+    """Heavy hitters: poly-A reads put > 1 M instances of ONE k-mer into one level-1 partition.  The optimistic
+    partition layout overflows (exact-histogram layout), then that partition's sub-bucket overflows (global-table
+    recount).  Results must not change."""
+    from elba_b200.dnabuffer import DnaBuffer
+    from elba_b200.synth import make_dnabuffer
+    from oracle import oracle as O
+    base = make_dnabuffer(genome_len=40_000, n_reads=120, mean_len=5000, sd_len=500, err=0.08, seed=21)
+    seqs = [base.read_ascii(i) for i in range(base.size())] + ["A" * 20000] * 60 + ["AC" * 6000] * 3
+    dna = DnaBuffer.from_strings(seqs)
+    ref = O.run(dna, 17, 2, 8)
+    for parts in (0, 8, 64):
+        out = _run_cuda(dna, 17, 2, 8, parts=parts)
+        _compare(out, ref, f"skew parts={parts}")
+        assert out["sizes"]["slow_partitions"] >= 1
+
+
 def test_stride_and_single_seed():
     from elba_b200.synth import make_dnabuffer
     from oracle import oracle as O

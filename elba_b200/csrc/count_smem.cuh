@@ -70,9 +70,11 @@ __device__ __forceinline__ u32 block_exclusive_scan_256(u32 v, u32 *s_warp /*[9]
     return s_warp[w] + incl - v;
 }
 
-// out: partition p occupies [part_start[p], part_start[p+1]); part_cnt[p] running fill (zeroed by the host).
+// out: partition p occupies [part_start[p], part_start[p+1]) — or, UNIFORM, [p * cap1, (p + 1) * cap1);
+// part_cnt[p] running fill (zeroed by the host).
 // flags[0] |= 1 when a partition region overflows (the host then lays the regions out from an exact histogram).
-__global__ void __launch_bounds__(S1_THREADS, 2) k_scatter1(ReadsView rv, int k, int stride, u32 P1,
+template <bool UNIFORM>
+__global__ void __launch_bounds__(S1_THREADS, 2) k_scatter1(ReadsView rv, int k, int stride, u32 P1, u32 cap1,
                                                             const u64 *__restrict__ part_start, u32 *__restrict__ part_cnt,
                                                             u64 *__restrict__ out, u32 *__restrict__ flags)
 {
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(S1_THREADS, 2) k_scatter1(ReadsView rv, int k,
 
     const u32 tid = threadIdx.x;
     const u64 ntiles = (rv.nchunks + S1_THREADS - 1) / S1_THREADS;
-    const u32 per = (P1 + S1_THREADS - 1) / S1_THREADS;
+    constexpr int PER = MAX_P1 / S1_THREADS;                      // partitions a thread owns: tid, tid+256, ...
     for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
     {
         for (u32 i = tid; i < P1; i += S1_THREADS) s_off[i] = 0;
@@ -99,19 +101,19 @@ __global__ void __launch_bounds__(S1_THREADS, 2) k_scatter1(ReadsView rv, int k,
                 u32 r = atomicAdd(&s_off[part1(h, P1)], 1u);
                 hk[s] = h; rk[s >> 1] |= r << ((s & 1) * 16); vmask |= 1u << s; });
         __syncthreads();
-        // offsets: thread t owns partitions t, t+256, ... (any order is a valid packing; the copy-out recomputes p)
-        u32 sum = 0;
-        for (u32 j = 0; j < per; ++j) { u32 p = tid + j * S1_THREADS; if (p < P1) sum += s_off[p]; }
+        // offsets (any order of the partitions inside the tile is a valid packing; the copy-out recomputes p from h).
+        // The global reservations of a thread's partitions go out back to back, nothing waits in between.
+        u32 c[PER], base[PER]; u32 sum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) { u32 p = tid + j * S1_THREADS; c[j] = p < P1 ? s_off[p] : 0u; sum += c[j]; }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) base[j] = c[j] ? atomicAdd(&part_cnt[tid + j * S1_THREADS], c[j]) : 0u;
         u32 run = block_exclusive_scan_256(sum, s_warp);
-        for (u32 j = 0; j < per; ++j)
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
         {
             u32 p = tid + j * S1_THREADS;
-            if (p < P1)
-            {
-                u32 c = s_off[p];
-                u32 base = c ? atomicAdd(&part_cnt[p], c) : 0u;
-                s_off[p] = run; s_delta[p] = base - run; run += c;
-            }
+            if (p < P1) { s_off[p] = run; s_delta[p] = base[j] - run; run += c[j]; }
         }
         const u32 total = s_warp[8];
         __syncthreads();
@@ -119,13 +121,21 @@ __global__ void __launch_bounds__(S1_THREADS, 2) k_scatter1(ReadsView rv, int k,
         for (int s = 0; s < CHUNK; ++s)
             if (vmask & (1u << s)) { u64 h = hk[s]; s_sorted[s_off[part1(h, P1)] + ((rk[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu)] = h; }
         __syncthreads();
+#pragma unroll 4
         for (u32 i = tid; i < total; i += S1_THREADS)
         {
             u64 h = s_sorted[i];
             u32 p = part1(h, P1);
             u32 d = s_delta[p] + i;
-            u64 ps = __ldg(part_start + p), pe = __ldg(part_start + p + 1);
-            if (ps + d < pe) out[ps + d] = h; else atomicOr(flags, 1u);
+            if (UNIFORM)
+            {
+                if (d < cap1) out[(u64)p * cap1 + d] = h; else atomicOr(flags, 1u);
+            }
+            else
+            {
+                u64 ps = __ldg(part_start + p), pe = __ldg(part_start + p + 1);
+                if (ps + d < pe) out[ps + d] = h; else atomicOr(flags, 1u);
+            }
         }
         __syncthreads();
     }
@@ -177,7 +187,8 @@ __device__ __forceinline__ u32 upper_seg(const u32 *__restrict__ a, u32 lo, u32 
 
 // partitions [g0, g1) -> scratch: sub-bucket b (global numbering bucket_start[p] + q) of the group lives at
 // scratch[(b - bucket_start[g0]) * BUCKET_CAP ...], fill count bfill[b].  pflags[p] = 1 when a sub-bucket overflows.
-__global__ void __launch_bounds__(S2_THREADS) k_scatter2(PartInput pi, PartPlan pl, u32 P1_total, u32 part_id_base, u32 g0, u32 g1,
+template <bool ONE_SLAB>
+__global__ void __launch_bounds__(S2_THREADS) k_scatter2(PartInput pi, PartPlan pl, u32 P1_total, u32 g0, u32 g1,
                                                          u64 *__restrict__ scratch, u32 *__restrict__ bfill, u32 *__restrict__ pflags)
 {
     __shared__ __align__(16) u64 s_sorted[S2_TILE];
@@ -187,51 +198,57 @@ __global__ void __launch_bounds__(S2_THREADS) k_scatter2(PartInput pi, PartPlan 
     const u32 tid = threadIdx.x;
     const u32 t0 = __ldg(pl.tile_start + g0), t1 = __ldg(pl.tile_start + g1);
     const u32 b0 = __ldg(pl.bucket_start + g0);
+    constexpr int PER = MAX_P2 / S2_THREADS;
     for (u32 w = t0 + blockIdx.x; w < t1; w += gridDim.x)
     {
         const u32 p = upper_seg(pl.tile_start, g0, g1, w);
         const u32 n = __ldg(pl.n + p), P2 = __ldg(pl.p2 + p);
         const u32 first = (w - __ldg(pl.tile_start + p)) * S2_TILE;
-        const u32 Pglob = part_id_base + p;            // this partition's level-1 digit (fixed for all its instances)
-        (void)Pglob;
+        const u32 bs = __ldg(pl.bucket_start + p);
         for (u32 i = tid; i < P2; i += S2_THREADS) s_off[i] = 0;
         __syncthreads();
         u64 hk[S2_PER]; u32 rk[S2_PER / 2]; u32 vmask = 0;
 #pragma unroll
         for (int s = 0; s < S2_PER / 2; ++s) rk[s] = 0;
-        // logical index -> (slab, offset)
-        const u64 pstart = __ldg(pi.part_start + p);
-#pragma unroll
-        for (int s = 0; s < S2_PER; ++s)
+        const u64 *src = pi.in + __ldg(pi.part_start + p);
+        const u32 left = n > first ? n - first : 0u;                // instances of this tile and after
+        if (ONE_SLAB)
         {
-            u32 i = first + s * S2_THREADS + tid;
-            hk[s] = 0;
-            if (i < n)
+            const u64 *q = src + first + tid;
+#pragma unroll
+            for (int s = 0; s < S2_PER; ++s)
+                if ((u32)(s * S2_THREADS) + tid < left) { hk[s] = __ldcs(q + s * S2_THREADS); vmask |= 1u << s; }
+        }
+        else
+        {
+#pragma unroll
+            for (int s = 0; s < S2_PER; ++s)
             {
-                u32 j = 0, c = __ldg(pi.cnt + p);
-                while (i >= c) { i -= c; ++j; c = __ldg(pi.cnt + (size_t)j * pi.P + p); }
-                hk[s] = __ldcs(pi.in + (size_t)j * pi.slab_stride + pstart + i);
-                vmask |= 1u << s;
+                u32 i = first + s * S2_THREADS + tid;
+                if (i < n)
+                {
+                    u32 j = 0, cc = __ldg(pi.cnt + p);
+                    while (i >= cc) { i -= cc; ++j; cc = __ldg(pi.cnt + (size_t)j * pi.P + p); }
+                    hk[s] = __ldcs(src + (size_t)j * pi.slab_stride + i);
+                    vmask |= 1u << s;
+                }
             }
         }
 #pragma unroll
         for (int s = 0; s < S2_PER; ++s)
             if (vmask & (1u << s)) { u32 r = atomicAdd(&s_off[part2(hk[s], P1_total, P2)], 1u); rk[s >> 1] |= r << ((s & 1) * 16); }
         __syncthreads();
-        u32 sum = 0;
+        u32 c[PER], base[PER]; u32 sum = 0;
 #pragma unroll
-        for (u32 j = 0; j < MAX_P2 / S2_THREADS; ++j) { u32 q = tid + j * S2_THREADS; if (q < P2) sum += s_off[q]; }
+        for (int j = 0; j < PER; ++j) { u32 q = tid + j * S2_THREADS; c[j] = q < P2 ? s_off[q] : 0u; sum += c[j]; }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) base[j] = c[j] ? atomicAdd(&bfill[bs + tid + j * S2_THREADS], c[j]) : 0u;
         u32 run = block_exclusive_scan_256(sum, s_warp);
 #pragma unroll
-        for (u32 j = 0; j < MAX_P2 / S2_THREADS; ++j)
+        for (int j = 0; j < PER; ++j)
         {
             u32 q = tid + j * S2_THREADS;
-            if (q < P2)
-            {
-                u32 c = s_off[q];
-                u32 base = c ? atomicAdd(&bfill[__ldg(pl.bucket_start + p) + q], c) : 0u;
-                s_off[q] = run; s_delta[q] = base - run; run += c;
-            }
+            if (q < P2) { s_off[q] = run; s_delta[q] = base[j] - run; run += c[j]; }
         }
         const u32 total = s_warp[8];
         __syncthreads();
@@ -239,13 +256,14 @@ __global__ void __launch_bounds__(S2_THREADS) k_scatter2(PartInput pi, PartPlan 
         for (int s = 0; s < S2_PER; ++s)
             if (vmask & (1u << s)) s_sorted[s_off[part2(hk[s], P1_total, P2)] + ((rk[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu)] = hk[s];
         __syncthreads();
-        const u64 sbase = (u64)(__ldg(pl.bucket_start + p) - b0) * BUCKET_CAP;
+        u64 *dst = scratch + (u64)(bs - b0) * BUCKET_CAP;
+#pragma unroll 4
         for (u32 i = tid; i < total; i += S2_THREADS)
         {
             u64 h = s_sorted[i];
             u32 q = part2(h, P1_total, P2);
             u32 d = s_delta[q] + i;
-            if (d < BUCKET_CAP) scratch[sbase + (u64)q * BUCKET_CAP + d] = h; else pflags[p] = 1u;
+            if (d < BUCKET_CAP) dst[q * BUCKET_CAP + d] = h; else pflags[p] = 1u;
         }
         __syncthreads();
     }
@@ -294,8 +312,8 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_count_buckets(PartPlan pl, u3
         {
             const u64 h = x[j];
             if (h == EMPTY_H) continue;
-            u32 s = (u32)h & (BUCKET_SLOTS - 1);
-            while (true)
+            u32 s = (u32)h & (BUCKET_SLOTS - 1), step = 0;
+            while (true)                                           // triangular probing: every slot once, short tails
             {
                 u64 cur = reinterpret_cast<volatile u64*>(s_key)[s];
                 if (cur == h) break;
@@ -304,7 +322,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_count_buckets(PartPlan pl, u3
                     u64 prev = atomicCAS(&s_key[s], EMPTY_H, h);
                     if (prev == EMPTY_H || prev == h) break;
                 }
-                s = (s + 1) & (BUCKET_SLOTS - 1);
+                s = (s + ++step) & (BUCKET_SLOTS - 1);
             }
             atomicAdd(&s_cnt[s], 1u);
         }

@@ -56,7 +56,7 @@ struct elba_fe_ctx
     DevBuf plan, bfill, pflags, scratch[2];
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     u64 scratch_mb = 64;
-    u64 lut_mask = 0; u64 rel_cap = 0; u32 filter_mask = 0;
+    u32 lut_slots = 0; u64 rel_cap = 0; u32 filter_words = 0; u64 cand_cap = 0;
     // A
     DevBuf seed_key, seed_pos, seed_key2, seed_pos2, idx, a_key, a_rowptr, a_col, a_pos, at_key, at_key2, at_pos2, at_colptr, at_row, at_pos, prod;
     int col_bits = 1, read_bits = 1;
@@ -204,7 +204,8 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (const char *e = getenv("ELBA_FE_SCRATCH_MB")) { long v = atol(e); if (v >= 8 && v <= 65536) ctx->scratch_mb = (u64)v; }
     // opt in to large dynamic shared memory
-    cudaFuncSetAttribute(k_scatter1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S1_TILE + 2 * sizeof(u32) * MAX_P1));
+    cudaFuncSetAttribute(k_scatter1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S1_TILE + 2 * sizeof(u32) * MAX_P1));
+    cudaFuncSetAttribute(k_scatter1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S1_TILE + 2 * sizeof(u32) * MAX_P1));
     cudaFuncSetAttribute(k_count_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS));
     *out = ctx;
     return 0;
@@ -321,7 +322,8 @@ int elba_fe_count(elba_fe_ctx *ctx)
 
     const u64 Ms = ctx->Ms;
     // level-1 partitions of about PART_TARGET instances (8 MB of h values each)
-    const u64 PART_TARGET = 1ull << 20;
+    u64 PART_TARGET = 2ull << 20;
+    if (const char *e = getenv("ELBA_FE_PART_TARGET")) { long long v = atoll(e); if (v >= 4096) PART_TARGET = (u64)v; }
     u32 P1 = (u32)ctx->cfg.num_partitions;
     const bool direct = (P1 == 1) || (P1 == 0 && Ms <= 65536);
     if (P1 == 0) P1 = (u32)std::min<u64>(MAX_P1, std::max<u64>(1, (Ms + PART_TARGET - 1) / PART_TARGET));
@@ -373,7 +375,8 @@ int elba_fe_count(elba_fe_ctx *ctx)
                 CK(cudaMemcpyAsync(ctx->phist.p, start.data(), sizeof(u64) * (P1 + 1), cudaMemcpyHostToDevice, st));
                 CK(cudaMemsetAsync(ctx->pcursor.p, 0, sizeof(u32) * (P1 + 1), st));
                 CK(cudaMemsetAsync(d_flag1, 0, 4, st));
-                k_scatter1<<<grid_for(ctx, 2), S1_THREADS, smem1, st>>>(rv, k, stride, P1, ctx->phist.as<u64>(), ctx->pcursor.as<u32>(), ctx->partbuf.as<u64>(), d_flag1);
+                if (lay == 0) k_scatter1<true><<<grid_for(ctx, 2), S1_THREADS, smem1, st>>>(rv, k, stride, P1, (u32)cap1, ctx->phist.as<u64>(), ctx->pcursor.as<u32>(), ctx->partbuf.as<u64>(), d_flag1);
+                else          k_scatter1<false><<<grid_for(ctx, 2), S1_THREADS, smem1, st>>>(rv, k, stride, P1, 0u, ctx->phist.as<u64>(), ctx->pcursor.as<u32>(), ctx->partbuf.as<u64>(), d_flag1);
                 CKL(); LAUNCHED(ctx);
                 u32 flag = 0;
                 CK(cudaMemcpyAsync(cnt.data(), ctx->pcursor.p, sizeof(u32) * P1, cudaMemcpyDeviceToHost, st));
@@ -431,7 +434,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
                 if (nt)
                 {
                     cudaStream_t s2 = which ? ctx->aux : st; used_aux |= which != 0;
-                    k_scatter2<<<std::min<u32>(nt, grid_for(ctx, 5)), S2_THREADS, 0, s2>>>(pi, pl, P1, 0, g0, g1, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ctx->pflags.as<u32>());
+                    k_scatter2<true><<<std::min<u32>(nt, grid_for(ctx, 5)), S2_THREADS, 0, s2>>>(pi, pl, P1, g0, g1, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ctx->pflags.as<u32>());
                     CKL(); LAUNCHED(ctx);
                     k_count_buckets<<<std::min<u32>(nb, grid_for(ctx, 2)), CB_THREADS, smemc, s2>>>(pl, g0, g1, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ctx->pflags.as<u32>(),
                         lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
@@ -473,18 +476,19 @@ int elba_fe_count(elba_fe_ctx *ctx)
     CK(ctx->rel_key_s.ensure(sizeof(u64) * std::max<u64>(R, 1))); CK(ctx->rel_cnt_s.ensure(sizeof(u32) * std::max<u64>(R, 1)));
     int rc = sort_pairs(ctx, ctx->rel_key.as<u64>(), ctx->rel_key_s.as<u64>(), ctx->rel_cnt.as<u32>(), ctx->rel_cnt_s.as<u32>(), R, 64 - 2 * k, 64);
     if (rc) return rc;
-    // lookup table k-mer -> column id, fronted by a blocked Bloom filter small enough to live in L2
-    u64 lslots = next_pow2(std::max<u64>(2 * R, 1024));
+    // k-mer -> column id table in HBM, fronted by a blocked Bloom filter sized to stay L2-resident
+    u64 lslots = std::max<u64>(R + R / 2 + 64, 1024);
+    if (lslots >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "too many reliable k-mers for the column table");
     CK(ctx->lut.ensure(sizeof(Slot) * lslots));
-    ctx->lut_mask = lslots - 1;
-    u64 bits_per_key = (R * 2 <= (32ull << 20)) ? 16 : 8;
-    u64 fwords = next_pow2(std::max<u64>(R * bits_per_key / 64, 1024));
+    ctx->lut_slots = (u32)lslots;
+    const u64 bits_per_key = (R * 2 <= (32ull << 20)) ? 16 : (R * 3 / 2 <= (64ull << 20)) ? 12 : 8;
+    u64 fwords = std::max<u64>((R * bits_per_key + 63) / 64, 1024);
     CK(ctx->filter.ensure(8 * fwords));
-    ctx->filter_mask = (u32)(fwords - 1);
+    ctx->filter_words = (u32)fwords;
     CK(cudaMemsetAsync(ctx->filter.p, 0, 8 * fwords, st));
     k_table_clear<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->lut.as<Slot>(), lslots, EMPTY_KEY); CKL(); LAUNCHED(ctx);
-    if (R) { k_lookup_build<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), (u32)R, ctx->lut.as<Slot>(), ctx->lut_mask,
-                                                       ctx->filter.as<u64>(), ctx->filter_mask); CKL(); LAUNCHED(ctx); }
+    if (R) { k_lookup_build<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), (u32)R, ctx->lut.as<Slot>(), ctx->lut_slots,
+                                                       ctx->filter.as<u64>(), ctx->filter_words); CKL(); LAUNCHED(ctx); }
     CK(cudaEventRecord(ctx->ev[3], st));
     ctx->phase = 2;
     return 0;
@@ -508,20 +512,36 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     const u64 cap = std::max<u64>(npre, 1);
     CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); CK(ctx->seed_key2.ensure(8 * cap)); CK(ctx->seed_pos2.ensure(4 * cap));
     // sweep 2: every instance of a reliable k-mer -> (read, column, pos)
+    u64 emitted = 0;
     {
         EventPair &lp = next_pair(ctx->lev, ctx->lev_used);
         CK(cudaEventRecord(lp.a, st));
         if (ctx->nchunks && R)
         {
-            k_emit_seeds<<<grid_for(ctx, 8), 256, 0, st>>>(rv, ctx->cfg.k, ctx->cfg.stride, ctx->lut.as<Slot>(), ctx->lut_mask,
-                ctx->filter.as<u64>(), ctx->filter_mask, ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, npre, cb);
-            CKL(); LAUNCHED(ctx);
+            // candidates = true instances + filter false positives (a few % of all instances); exact size after one try
+            u64 ccap = std::max<u64>(ctx->cand_cap, npre + std::max<u64>(ctx->Ms / 32, 1u << 16));
+            for (int attempt = 0; attempt < 2; ++attempt)
+            {
+                CK(ctx->cand.ensure(sizeof(Candidate) * ccap));
+                ctx->cand_cap = ccap;
+                CK(cudaMemsetAsync(d_ctr, 0, 64, st));
+                k_probe_filter<<<grid_for(ctx, 2), PF_THREADS, 0, st>>>(rv, ctx->cfg.k, ctx->cfg.stride, ctx->filter.as<u64>(), ctx->filter_words,
+                    ctx->cand.as<Candidate>(), d_ctr + 1, ccap);
+                CKL(); LAUNCHED(ctx);
+                u64 ncand = 0;
+                CK(cudaMemcpyAsync(&ncand, d_ctr + 1, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                ctx->sz.candidates = ncand;
+                if (ncand > ccap) { if (attempt) return fail(ctx, ELBA_FE_ERR_CUDA, "candidate list overflow after resize"); ccap = ncand; continue; }
+                if (ncand) { k_resolve<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->cand.as<Candidate>(), ncand, ctx->lut.as<Slot>(), ctx->lut_slots,
+                                 ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, npre, cb); CKL(); LAUNCHED(ctx); }
+                break;
+            }
         }
         CK(cudaEventRecord(lp.b, st));
+        CK(cudaMemcpyAsync(&emitted, d_ctr, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
     }
-    u64 emitted = 0;
-    CK(cudaMemcpyAsync(&emitted, d_ctr, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
     if (emitted != npre) { char b[160]; snprintf(b, sizeof b, "seed emission produced %llu triples, counting promised %llu", (unsigned long long)emitted, (unsigned long long)npre); return fail(ctx, ELBA_FE_ERR_CUDA, b); }
 
     int rc;

@@ -180,83 +180,118 @@ __global__ void __launch_bounds__(256) k_table_collect(Slot *__restrict__ tab, u
 }
 
 // ------------------------------------------------------------------------------------------
-// reliable k-mer -> column id: a hash table in HBM fronted by an L2-resident blocked Bloom filter (two bits of
-// one 64-bit word per k-mer).  In sweep 2 almost every k-mer instance is NOT reliable; the filter answers those
-// from L2 and only ~2-5 % false positives plus the true hits touch the table in DRAM.
-__device__ __forceinline__ void filter_bits(u64 h, u32 fmask, u32 &word, u64 &bits)
-{
-    word = (u32)(h >> 32) & fmask;
-    bits = (1ull << (h & 63)) | (1ull << ((h >> 6) & 63));
-}
+// Sweep 2: which instances belong to a reliable k-mer, and to which column.
+//
+// v1 probed a filter and then a DRAM-resident table per instance inside one divergent loop: 2-3 lanes of a warp
+// waiting on DRAM at a time (profiles/r1_count_v1.md, 14.7 ps per instance).  Now two dense stages:
+//   k_probe_filter   every instance: h = mix64(k-mer), one load from an L2-resident blocked Bloom filter
+//                    (3 bits in one 64-bit word).  The 32 k-mers of a chunk stay in registers, loads go out in
+//                    batches of 8 with no branch between them; hits become 16-byte candidate records.
+//   k_resolve        every candidate (a few % of the instances): one thread each, all lanes busy, probes the
+//                    k-mer -> column table in HBM; false positives of the filter are dropped here.
+__device__ __forceinline__ u32 filter_word(u64 h, u32 fwords) { return __umulhi((u32)(h >> 32), fwords); }
+__device__ __forceinline__ u64 filter_bits(u64 h) { return (1ull << (h & 63)) | (1ull << ((h >> 6) & 63)) | (1ull << ((h >> 12) & 63)); }
+__device__ __forceinline__ u32 lut_slot(u64 h, u32 lslots) { return __umulhi((u32)h, lslots); }
 
-__global__ void k_lookup_build(const u64 *__restrict__ keys, const u32 *__restrict__ cnts, u32 R, Slot *__restrict__ tab, u64 mask,
-                               u64 *__restrict__ filter, u32 fmask)
+__global__ void k_lookup_build(const u64 *__restrict__ keys, const u32 *__restrict__ cnts, u32 R, Slot *__restrict__ tab, u32 lslots,
+                               u64 *__restrict__ filter, u32 fwords)
 {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
     u64 x = keys[i];
-    u64 h = slot_hash(x);
-    u32 w; u64 bits; filter_bits(h, fmask, w, bits);
-    atomicOr(&filter[w], bits);
-    u64 s = h & mask;
+    u64 h = mix64(x);
+    atomicOr(&filter[filter_word(h, fwords)], filter_bits(h));
+    u32 s = lut_slot(h, lslots);
     while (true)
     {
         u64 prev = atomicCAS(&tab[s].key, EMPTY_KEY, x);
         if (prev == EMPTY_KEY) { tab[s].cnt = cnts[i]; tab[s].aux = i; return; }
-        s = (s + 1) & mask;
+        s = (s + 1 == lslots) ? 0 : s + 1;
     }
 }
 
-__device__ __forceinline__ bool lookup(const Slot *__restrict__ tab, u64 mask, const u64 *__restrict__ filter, u32 fmask, u64 x, u32 &col)
-{
-    u64 h = slot_hash(x);
-    u32 w; u64 bits; filter_bits(h, fmask, w, bits);
-    if ((__ldg(filter + w) & bits) != bits) return false;
-    u64 s = h & mask;
-    while (true)
-    {
-        ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tab + s));
-        if (v.x == x) { col = (u32)(v.y >> 32); return true; }
-        if (v.x == EMPTY_KEY) return false;
-        s = (s + 1) & mask;
-    }
-}
+struct __align__(16) Candidate { u64 kmer; u32 pos; u32 read; };
 
-// Sweep 2.  Every instance of a reliable k-mer becomes one triple: key = (local read << col_bits | column), val = pos.
-// A thread first marks its hits (bitmask over its chunk), the warp reserves output space with ONE atomic,
-// then the hits are recomputed from the staged bases and written.
-__global__ void __launch_bounds__(256) k_emit_seeds(ReadsView rv, int k, int stride, const Slot *__restrict__ tab, u64 mask,
-                                                    const u64 *__restrict__ filter, u32 fmask,
-                                                    u64 *__restrict__ out_key, u32 *__restrict__ out_pos, u64 *__restrict__ cursor, u64 cap, int col_bits)
+static constexpr int PF_THREADS = 256;
+__global__ void __launch_bounds__(PF_THREADS, 2) k_probe_filter(ReadsView rv, int k, int stride, const u64 *__restrict__ filter, u32 fwords,
+                                                                Candidate *__restrict__ out, u64 *__restrict__ cursor, u64 cap)
 {
-    u64 step = (u64)gridDim.x * blockDim.x;
-    u64 rounds = (rv.nchunks + step - 1) / step;
-    int lane = threadIdx.x & 31;
+    const u64 step = (u64)gridDim.x * blockDim.x;
+    const u64 rounds = (rv.nchunks + step - 1) / step;
+    const int lane = threadIdx.x & 31;
     for (u64 it = 0; it < rounds; ++it)
     {
-        u64 g = it * step + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-        ChunkInfo ci; bool have = locate_chunk(rv, g, k, ci);
+        const u64 g = it * step + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+        ChunkInfo ci; const bool have = locate_chunk(rv, g, k, ci);
+        u64 x[CHUNK]; u32 vmask = 0;
+        if (have) foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 c, u32, int s) { x[s] = c; vmask |= 1u << s; });
         u32 hits = 0;
-        if (have) foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32, int s) { u32 c; if (lookup(tab, mask, filter, fmask, x, c)) hits |= 1u << s; });
-        u32 n = __popc(hits);
+#pragma unroll
+        for (int b = 0; b < CHUNK; b += 8)
+        {
+            u64 w[8], bits[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+            {
+                u64 h = mix64(x[b + j]);
+                bits[j] = filter_bits(h);
+                w[j] = (vmask >> (b + j)) & 1u ? __ldg(filter + filter_word(h, fwords)) : 0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hits |= ((w[j] & bits[j]) == bits[j] ? 1u : 0u) << (b + j);
+        }
+        hits &= vmask;
+        const u32 n = __popc(hits);
         u32 incl = n;
+#pragma unroll
         for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        const u32 total = __shfl_sync(0xffffffffu, incl, 31);
         if (total == 0) continue;
         u64 base = 0;
         if (lane == 31) base = atomicAdd(cursor, (u64)total);
         base = __shfl_sync(0xffffffffu, base, 31) + (incl - n);
         if (n)
         {
-            foreach_kmer_in_chunk(rv, ci, k, stride, [&](u64 x, u32 p, int s) {
+#pragma unroll
+            for (int s = 0; s < CHUNK; ++s)
                 if (hits & (1u << s))
                 {
-                    u32 c = 0; lookup(tab, mask, filter, fmask, x, c);
-                    if (base < cap) { out_key[base] = ((u64)ci.read << col_bits) | c; out_pos[base] = p; }
-                    base++;
+                    if (base < cap) { Candidate c; c.kmer = x[s]; c.pos = ci.p0 + s; c.read = ci.read; out[base] = c; }
+                    ++base;
                 }
-            });
         }
+    }
+}
+
+// candidates -> triples: key = (local read << col_bits | column), val = pos
+__global__ void __launch_bounds__(256) k_resolve(const Candidate *__restrict__ cand, u64 n, const Slot *__restrict__ tab, u32 lslots,
+                                                 u64 *__restrict__ out_key, u32 *__restrict__ out_pos, u64 *__restrict__ cursor, u64 cap, int col_bits)
+{
+    const u64 step = (u64)gridDim.x * blockDim.x;
+    const u64 rounds = (n + step - 1) / step;
+    const int lane = threadIdx.x & 31;
+    for (u64 it = 0; it < rounds; ++it)
+    {
+        const u64 i = it * step + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+        bool ok = false; u32 col = 0; Candidate c; c.kmer = 0; c.pos = 0; c.read = 0;
+        if (i < n)
+        {
+            c = cand[i];
+            u32 s = lut_slot(mix64(c.kmer), lslots);
+            while (true)
+            {
+                ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(tab + s));
+                if (v.x == c.kmer) { col = (u32)(v.y >> 32); ok = true; break; }
+                if (v.x == EMPTY_KEY) break;
+                s = (s + 1 == lslots) ? 0 : s + 1;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (!m) continue;
+        u64 base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (u64)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0) + __popc(m & ((1u << lane) - 1));
+        if (ok && base < cap) { out_key[base] = ((u64)c.read << col_bits) | col; out_pos[base] = c.pos; }
     }
 }
 

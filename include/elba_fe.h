@@ -120,7 +120,8 @@ typedef struct {
     uint64_t partitions;    /* k-mer partitions actually used */
     uint64_t table_slots;   /* slots of one count table */
     uint64_t slow_partitions; /* partitions recounted with the global-table kernel (sub-bucket overflow: heavy hitters) */
-    uint64_t reserved[4];
+    uint64_t candidates;    /* sweep-2 filter hits (true instances + false positives) */
+    uint64_t reserved[3];
 } elba_fe_sizes_t;
 int elba_fe_sizes(elba_fe_ctx *ctx, elba_fe_sizes_t *out);
 

@@ -44,7 +44,7 @@ __device__ __forceinline__ u32 part2(u64 h, u32 P1, u32 P2) { return __umulhi((u
 static constexpr u32 BUCKET_SLOTS = 8192;          // shared-memory table of one sub-bucket
 static constexpr u32 BUCKET_CAP = 6144;            // instances per sub-bucket <= 0.75 * slots: the table can never fill
 static constexpr u32 MAX_P1 = 4096;
-static constexpr u32 MAX_P2 = 1024;
+static constexpr u32 MAX_P2 = 2048;
 
 // ---- level 1 -----------------------------------------------------------------------------------
 static constexpr int S1_THREADS = 256;
@@ -186,14 +186,19 @@ __device__ __forceinline__ u32 upper_seg(const u32 *__restrict__ a, u32 lo, u32 
 }
 
 // partitions [g0, g1) -> scratch: sub-bucket b (global numbering bucket_start[p] + q) of the group lives at
-// scratch[(b - bucket_start[g0]) * BUCKET_CAP ...], fill count bfill[b].  pflags[p] = 1 when a sub-bucket overflows.
+// scratch[(b - bucket_start[g0]) * BUCKET_CAP ...], fill count bfill[b].  Instances beyond BUCKET_CAP (repeat-rich
+// buckets: the sizes are compound-Poisson, not Poisson) go to the overflow list; k_count_buckets moves the rest of
+// such a bucket there too and the host counts the list with the global-table kernel.
+struct Overflow { u64 *list; u64 *cursor; u64 cap; };
+
 template <bool ONE_SLAB>
-__global__ void __launch_bounds__(S2_THREADS) k_scatter2(PartInput pi, PartPlan pl, u32 P1_total, u32 g0, u32 g1,
-                                                         u64 *__restrict__ scratch, u32 *__restrict__ bfill, u32 *__restrict__ pflags)
+__global__ void __launch_bounds__(S2_THREADS) k_scatter2(PartInput pi, PartPlan pl, u32 P1_total, u32 g0, u32 g1, u32 p2max,
+                                                         u64 *__restrict__ scratch, u32 *__restrict__ bfill, Overflow ovf)
 {
-    __shared__ __align__(16) u64 s_sorted[S2_TILE];
-    __shared__ u32 s_off[MAX_P2];
-    __shared__ u32 s_delta[MAX_P2];
+    extern __shared__ __align__(16) unsigned char s_raw[];        // S2_TILE * 8 + 2 * 4 * p2max bytes
+    u64 *s_sorted = reinterpret_cast<u64*>(s_raw);
+    u32 *s_off = reinterpret_cast<u32*>(s_sorted + S2_TILE);
+    u32 *s_delta = s_off + p2max;
     __shared__ u32 s_warp[9];
     const u32 tid = threadIdx.x;
     const u32 t0 = __ldg(pl.tile_start + g0), t1 = __ldg(pl.tile_start + g1);
@@ -263,7 +268,8 @@ __global__ void __launch_bounds__(S2_THREADS) k_scatter2(PartInput pi, PartPlan 
             u64 h = s_sorted[i];
             u32 q = part2(h, P1_total, P2);
             u32 d = s_delta[q] + i;
-            if (d < BUCKET_CAP) dst[q * BUCKET_CAP + d] = h; else pflags[p] = 1u;
+            if (d < BUCKET_CAP) dst[q * BUCKET_CAP + d] = h;
+            else { u64 o = atomicAdd(ovf.cursor, 1ull); if (o < ovf.cap) ovf.list[o] = h; }
         }
         __syncthreads();
     }
@@ -276,7 +282,7 @@ static constexpr int CB_SLOTS_PER = BUCKET_SLOTS / CB_THREADS;    // 16 table sl
 
 // counters: [0] reliable cursor, [1] sum of reliable counts, [2] distinct
 __global__ void __launch_bounds__(CB_THREADS, 2) k_count_buckets(PartPlan pl, u32 g0, u32 g1, const u64 *__restrict__ scratch,
-                                                                 const u32 *__restrict__ bfill, const u32 *__restrict__ pflags,
+                                                                 const u32 *__restrict__ bfill, Overflow ovf,
                                                                  u32 lower, u32 upper, u64 *__restrict__ out_h, u32 *__restrict__ out_cnt,
                                                                  u64 *__restrict__ counters, u64 cap)
 {
@@ -290,10 +296,17 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_count_buckets(PartPlan pl, u3
     u32 my_distinct = 0; u64 my_sum = 0;
     for (u32 b = b0 + blockIdx.x; b < b1; b += gridDim.x)
     {
-        const u32 p = upper_seg(pl.bucket_start, g0, g1, b);
-        if (__ldg(pflags + p)) continue;                           // uniform across the CTA: the whole partition is recounted by the host path
-        const u32 n = min(__ldg(bfill + b), BUCKET_CAP);
+        const u32 nraw = __ldg(bfill + b);
         const u64 *src = scratch + (u64)(b - b0) * BUCKET_CAP;
+        if (nraw > BUCKET_CAP)                                     // uniform across the CTA: the whole bucket joins its overflow
+        {
+            if (tid == 0) s_base = atomicAdd(ovf.cursor, (u64)BUCKET_CAP);
+            __syncthreads();
+            for (u32 i = tid; i < BUCKET_CAP; i += CB_THREADS) { u64 o = s_base + i; if (o < ovf.cap) ovf.list[o] = src[i]; }
+            __syncthreads();
+            continue;
+        }
+        const u32 n = nraw;
         // the instances are requested first, the table is cleared while they fly
         u64 x[CB_PER];
 #pragma unroll

@@ -53,7 +53,8 @@ struct elba_fe_ctx
     u32 n = 0; u64 packed_bytes = 0, nchunks = 0, M = 0, Ms = 0; int64_t read_id_offset = 0;
     // counting
     DevBuf table, cand, ctr, partbuf, phist, pcursor, rel_key, rel_cnt, rel_key_s, rel_cnt_s, lut, filter;
-    DevBuf plan, bfill, pflags, scratch[2];
+    DevBuf plan, bfill, ovf, scratch[2];
+    u64 ovf_cap = 0;
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     u64 scratch_mb = 64;
     u32 lut_slots = 0; u64 rel_cap = 0; u32 filter_words = 0; u64 cand_cap = 0;
@@ -206,6 +207,8 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     // opt in to large dynamic shared memory
     cudaFuncSetAttribute(k_scatter1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S1_TILE + 2 * sizeof(u32) * MAX_P1));
     cudaFuncSetAttribute(k_scatter1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S1_TILE + 2 * sizeof(u32) * MAX_P1));
+    cudaFuncSetAttribute(k_scatter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
+    cudaFuncSetAttribute(k_scatter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_count_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS));
     *out = ctx;
     return 0;
@@ -222,7 +225,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
         &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->bins, &ctx->small_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
-        &ctx->plan, &ctx->bfill, &ctx->pflags, &ctx->scratch[0], &ctx->scratch[1] };
+        &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1] };
     for (DevBuf *b : all) b->release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     for (auto *v : { &ctx->kev, &ctx->sev, &ctx->pev, &ctx->lev }) for (auto &p : *v) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -322,7 +325,8 @@ int elba_fe_count(elba_fe_ctx *ctx)
 
     const u64 Ms = ctx->Ms;
     // level-1 partitions of about PART_TARGET instances (8 MB of h values each)
-    u64 PART_TARGET = 2ull << 20;
+    // balanced digits: P1 ~ P2 ~ sqrt(#sub-buckets); both scatters then write runs of similar length
+    u64 PART_TARGET = std::max<u64>(1u << 16, (u64)std::sqrt((double)Ms * (double)BUCKET_CAP / 1.4));
     if (const char *e = getenv("ELBA_FE_PART_TARGET")) { long long v = atoll(e); if (v >= 4096) PART_TARGET = (u64)v; }
     u32 P1 = (u32)ctx->cfg.num_partitions;
     const bool direct = (P1 == 1) || (P1 == 0 && Ms <= 65536);
@@ -333,8 +337,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
     u64 rel_cap = Ms / lower + 1;
     if (rel_cap * 12 > (1ull << 30)) rel_cap = std::max<u64>(ctx->rel_cap, std::max<u64>(Ms / 8, (1ull << 30) / 12));
     u64 R = 0, sumcnt = 0, D = 0;
-
-    for (int attempt = 0; attempt < 2; ++attempt)
+    for (int attempt = 0; attempt < 4; ++attempt)
     {
         CK(ctx->rel_key.ensure(sizeof(u64) * rel_cap)); CK(ctx->rel_cnt.ensure(sizeof(u32) * rel_cap));
         ctx->rel_cap = rel_cap;
@@ -402,7 +405,8 @@ int elba_fe_count(elba_fe_ctx *ctx)
             for (u32 p = 0; p < P1; ++p)
             {
                 u64 n = cnt[p];
-                u64 p2 = n ? std::max<u64>(1, (n * 5 / 4 + BUCKET_CAP - 1) / BUCKET_CAP) : 0;
+                // mean fill = BUCKET_CAP / 1.4: with repeats the bucket sizes are compound-Poisson (sigma ~ sqrt(mean * copy number))
+                u64 p2 = n ? std::max<u64>(1, (n * 7 / 5 + BUCKET_CAP - 1) / BUCKET_CAP) : 0;
                 if (p2 > MAX_P2) { slow.push_back(p); n = 0; p2 = 0; }
                 pn[p] = (u32)n; pp2[p] = (u32)p2;
                 ptile[p + 1] = ptile[p] + (u32)((n + S2_TILE - 1) / S2_TILE);
@@ -411,9 +415,11 @@ int elba_fe_count(elba_fe_ctx *ctx)
             const u32 nbuckets = pbucket[P1];
             CK(ctx->plan.ensure(sizeof(u32) * plan.size()));
             CK(cudaMemcpyAsync(ctx->plan.p, plan.data(), sizeof(u32) * plan.size(), cudaMemcpyHostToDevice, st));
-            CK(ctx->bfill.ensure(sizeof(u32) * ((size_t)nbuckets + 1))); CK(ctx->pflags.ensure(sizeof(u32) * ((size_t)P1 + 1)));
+            CK(ctx->bfill.ensure(sizeof(u32) * ((size_t)nbuckets + 1)));
+            u64 ovf_cap = std::max<u64>(ctx->ovf_cap, std::max<u64>(Ms / 16, 1u << 20));
+            CK(ctx->ovf.ensure(sizeof(u64) * ovf_cap)); ctx->ovf_cap = ovf_cap;
+            Overflow ovf{ctx->ovf.as<u64>(), d_ctr + 5, ovf_cap};
             CK(cudaMemsetAsync(ctx->bfill.p, 0, sizeof(u32) * ((size_t)nbuckets + 1), st));
-            CK(cudaMemsetAsync(ctx->pflags.p, 0, sizeof(u32) * ((size_t)P1 + 1), st));
             PartPlan pl; pl.n = ctx->plan.as<u32>(); pl.p2 = pl.n + P1; pl.tile_start = pl.p2 + P1; pl.bucket_start = pl.tile_start + P1 + 1;
             PartInput pi; pi.in = ctx->partbuf.as<u64>(); pi.W = 1; pi.slab_stride = 0; pi.part_start = ctx->phist.as<u64>(); pi.cnt = ctx->pcursor.as<u32>(); pi.P = P1;
 
@@ -431,12 +437,14 @@ int elba_fe_count(elba_fe_ctx *ctx)
                 u32 g1 = g0 + 1;
                 while (g1 < P1 && (u64)(pbucket[g1 + 1] - pbucket[g0]) <= group_buckets) ++g1;
                 const u32 nt = ptile[g1] - ptile[g0], nb = pbucket[g1] - pbucket[g0];
+                u32 p2max = 1; for (u32 p = g0; p < g1; ++p) p2max = std::max(p2max, pp2[p]);
                 if (nt)
                 {
                     cudaStream_t s2 = which ? ctx->aux : st; used_aux |= which != 0;
-                    k_scatter2<true><<<std::min<u32>(nt, grid_for(ctx, 5)), S2_THREADS, 0, s2>>>(pi, pl, P1, g0, g1, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ctx->pflags.as<u32>());
+                    const size_t smem2 = sizeof(u64) * S2_TILE + 2 * sizeof(u32) * p2max;
+                    k_scatter2<true><<<std::min<u32>(nt, grid_for(ctx, 5)), S2_THREADS, smem2, s2>>>(pi, pl, P1, g0, g1, p2max, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ovf);
                     CKL(); LAUNCHED(ctx);
-                    k_count_buckets<<<std::min<u32>(nb, grid_for(ctx, 2)), CB_THREADS, smemc, s2>>>(pl, g0, g1, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ctx->pflags.as<u32>(),
+                    k_count_buckets<<<std::min<u32>(nb, grid_for(ctx, 2)), CB_THREADS, smemc, s2>>>(pl, g0, g1, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ovf,
                         lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
                     CKL(); LAUNCHED(ctx);
                     which ^= 1;
@@ -446,12 +454,24 @@ int elba_fe_count(elba_fe_ctx *ctx)
             if (used_aux) { CK(cudaEventRecord(ctx->ev_join, ctx->aux)); CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); }
             CK(cudaEventRecord(ep.b, st));
 
-            // ---- partitions the fast path gave up on (a sub-bucket overflowed: heavy hitters): exact global-table count
-            std::vector<u32> pf(P1);
-            CK(cudaMemcpyAsync(pf.data(), ctx->pflags.p, sizeof(u32) * P1, cudaMemcpyDeviceToHost, st));
+            // ---- what the fast path gave up on: instances of overflowing sub-buckets (repeat-rich / heavy hitters) and
+            //      partitions too large for MAX_P2 sub-buckets -> exact global-table count
+            u64 novf = 0;
+            CK(cudaMemcpyAsync(&novf, d_ctr + 5, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            for (u32 p = 0; p < P1; ++p) if (pf[p]) slow.push_back(p);
-            ctx->sz.slow_partitions = slow.size();
+            if (novf > ovf_cap)
+            {
+                if (attempt == 3) return fail(ctx, ELBA_FE_ERR_CUDA, "overflow list resize did not converge");
+                ctx->ovf_cap = novf + (novf >> 3);      // the list length does not depend on scheduling: exact next time
+                continue;
+            }
+            ctx->sz.slow_partitions = slow.size(); ctx->sz.overflow_instances = novf;
+            if (novf)
+            {
+                std::vector<std::pair<const u64*, u64>> slabs{{ctx->ovf.as<u64>(), novf}};
+                int rc = count_with_global_table(ctx, slabs, novf, rel_cap);
+                if (rc) return rc;
+            }
             for (u32 p : slow)
             {
                 std::vector<std::pair<const u64*, u64>> slabs{{ctx->partbuf.as<u64>() + start[p], (u64)cnt[p]}};
@@ -465,7 +485,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
         R = h[0]; sumcnt = h[1]; D = h[2];
         if ((u32)h[3] != 0) return fail(ctx, ELBA_FE_ERR_CUDA, "count table overflow");
         if (R <= rel_cap) break;
-        if (attempt == 1) return fail(ctx, ELBA_FE_ERR_CUDA, "reliable list overflow after resize");
+        if (attempt == 3) return fail(ctx, ELBA_FE_ERR_CUDA, "reliable list overflow after resize");
         rel_cap = R;       // exact; redo the count
     }
     if (R >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers on one context");
@@ -519,8 +539,9 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
         if (ctx->nchunks && R)
         {
             // candidates = true instances + filter false positives (a few % of all instances); exact size after one try
-            u64 ccap = std::max<u64>(ctx->cand_cap, npre + std::max<u64>(ctx->Ms / 32, 1u << 16));
-            for (int attempt = 0; attempt < 2; ++attempt)
+            const u64 chunk_slack = (u64)grid_for(ctx, 2) * (PF_THREADS / 32) * PF_CHUNK;     // every warp may leave one chunk partly used
+            u64 ccap = std::max<u64>(ctx->cand_cap, npre + std::max<u64>(ctx->Ms / 32, 1u << 16) + chunk_slack);
+            for (int attempt = 0; attempt < 3; ++attempt)
             {
                 CK(ctx->cand.ensure(sizeof(Candidate) * ccap));
                 ctx->cand_cap = ccap;
@@ -532,7 +553,7 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
                 CK(cudaMemcpyAsync(&ncand, d_ctr + 1, 8, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 ctx->sz.candidates = ncand;
-                if (ncand > ccap) { if (attempt) return fail(ctx, ELBA_FE_ERR_CUDA, "candidate list overflow after resize"); ccap = ncand; continue; }
+                if (ncand > ccap) { if (attempt == 2) return fail(ctx, ELBA_FE_ERR_CUDA, "candidate list overflow after resize"); ccap = ncand + ncand / 8 + chunk_slack; continue; }
                 if (ncand) { k_resolve<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->cand.as<Candidate>(), ncand, ctx->lut.as<Slot>(), ctx->lut_slots,
                                  ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, npre, cb); CKL(); LAUNCHED(ctx); }
                 break;

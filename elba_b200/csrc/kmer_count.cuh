@@ -213,12 +213,18 @@ __global__ void k_lookup_build(const u64 *__restrict__ keys, const u32 *__restri
 struct __align__(16) Candidate { u64 kmer; u32 pos; u32 read; };
 
 static constexpr int PF_THREADS = 256;
+static constexpr u32 PF_CHUNK = 2048;       // candidate records a warp reserves at a time (one global atomic per 2048 hits)
+
+// Candidates are appended into warp-private chunks of PF_CHUNK records; the unused tail of a chunk is marked with
+// kmer = EMPTY_KEY (k_resolve skips those).  *cursor ends as the number of record slots handed out.
 __global__ void __launch_bounds__(PF_THREADS, 2) k_probe_filter(ReadsView rv, int k, int stride, const u64 *__restrict__ filter, u32 fwords,
                                                                 Candidate *__restrict__ out, u64 *__restrict__ cursor, u64 cap)
 {
     const u64 step = (u64)gridDim.x * blockDim.x;
     const u64 rounds = (rv.nchunks + step - 1) / step;
     const int lane = threadIdx.x & 31;
+    u64 cbase = 0; u32 cused = PF_CHUNK;     // warp-uniform
+    Candidate hole; hole.kmer = EMPTY_KEY; hole.pos = 0; hole.read = 0;
     for (u64 it = 0; it < rounds; ++it)
     {
         const u64 g = it * step + (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,9 +253,15 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_probe_filter(ReadsView rv, in
         for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         const u32 total = __shfl_sync(0xffffffffu, incl, 31);
         if (total == 0) continue;
-        u64 base = 0;
-        if (lane == 31) base = atomicAdd(cursor, (u64)total);
-        base = __shfl_sync(0xffffffffu, base, 31) + (incl - n);
+        if (cused + total > PF_CHUNK)
+        {
+            for (u32 i = cused + lane; i < PF_CHUNK; i += 32) if (cbase + i < cap) out[cbase + i] = hole;
+            if (lane == 0) cbase = atomicAdd(cursor, (u64)PF_CHUNK);
+            cbase = __shfl_sync(0xffffffffu, cbase, 0);
+            cused = 0;
+        }
+        u64 base = cbase + cused + (incl - n);
+        cused += total;
         if (n)
         {
 #pragma unroll
@@ -261,22 +273,25 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_probe_filter(ReadsView rv, in
                 }
         }
     }
+    for (u32 i = cused + lane; i < PF_CHUNK; i += 32) if (cbase + i < cap) out[cbase + i] = hole;
 }
 
-// candidates -> triples: key = (local read << col_bits | column), val = pos
+// candidates -> triples: key = (local read << col_bits | column), val = pos.  One output reservation per CTA round.
 __global__ void __launch_bounds__(256) k_resolve(const Candidate *__restrict__ cand, u64 n, const Slot *__restrict__ tab, u32 lslots,
                                                  u64 *__restrict__ out_key, u32 *__restrict__ out_pos, u64 *__restrict__ cursor, u64 cap, int col_bits)
 {
+    __shared__ u32 s_wcnt[8];
+    __shared__ u64 s_base;
     const u64 step = (u64)gridDim.x * blockDim.x;
     const u64 rounds = (n + step - 1) / step;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (u64 it = 0; it < rounds; ++it)
     {
         const u64 i = it * step + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-        bool ok = false; u32 col = 0; Candidate c; c.kmer = 0; c.pos = 0; c.read = 0;
-        if (i < n)
+        bool ok = false; u32 col = 0; Candidate c; c.kmer = EMPTY_KEY; c.pos = 0; c.read = 0;
+        if (i < n) c = cand[i];
+        if (c.kmer != EMPTY_KEY)
         {
-            c = cand[i];
             u32 s = lut_slot(mix64(c.kmer), lslots);
             while (true)
             {
@@ -287,11 +302,19 @@ __global__ void __launch_bounds__(256) k_resolve(const Candidate *__restrict__ c
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (!m) continue;
-        u64 base = 0;
-        if (lane == 0) base = atomicAdd(cursor, (u64)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0) + __popc(m & ((1u << lane) - 1));
+        if (lane == 0) s_wcnt[w] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            u32 tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { u32 t = s_wcnt[j]; s_wcnt[j] = tot; tot += t; }
+            s_base = tot ? atomicAdd(cursor, (u64)tot) : 0ull;
+        }
+        __syncthreads();
+        const u64 base = s_base + s_wcnt[w] + __popc(m & ((1u << lane) - 1));
         if (ok && base < cap) { out_key[base] = ((u64)c.read << col_bits) | col; out_pos[base] = c.pos; }
+        __syncthreads();
     }
 }
 

@@ -39,7 +39,7 @@ class _Config(C.Structure):
 
 class Sizes(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("nreads", "num_kmers", "distinct", "reliable", "nnzA_pre", "nnzA", "products",
-                                          "nnzB_pre", "nnzB", "partitions", "table_slots", "slow_partitions", "candidates")] + [("reserved", C.c_uint64 * 3)]
+                                          "nnzB_pre", "nnzB", "partitions", "table_slots", "slow_partitions", "candidates", "overflow_instances")] + [("reserved", C.c_uint64 * 2)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}

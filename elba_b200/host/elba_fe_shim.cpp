@@ -1,0 +1,237 @@
+/*
+ * elba_fe_shim.cpp — the reference's five driver functions for the overlap-detection front end,
+ * re-implemented on top of the C ABI of libelba_fe.so (include/elba_fe.h).
+ *
+ * Build it INSTEAD OF src/KmerOps.cpp and src/SharedSeeds.cpp of PASSIONLab/ELBA (Makefile:36-55 OBJECTS) and link
+ * -lelba_fe: src/main.cpp:191-282 then compiles and runs unchanged.  It includes the reference's own
+ * headers and uses only their public accessors; it contains no CUDA and no algorithm — every result comes from the
+ * library.  Signatures replaced (reference file:line):
+ *
+ *   get_kmer_count_map_keys     include/KmerOps.hpp:27-28     src/KmerOps.cpp:18-204
+ *   get_kmer_count_map_values   include/KmerOps.hpp:30        src/KmerOps.cpp:206-350
+ *   create_kmer_matrix          include/KmerOps.hpp:24-25     src/KmerOps.cpp:361-401
+ *   GetKmerOwner                include/KmerOps.hpp:31        src/KmerOps.cpp:352-359
+ *   create_seed_matrix          include/SharedSeeds.hpp:98-99 src/SharedSeeds.cpp:4-10
+ *
+ * State between the calls lives in one elba_fe_ctx per rank, found through the address of the object the driver
+ * passes back in (the KmerCountMap, then A).  The driver's `kmermap.reset()` (main.cpp:266) and `A.reset()` (:284)
+ * therefore need no change; the context is destroyed after create_seed_matrix.
+ *
+ * Errors: the reference asserts / MPI_Aborts; so does this (fe_check).
+ * MPI ranks: one rank drives one GPU (device = local rank modulo device count).  With more than one rank the
+ * k-mer exchange and the panel exchange run inside the library over NCCL (elba_fe_comm_*, bootstrapped here by
+ * broadcasting the ncclUniqueId over MPI).
+ */
+#include "KmerOps.hpp"
+#include "SharedSeeds.hpp"
+#include "elba_fe.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace
+{
+
+struct FeState
+{
+    elba_fe_ctx *ctx = nullptr;
+    int64_t readoffset = 0, totreads = 0;
+    std::shared_ptr<CommGrid> grid;
+};
+
+std::map<const void*, FeState> g_states;      /* keyed by the KmerCountMap, later re-keyed by A */
+std::mutex g_mu;
+
+void fe_check(int rc, elba_fe_ctx *ctx, const char *what, MPI_Comm comm)
+{
+    if (rc == 0) return;
+    std::fprintf(stderr, "elba_fe: %s failed (%d): %s\n", what, rc, elba_fe_last_error(ctx));
+    MPI_Abort(comm, rc);
+    std::abort();
+}
+
+FeState take_state(const void *key)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_states.find(key);
+    assert(it != g_states.end() && "elba_fe shim: object was not produced by this library's functions");
+    FeState s = it->second;
+    g_states.erase(it);
+    return s;
+}
+
+FeState& peek_state(const void *key)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_states.find(key);
+    assert(it != g_states.end() && "elba_fe shim: object was not produced by this library's functions");
+    return it->second;
+}
+
+} // namespace
+
+/* src/KmerOps.cpp:352-359, kept because include/KmerOps.hpp declares it (the library partitions by its own hash) */
+int GetKmerOwner(const TKmer& kmer, int nprocs)
+{
+    uint64_t myhash = kmer.GetHash();
+    double range = static_cast<double>(myhash) * static_cast<double>(nprocs);
+    size_t owner = range / std::numeric_limits<uint64_t>::max();
+    assert(owner >= 0 && owner < static_cast<int>(nprocs));
+    return static_cast<int>(owner);
+}
+
+std::unique_ptr<KmerCountMap>
+get_kmer_count_map_keys(const DnaBuffer& myreads, std::shared_ptr<CommGrid> commgrid)
+{
+    static_assert(KMER_SIZE <= ELBA_FE_MAX_KMER_SIZE, "libelba_fe counts k-mers of one 64-bit word (TKmer = Kmer<1>)");
+    MPI_Comm comm = commgrid->GetWorld();
+    int myrank = commgrid->GetRank(), nprocs = commgrid->GetSize();
+
+    elba_fe_config cfg;
+    elba_fe_default_config(&cfg);
+    cfg.k = KMER_SIZE; cfg.lower = LOWER_KMER_FREQ; cfg.upper = UPPER_KMER_FREQ; cfg.stride = 1; cfg.seed_count = 2;
+    if (const char *d = std::getenv("ELBA_FE_DEVICE")) cfg.device = std::atoi(d);
+    else if (const char *l = std::getenv("OMPI_COMM_WORLD_LOCAL_RANK")) cfg.device = std::atoi(l);
+    else if (const char *l2 = std::getenv("SLURM_LOCALID")) cfg.device = std::atoi(l2);
+
+    FeState st; st.grid = commgrid;
+    fe_check(elba_fe_create(&cfg, &st.ctx), nullptr, "elba_fe_create", comm);
+
+    /* global read ids: the MPI_Exscan of src/KmerOps.cpp:215-216 */
+    size_t numreads = myreads.size();
+    int64_t mine = (int64_t)numreads, before = 0, total = mine;
+    MPI_Exscan(&mine, &before, 1, MPI_INT64_T, MPI_SUM, comm);
+    if (myrank == 0) before = 0;
+    MPI_Allreduce(MPI_IN_PLACE, &total, 1, MPI_INT64_T, MPI_SUM, comm);
+    st.readoffset = before; st.totreads = total;
+
+    /* the arena through DnaBuffer's public accessors only (include/DnaBuffer.hpp:18-23) */
+    std::vector<uint64_t> off(numreads), len(numreads);
+    const uint8_t *base = numreads ? myreads.getbufoffset(0) : nullptr;
+    for (size_t i = 0; i < numreads; ++i)
+    {
+        off[i] = (uint64_t)(myreads.getbufoffset(i) - base);
+        len[i] = (uint64_t)myreads[i].size();
+    }
+    uint64_t nbytes = numreads ? off[numreads - 1] + (uint64_t)myreads[numreads - 1].numbytes() : 0;
+
+    if (nprocs > 1)
+    {
+        /* one NCCL communicator over the grid's ranks; the id travels over MPI */
+        elba_fe_comm_id id;
+        if (myrank == 0) fe_check(elba_fe_comm_get_id(&id), st.ctx, "elba_fe_comm_get_id", comm);
+        MPI_Bcast(&id, (int)sizeof id, MPI_BYTE, 0, comm);
+        fe_check(elba_fe_comm_init(st.ctx, &id, myrank, nprocs), st.ctx, "elba_fe_comm_init", comm);
+    }
+    fe_check(elba_fe_upload_reads(st.ctx, base, nbytes, off.data(), len.data(), numreads, before), st.ctx, "elba_fe_upload_reads", comm);
+
+    auto kmermap = std::make_unique<KmerCountMap>();
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_states[kmermap.get()] = st;
+    }
+    return kmermap;
+}
+
+void get_kmer_count_map_values(const DnaBuffer& myreads, KmerCountMap& kmermap, std::shared_ptr<CommGrid> commgrid)
+{
+    (void)myreads;
+    FeState& st = peek_state(&kmermap);
+    MPI_Comm comm = commgrid->GetWorld();
+    fe_check(elba_fe_count(st.ctx), st.ctx, "elba_fe_count", comm);
+    fe_check(elba_fe_build_A(st.ctx), st.ctx, "elba_fe_build_A", comm);
+
+    /* Fill the map the driver holds: its size and the per-k-mer counts are logged (src/main.cpp:449-485) and it is what
+     * create_kmer_matrix receives.  Entries: this rank's share of the reliable k-mers, their exact instance counts, and
+     * the (read, position) pairs of A's column (one per read: duplicates inside a read were already merged to the
+     * largest position, the rule the SpParMat constructor applies in the reference, src/KmerOps.cpp:400). */
+    elba_fe_sizes_t sz;
+    fe_check(elba_fe_sizes(st.ctx, &sz), st.ctx, "elba_fe_sizes", comm);
+    std::vector<uint64_t> kmers(sz.reliable); std::vector<uint32_t> counts(sz.reliable);
+    fe_check(elba_fe_get_kmers(st.ctx, kmers.data(), counts.data()), st.ctx, "elba_fe_get_kmers", comm);
+    std::vector<int64_t> colptr(sz.reliable + 1); std::vector<uint32_t> rows(sz.nnzA), pos(sz.nnzA);
+    fe_check(elba_fe_get_AT(st.ctx, colptr.data(), rows.data(), pos.data()), st.ctx, "elba_fe_get_AT", comm);
+    int myrank = commgrid->GetRank(), nprocs = commgrid->GetSize();
+    kmermap.reserve(sz.reliable / nprocs + 1);
+    for (uint64_t c = 0; c < sz.reliable; ++c)
+    {
+        if ((int)(c % (uint64_t)nprocs) != myrank) continue;      /* the reliable list is replicated; each rank shows its slice */
+        TKmer kmer((const void*)&kmers[c]);
+        KmerCountEntry& e = kmermap[kmer];
+        READIDS& readids = std::get<0>(e); POSITIONS& positions = std::get<1>(e);
+        int n = 0;
+        for (int64_t q = colptr[c]; q < colptr[c + 1] && n < UPPER_KMER_FREQ; ++q, ++n) { readids[n] = (ReadId)rows[q] + st.readoffset; positions[n] = pos[q]; }
+        std::get<2>(e) = (int)counts[c];
+    }
+}
+
+std::unique_ptr<CT<PosInRead>::PSpParMat>
+create_kmer_matrix(const DnaBuffer& myreads, const KmerCountMap& kmermap, std::shared_ptr<CommGrid> commgrid)
+{
+    (void)myreads;
+    FeState st = take_state(&kmermap);
+    MPI_Comm comm = commgrid->GetWorld();
+    elba_fe_sizes_t sz;
+    fe_check(elba_fe_sizes(st.ctx, &sz), st.ctx, "elba_fe_sizes", comm);
+
+    /* this rank's rows of A as global triples, handed to the same constructor the reference uses (KmerOps.cpp:396-400) */
+    std::vector<int64_t> rowptr(sz.nreads + 1); std::vector<uint32_t> col(sz.nnzA), pos(sz.nnzA);
+    fe_check(elba_fe_get_A(st.ctx, rowptr.data(), col.data(), pos.data()), st.ctx, "elba_fe_get_A", comm);
+    std::vector<int64_t> local_rowids(sz.nnzA), local_colids(sz.nnzA);
+    std::vector<PosInRead> local_positions(pos.begin(), pos.end());
+    for (uint64_t r = 0; r < sz.nreads; ++r)
+        for (int64_t q = rowptr[r]; q < rowptr[r + 1]; ++q) { local_rowids[q] = (int64_t)r + st.readoffset; local_colids[q] = (int64_t)col[q]; }
+
+    CT<int64_t>::PDistVec drows(local_rowids, commgrid);
+    CT<int64_t>::PDistVec dcols(local_colids, commgrid);
+    CT<PosInRead>::PDistVec dvals(local_positions, commgrid);
+    auto A = std::make_unique<CT<PosInRead>::PSpParMat>(st.totreads, (int64_t)sz.reliable, drows, dcols, dvals, false);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_states[A.get()] = st;
+    }
+    return A;
+}
+
+std::unique_ptr<CT<SharedSeeds>::PSpParMat>
+create_seed_matrix(CT<PosInRead>::PSpParMat& A, CT<PosInRead>::PSpParMat& AT)
+{
+    (void)AT;                                   /* the library built A and its transpose together (elba_fe_build_A) */
+    FeState st = take_state(&A);
+    MPI_Comm comm = st.grid->GetWorld();
+    fe_check(elba_fe_spgemm(st.ctx), st.ctx, "elba_fe_spgemm", comm);
+    elba_fe_sizes_t sz;
+    fe_check(elba_fe_sizes(st.ctx, &sz), st.ctx, "elba_fe_sizes", comm);
+
+    std::vector<int64_t> rows(sz.nnzB), cols(sz.nnzB); std::vector<int32_t> num(sz.nnzB); std::vector<uint32_t> seeds(4 * sz.nnzB);
+    fe_check(elba_fe_get_B_triples(st.ctx, rows.data(), cols.data(), num.data(), seeds.data()), st.ctx, "elba_fe_get_B_triples", comm);
+    elba_fe_destroy(st.ctx);
+
+    /* field-wise: std::tuple's memory order is not its template order */
+    std::vector<SharedSeeds> vals; vals.reserve(sz.nnzB);
+    for (uint64_t e = 0; e < sz.nnzB; ++e)
+        vals.emplace_back(std::make_tuple((PosInRead)seeds[4 * e], (PosInRead)seeds[4 * e + 1]),
+                          std::make_tuple((PosInRead)seeds[4 * e + 2], (PosInRead)seeds[4 * e + 3]), (int)num[e]);
+
+#ifdef ELBA_FE_SHIM_SPTUPLES
+    /* real CombBLAS: SharedSeeds has no operator<, so the (rows, cols, vals) constructor (which merges duplicates with
+     * maximum<NT>) does not instantiate; build the local block from tuples exactly as CombBLAS returns SpGEMM results.
+     * The triples are this rank's block in local indices. */
+    int64_t nloc_r = 0, nloc_c = 0, roff = 0, coff = 0;
+    elba_fe_block_extent(st.totreads, st.grid->GetGridRows(), st.grid->GetRankInProcCol(), &roff, &nloc_r);
+    elba_fe_block_extent(st.totreads, st.grid->GetGridCols(), st.grid->GetRankInProcRow(), &coff, &nloc_c);
+    auto *tuples = new std::tuple<int64_t, int64_t, SharedSeeds>[sz.nnzB];
+    for (uint64_t e = 0; e < sz.nnzB; ++e) tuples[e] = std::make_tuple(rows[e] - roff, cols[e] - coff, vals[e]);
+    combblas::SpTuples<int64_t, SharedSeeds> spt((int64_t)sz.nnzB, nloc_r, nloc_c, tuples, false);
+    auto *dcsc = new CT<SharedSeeds>::PSpDCCols(spt, false);
+    return std::make_unique<CT<SharedSeeds>::PSpParMat>(dcsc, st.grid);
+#else
+    CT<int64_t>::PDistVec drows(rows, st.grid);
+    CT<int64_t>::PDistVec dcols(cols, st.grid);
+    CT<SharedSeeds>::PDistVec dvals(vals, st.grid);
+    return std::make_unique<CT<SharedSeeds>::PSpParMat>(st.totreads, st.totreads, drows, dcols, dvals, false);
+#endif
+}

@@ -119,9 +119,10 @@ typedef struct {
     uint64_t nnzB;          /* after Prune(numshared <= 1) */
     uint64_t partitions;    /* k-mer partitions actually used */
     uint64_t table_slots;   /* slots of one count table */
-    uint64_t slow_partitions; /* partitions recounted with the global-table kernel (sub-bucket overflow: heavy hitters) */
-    uint64_t candidates;    /* sweep-2 filter hits (true instances + false positives) */
-    uint64_t reserved[3];
+    uint64_t slow_partitions; /* partitions too large for the sub-bucket fan-out, counted whole with the global-table kernel */
+    uint64_t candidates;    /* sweep-2 candidate slots (filter hits: true instances + false positives, + chunk padding) */
+    uint64_t overflow_instances; /* instances of overflowing sub-buckets (heavy hitters / repeats), counted with the global-table kernel */
+    uint64_t reserved[2];
 } elba_fe_sizes_t;
 int elba_fe_sizes(elba_fe_ctx *ctx, elba_fe_sizes_t *out);
 

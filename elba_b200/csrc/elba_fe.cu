@@ -6,6 +6,7 @@
 #include "sketch.cuh"
 #include "matrix_build.cuh"
 #include "spgemm.cuh"
+#include "comm.cuh"
 #include <cub/cub.cuh>
 #include <string>
 #include <vector>
@@ -55,7 +56,8 @@ struct elba_fe_ctx
     DevBuf table, cand, ctr, partbuf, phist, pcursor, rel_key, rel_cnt, rel_key_s, rel_cnt_s, lut, filter;
     DevBuf plan, bfill, ovf, scratch[2];
     u64 ovf_cap = 0;
-    cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_x0 = nullptr, ev_x1 = nullptr;
+    u64 exchange_bytes = 0, panel_bytes = 0;
     u64 scratch_mb = 64;
     u32 lut_slots = 0; u64 rel_cap = 0; u32 filter_words = 0; u64 cand_cap = 0;
     // A
@@ -65,6 +67,13 @@ struct elba_fe_ctx
     DevBuf t_col, t_num, t_seeds, row_off, row_nnz, bins, small_rows, big_rows, ovf_rows, gscratch, b_rowptr, b_col, b_num, b_seeds;
     u64 b_cap_hint = 0;
     DevBuf cubtmp, hll_regs, bloom;
+    // multi-GPU
+    Comm comm;
+    u64 N_total = 0;
+    DevBuf recvbuf, recvcnt, tmp64, rel_all_key, rel_all_cnt, g_key, g_pos, pack_key, l_rowptr, l_col, r_key, r_key2, r_pos, r_colptr, r_row, r_ptr;
+    // SpGEMM operands: left rows (CSR) x right rows by column (CSC); one GPU: A and its transpose
+    struct { const int64_t *l_rowptr; const u32 *l_col, *l_pos; u32 l_rows; u64 l_nnz; const int64_t *r_colptr; const u32 *r_row, *r_pos; int64_t row0, col0; } op;
+    u32 b_rows = 0;
     elba_fe_sizes_t sz;
     elba_fe_timings_t tm;
     cudaEvent_t ev[8];
@@ -203,6 +212,7 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaEventCreate(&ctx->ev_x0); cudaEventCreate(&ctx->ev_x1);
     if (const char *e = getenv("ELBA_FE_SCRATCH_MB")) { long v = atol(e); if (v >= 8 && v <= 65536) ctx->scratch_mb = (u64)v; }
     // opt in to large dynamic shared memory
     cudaFuncSetAttribute(k_scatter1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S1_TILE + 2 * sizeof(u32) * MAX_P1));
@@ -225,14 +235,19 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
         &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->bins, &ctx->small_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
-        &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1] };
+        &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1],
+        &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
+        &ctx->r_key, &ctx->r_key2, &ctx->r_pos, &ctx->r_colptr, &ctx->r_row, &ctx->r_ptr };
     for (DevBuf *b : all) b->release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     for (auto *v : { &ctx->kev, &ctx->sev, &ctx->pev, &ctx->lev }) for (auto &p : *v) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (ctx->comm.comm) ctx->comm.api->CommDestroy(ctx->comm.comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_x0) cudaEventDestroy(ctx->ev_x0);
+    if (ctx->ev_x1) cudaEventDestroy(ctx->ev_x1);
     delete ctx;
     return 0;
 }
@@ -290,6 +305,48 @@ int elba_fe_set_reads_device(elba_fe_ctx *ctx, const uint8_t *d_packed, uint64_t
 }
 
 // -------------------------------------------------------------------------------------------------
+#define NC(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) \
+    return fail(ctx, ELBA_FE_ERR_COMM, std::string(#call) + ": " + ctx->comm.api->GetErrorString(r__)); } while (0)
+
+static int allreduce_u64(elba_fe_ctx *ctx, u64 *vals, int n, ncclRedOp_t op)
+{
+    if (ctx->comm.nranks == 1) return 0;
+    CK(ctx->tmp64.ensure(8 * (size_t)std::max(n, 64)));
+    CK(cudaMemcpyAsync(ctx->tmp64.p, vals, 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx->comm.api->AllReduce(ctx->tmp64.p, ctx->tmp64.p, (size_t)n, ncclUint64, op, ctx->comm.comm, ctx->stream));
+    CK(cudaMemcpyAsync(vals, ctx->tmp64.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int allgather_u64(elba_fe_ctx *ctx, u64 mine, std::vector<u64> &all)
+{
+    const int W = ctx->comm.nranks;
+    all.assign(W, mine);
+    if (W == 1) return 0;
+    CK(ctx->tmp64.ensure(8 * (size_t)std::max(W + 1, 64)));
+    CK(cudaMemcpyAsync(ctx->tmp64.as<u64>() + W, &mine, 8, cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx->comm.api->AllGather(ctx->tmp64.as<u64>() + W, ctx->tmp64.p, 1, ncclUint64, ctx->comm.comm, ctx->stream));
+    CK(cudaMemcpyAsync(all.data(), ctx->tmp64.p, 8 * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// every rank contributes count[r] elements of `esize` bytes; recv holds them in rank order
+static int allgatherv(elba_fe_ctx *ctx, const void *send, void *recv, const std::vector<u64> &count, size_t esize)
+{
+    const int W = ctx->comm.nranks;
+    NC(ctx->comm.api->GroupStart());
+    u64 off = 0;
+    for (int r = 0; r < W; ++r)
+    {
+        if (count[r]) NC(ctx->comm.api->Broadcast(send, (char*)recv + off * esize, count[r] * esize, ncclUint8, r, ctx->comm.comm, ctx->stream));
+        off += count[r];
+    }
+    NC(ctx->comm.api->GroupEnd());
+    return 0;
+}
+
 // Slow, always-correct counting of one set of h slabs with a global table (heavy-hitter partitions, direct mode).
 static int count_with_global_table(elba_fe_ctx *ctx, const std::vector<std::pair<const u64*, u64>> &slabs, u64 total, u64 rel_cap)
 {
@@ -324,18 +381,31 @@ int elba_fe_count(elba_fe_ctx *ctx)
     u32 *d_flag1 = reinterpret_cast<u32*>(d_ctr + 4);
 
     const u64 Ms = ctx->Ms;
-    // level-1 partitions of about PART_TARGET instances (8 MB of h values each)
+    const int W = ctx->comm.nranks, me = ctx->comm.rank;
+    // instances over all GPUs decide the partitioning; the largest local share decides the slab capacity
+    u64 Ms_total = Ms, Ms_max = Ms;
+    if (W > 1)
+    {
+        int rc0;
+        if ((rc0 = allreduce_u64(ctx, &Ms_total, 1, ncclSum))) return rc0;
+        if ((rc0 = allreduce_u64(ctx, &Ms_max, 1, ncclMax))) return rc0;
+        u64 nt = ctx->n; if ((rc0 = allreduce_u64(ctx, &nt, 1, ncclSum))) return rc0;
+        ctx->N_total = nt;
+    }
+    else ctx->N_total = ctx->n;
     // balanced digits: P1 ~ P2 ~ sqrt(#sub-buckets); both scatters then write runs of similar length
-    u64 PART_TARGET = std::max<u64>(1u << 16, (u64)std::sqrt((double)Ms * (double)BUCKET_CAP / 1.4));
+    u64 PART_TARGET = std::max<u64>(1u << 16, (u64)std::sqrt((double)Ms_total * (double)BUCKET_CAP / 1.4));
     if (const char *e = getenv("ELBA_FE_PART_TARGET")) { long long v = atoll(e); if (v >= 4096) PART_TARGET = (u64)v; }
     u32 P1 = (u32)ctx->cfg.num_partitions;
-    const bool direct = (P1 == 1) || (P1 == 0 && Ms <= 65536);
-    if (P1 == 0) P1 = (u32)std::min<u64>(MAX_P1, std::max<u64>(1, (Ms + PART_TARGET - 1) / PART_TARGET));
+    const bool direct = W == 1 && ((P1 == 1) || (P1 == 0 && Ms <= 65536));
+    if (P1 == 0) P1 = (u32)std::min<u64>(MAX_P1, std::max<u64>(1, (Ms_total + PART_TARGET - 1) / PART_TARGET));
     if (direct) P1 = 1;
+    if (W > 1) { P1 = (P1 + W - 1) / W * W; if (P1 > MAX_P1) P1 = MAX_P1 / W * W; }      // every rank owns P1 / W partitions
+    const u32 Pown = P1 / (u32)W;
     ctx->sz.partitions = P1;
 
-    u64 rel_cap = Ms / lower + 1;
-    if (rel_cap * 12 > (1ull << 30)) rel_cap = std::max<u64>(ctx->rel_cap, std::max<u64>(Ms / 8, (1ull << 30) / 12));
+    u64 rel_cap = Ms_max / lower + 1;
+    if (rel_cap * 12 > (1ull << 30)) rel_cap = std::max<u64>(ctx->rel_cap, std::max<u64>(Ms_max / 8, (1ull << 30) / 12));
     u64 R = 0, sumcnt = 0, D = 0;
     for (int attempt = 0; attempt < 4; ++attempt)
     {
@@ -362,7 +432,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
         {
             ctx->sz.table_slots = BUCKET_SLOTS;
             // ---- level 1: optimistic uniform regions; exact regions from a histogram if one overflows
-            const u64 mean = (Ms + P1 - 1) / P1;
+            const u64 mean = (Ms_max + P1 - 1) / P1;
             u64 cap1 = (u64)((double)mean * 1.03) + 4096; cap1 = (cap1 + 15) & ~15ull;
             if (cap1 >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "level-1 partition exceeds 2^32 instances");
             std::vector<u64> start(P1 + 1);
@@ -372,20 +442,23 @@ int elba_fe_count(elba_fe_ctx *ctx)
             const size_t smem1 = sizeof(u64) * S1_TILE + 2 * sizeof(u32) * P1;
             EventPair &pp = next_pair(ctx->pev, ctx->pev_used);
             CK(cudaEventRecord(pp.a, st));
+            bool uniform = true;
             for (int lay = 0; lay < 2; ++lay)
             {
                 CK(ctx->partbuf.ensure(sizeof(u64) * std::max<u64>(start[P1], 1)));
                 CK(cudaMemcpyAsync(ctx->phist.p, start.data(), sizeof(u64) * (P1 + 1), cudaMemcpyHostToDevice, st));
                 CK(cudaMemsetAsync(ctx->pcursor.p, 0, sizeof(u32) * (P1 + 1), st));
                 CK(cudaMemsetAsync(d_flag1, 0, 4, st));
-                if (lay == 0) k_scatter1<true><<<grid_for(ctx, 2), S1_THREADS, smem1, st>>>(rv, k, stride, P1, (u32)cap1, ctx->phist.as<u64>(), ctx->pcursor.as<u32>(), ctx->partbuf.as<u64>(), d_flag1);
-                else          k_scatter1<false><<<grid_for(ctx, 2), S1_THREADS, smem1, st>>>(rv, k, stride, P1, 0u, ctx->phist.as<u64>(), ctx->pcursor.as<u32>(), ctx->partbuf.as<u64>(), d_flag1);
+                if (uniform) k_scatter1<true><<<grid_for(ctx, 2), S1_THREADS, smem1, st>>>(rv, k, stride, P1, (u32)cap1, ctx->phist.as<u64>(), ctx->pcursor.as<u32>(), ctx->partbuf.as<u64>(), d_flag1);
+                else         k_scatter1<false><<<grid_for(ctx, 2), S1_THREADS, smem1, st>>>(rv, k, stride, P1, 0u, ctx->phist.as<u64>(), ctx->pcursor.as<u32>(), ctx->partbuf.as<u64>(), d_flag1);
                 CKL(); LAUNCHED(ctx);
                 u32 flag = 0;
                 CK(cudaMemcpyAsync(cnt.data(), ctx->pcursor.p, sizeof(u32) * P1, cudaMemcpyDeviceToHost, st));
                 CK(cudaMemcpyAsync(&flag, d_flag1, 4, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
-                if (!flag) break;
+                u64 anyflag = flag;
+                if (W > 1) { int rc0 = allreduce_u64(ctx, &anyflag, 1, ncclMax); if (rc0) return rc0; }
+                if (!anyflag) break;
                 if (lay == 1) return fail(ctx, ELBA_FE_ERR_CUDA, "level-1 scatter overflowed an exact layout");
                 // skewed partition sizes (heavy hitters): exact histogram, exact regions
                 CK(ctx->lut.ensure(sizeof(u64) * (P1 + 1)));
@@ -394,17 +467,64 @@ int elba_fe_count(elba_fe_ctx *ctx)
                 std::vector<u64> hist(P1);
                 CK(cudaMemcpyAsync(hist.data(), ctx->lut.p, sizeof(u64) * P1, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
-                for (u32 p = 0; p < P1; ++p) { if (hist[p] >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "level-1 partition exceeds 2^32 instances"); start[p + 1] = start[p] + ((hist[p] + 15) & ~15ull); }
+                u64 hmax = 0;
+                for (u32 p = 0; p < P1; ++p) hmax = std::max(hmax, hist[p]);
+                if (W > 1)
+                {
+                    // slabs must have one shape on every rank: uniform regions of the largest partition anywhere
+                    int rc0 = allreduce_u64(ctx, &hmax, 1, ncclMax); if (rc0) return rc0;
+                    cap1 = (hmax + 15) & ~15ull;
+                    if (cap1 >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "level-1 partition exceeds 2^32 instances");
+                    for (u32 p = 0; p <= P1; ++p) start[p] = (u64)p * cap1;
+                }
+                else
+                {
+                    if (hmax >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "level-1 partition exceeds 2^32 instances");
+                    for (u32 p = 0; p < P1; ++p) start[p + 1] = start[p] + ((hist[p] + 15) & ~15ull);
+                    uniform = false;
+                }
             }
             CK(cudaEventRecord(pp.b, st));
 
-            // ---- plan of level 2
-            std::vector<u32> plan(4 * (size_t)P1 + 2, 0);
-            u32 *pn = plan.data(), *pp2 = pn + P1, *ptile = pp2 + P1, *pbucket = ptile + P1 + 1;
-            std::vector<u32> slow;
-            for (u32 p = 0; p < P1; ++p)
+            // ---- several GPUs: partition p belongs to rank p / Pown; one personalised all-to-all of the slabs
+            //      (the reference's Alltoallv of 8-byte k-mers, src/KmerOps.cpp:151) and of their fill counts
+            const u64 *lvl2_in = ctx->partbuf.as<u64>();
+            u64 slab_stride = 0;
+            std::vector<u32> cnt_all;                   // [W][Pown] fills of my partitions in every rank's slab
+            if (W > 1)
             {
-                u64 n = cnt[p];
+                const u64 slab = (u64)Pown * cap1;
+                CK(ctx->recvbuf.ensure(sizeof(u64) * slab * W)); CK(ctx->recvcnt.ensure(sizeof(u32) * (size_t)P1));
+                CK(cudaEventRecord(ctx->ev_x0, st));
+                NC(ctx->comm.api->GroupStart());
+                for (int r = 0; r < W; ++r)
+                {
+                    NC(ctx->comm.api->Send(ctx->partbuf.as<u64>() + slab * r, slab, ncclUint64, r, ctx->comm.comm, st));
+                    NC(ctx->comm.api->Recv(ctx->recvbuf.as<u64>() + slab * r, slab, ncclUint64, r, ctx->comm.comm, st));
+                    NC(ctx->comm.api->Send(ctx->pcursor.as<u32>() + (size_t)Pown * r, Pown, ncclUint32, r, ctx->comm.comm, st));
+                    NC(ctx->comm.api->Recv(ctx->recvcnt.as<u32>() + (size_t)Pown * r, Pown, ncclUint32, r, ctx->comm.comm, st));
+                }
+                NC(ctx->comm.api->GroupEnd());
+                CK(cudaEventRecord(ctx->ev_x1, st));
+                cnt_all.resize(P1);
+                CK(cudaMemcpyAsync(cnt_all.data(), ctx->recvcnt.p, sizeof(u32) * (size_t)P1, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                lvl2_in = ctx->recvbuf.as<u64>(); slab_stride = slab;
+                ctx->exchange_bytes = sizeof(u64) * slab * (W - 1);
+            }
+            else cnt_all = cnt;
+
+            // ---- plan of level 2 over MY partitions (all of them on one GPU)
+            std::vector<u32> plan(4 * (size_t)Pown + 2, 0);
+            u32 *pn = plan.data(), *pp2 = pn + Pown, *ptile = pp2 + Pown, *pbucket = ptile + Pown + 1;
+            std::vector<u32> slow;
+            std::vector<u64> ntot(Pown, 0);
+            for (u32 p = 0; p < Pown; ++p)
+            {
+                u64 n = 0;
+                for (int j = 0; j < W; ++j) n += cnt_all[(size_t)j * Pown + p];
+                ntot[p] = n;
+                if (n >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "level-1 partition exceeds 2^32 instances");
                 // mean fill = BUCKET_CAP / 1.4: with repeats the bucket sizes are compound-Poisson (sigma ~ sqrt(mean * copy number))
                 u64 p2 = n ? std::max<u64>(1, (n * 7 / 5 + BUCKET_CAP - 1) / BUCKET_CAP) : 0;
                 if (p2 > MAX_P2) { slow.push_back(p); n = 0; p2 = 0; }
@@ -412,16 +532,18 @@ int elba_fe_count(elba_fe_ctx *ctx)
                 ptile[p + 1] = ptile[p] + (u32)((n + S2_TILE - 1) / S2_TILE);
                 pbucket[p + 1] = pbucket[p] + (u32)p2;
             }
-            const u32 nbuckets = pbucket[P1];
+            const u32 nbuckets = pbucket[Pown];
             CK(ctx->plan.ensure(sizeof(u32) * plan.size()));
             CK(cudaMemcpyAsync(ctx->plan.p, plan.data(), sizeof(u32) * plan.size(), cudaMemcpyHostToDevice, st));
             CK(ctx->bfill.ensure(sizeof(u32) * ((size_t)nbuckets + 1)));
-            u64 ovf_cap = std::max<u64>(ctx->ovf_cap, std::max<u64>(Ms / 16, 1u << 20));
+            u64 ovf_cap = std::max<u64>(ctx->ovf_cap, std::max<u64>(Ms_max / 16, 1u << 20));
             CK(ctx->ovf.ensure(sizeof(u64) * ovf_cap)); ctx->ovf_cap = ovf_cap;
             Overflow ovf{ctx->ovf.as<u64>(), d_ctr + 5, ovf_cap};
             CK(cudaMemsetAsync(ctx->bfill.p, 0, sizeof(u32) * ((size_t)nbuckets + 1), st));
-            PartPlan pl; pl.n = ctx->plan.as<u32>(); pl.p2 = pl.n + P1; pl.tile_start = pl.p2 + P1; pl.bucket_start = pl.tile_start + P1 + 1;
-            PartInput pi; pi.in = ctx->partbuf.as<u64>(); pi.W = 1; pi.slab_stride = 0; pi.part_start = ctx->phist.as<u64>(); pi.cnt = ctx->pcursor.as<u32>(); pi.P = P1;
+            PartPlan pl; pl.n = ctx->plan.as<u32>(); pl.p2 = pl.n + Pown; pl.tile_start = pl.p2 + Pown; pl.bucket_start = pl.tile_start + Pown + 1;
+            // my partitions start at region me * Pown of every slab; on one GPU that is region 0 of the only slab
+            PartInput pi; pi.in = lvl2_in; pi.W = (u32)W; pi.slab_stride = slab_stride; pi.part_start = ctx->phist.as<u64>(); pi.P = Pown;
+            pi.cnt = W > 1 ? ctx->recvcnt.as<u32>() : ctx->pcursor.as<u32>();
 
             // ---- groups of partitions whose sub-buckets fit one scratch buffer; two buffers, two streams
             const u64 group_buckets = std::max<u64>(MAX_P2, (ctx->scratch_mb << 20) / (sizeof(u64) * BUCKET_CAP));
@@ -432,17 +554,18 @@ int elba_fe_count(elba_fe_ctx *ctx)
             CK(cudaEventRecord(ctx->ev_fork, st));
             CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
             int which = 0; bool used_aux = false;
-            for (u32 g0 = 0; g0 < P1;)
+            for (u32 g0 = 0; g0 < Pown;)
             {
                 u32 g1 = g0 + 1;
-                while (g1 < P1 && (u64)(pbucket[g1 + 1] - pbucket[g0]) <= group_buckets) ++g1;
+                while (g1 < Pown && (u64)(pbucket[g1 + 1] - pbucket[g0]) <= group_buckets) ++g1;
                 const u32 nt = ptile[g1] - ptile[g0], nb = pbucket[g1] - pbucket[g0];
                 u32 p2max = 1; for (u32 p = g0; p < g1; ++p) p2max = std::max(p2max, pp2[p]);
                 if (nt)
                 {
                     cudaStream_t s2 = which ? ctx->aux : st; used_aux |= which != 0;
                     const size_t smem2 = sizeof(u64) * S2_TILE + 2 * sizeof(u32) * p2max;
-                    k_scatter2<true><<<std::min<u32>(nt, grid_for(ctx, 5)), S2_THREADS, smem2, s2>>>(pi, pl, P1, g0, g1, p2max, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ovf);
+                    if (W == 1) k_scatter2<true><<<std::min<u32>(nt, grid_for(ctx, 5)), S2_THREADS, smem2, s2>>>(pi, pl, P1, g0, g1, p2max, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ovf);
+                    else        k_scatter2<false><<<std::min<u32>(nt, grid_for(ctx, 5)), S2_THREADS, smem2, s2>>>(pi, pl, P1, g0, g1, p2max, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ovf);
                     CKL(); LAUNCHED(ctx);
                     k_count_buckets<<<std::min<u32>(nb, grid_for(ctx, 2)), CB_THREADS, smemc, s2>>>(pl, g0, g1, ctx->scratch[which].as<u64>(), ctx->bfill.as<u32>(), ovf,
                         lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
@@ -459,10 +582,12 @@ int elba_fe_count(elba_fe_ctx *ctx)
             u64 novf = 0;
             CK(cudaMemcpyAsync(&novf, d_ctr + 5, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            if (novf > ovf_cap)
+            u64 retry = novf > ovf_cap;
+            if (retry) ctx->ovf_cap = novf + (novf >> 3);      // the list length does not depend on scheduling: exact next time
+            if (W > 1) { int rc0 = allreduce_u64(ctx, &retry, 1, ncclMax); if (rc0) return rc0; }      // collective: everybody redoes the exchange
+            if (retry)
             {
                 if (attempt == 3) return fail(ctx, ELBA_FE_ERR_CUDA, "overflow list resize did not converge");
-                ctx->ovf_cap = novf + (novf >> 3);      // the list length does not depend on scheduling: exact next time
                 continue;
             }
             ctx->sz.slow_partitions = slow.size(); ctx->sz.overflow_instances = novf;
@@ -474,8 +599,10 @@ int elba_fe_count(elba_fe_ctx *ctx)
             }
             for (u32 p : slow)
             {
-                std::vector<std::pair<const u64*, u64>> slabs{{ctx->partbuf.as<u64>() + start[p], (u64)cnt[p]}};
-                int rc = count_with_global_table(ctx, slabs, cnt[p], rel_cap);
+                std::vector<std::pair<const u64*, u64>> slabs;
+                for (int j = 0; j < W; ++j)
+                    slabs.push_back({lvl2_in + (u64)j * slab_stride + (W > 1 ? (u64)p * cap1 : start[p]), (u64)cnt_all[(size_t)j * Pown + p]});
+                int rc = count_with_global_table(ctx, slabs, ntot[p], rel_cap);
                 if (rc) return rc;
             }
         }
@@ -484,17 +611,34 @@ int elba_fe_count(elba_fe_ctx *ctx)
         CK(cudaStreamSynchronize(st));
         R = h[0]; sumcnt = h[1]; D = h[2];
         if ((u32)h[3] != 0) return fail(ctx, ELBA_FE_ERR_CUDA, "count table overflow");
-        if (R <= rel_cap) break;
+        u64 retry = R > rel_cap;
+        if (W > 1) { int rc0 = allreduce_u64(ctx, &retry, 1, ncclMax); if (rc0) return rc0; }
+        if (!retry) break;
         if (attempt == 3) return fail(ctx, ELBA_FE_ERR_CUDA, "reliable list overflow after resize");
-        rel_cap = R;       // exact; redo the count
+        rel_cap = std::max(rel_cap, R);       // exact; redo the count
+    }
+    (void)me;
+    ctx->sz.distinct = D; ctx->sz.nnzA_pre = sumcnt;
+
+    // ---- several GPUs: every rank needs the whole reliable list (column ids are ranks among ALL reliable k-mers)
+    u64 *rk = ctx->rel_key.as<u64>(); u32 *rc_ = ctx->rel_cnt.as<u32>();
+    if (W > 1)
+    {
+        std::vector<u64> Rr;
+        int rc0 = allgather_u64(ctx, R, Rr); if (rc0) return rc0;
+        u64 Rt = 0; for (u64 v : Rr) Rt += v;
+        CK(ctx->rel_all_key.ensure(sizeof(u64) * std::max<u64>(Rt, 1))); CK(ctx->rel_all_cnt.ensure(sizeof(u32) * std::max<u64>(Rt, 1)));
+        if ((rc0 = allgatherv(ctx, ctx->rel_key.p, ctx->rel_all_key.p, Rr, sizeof(u64)))) return rc0;
+        if ((rc0 = allgatherv(ctx, ctx->rel_cnt.p, ctx->rel_all_cnt.p, Rr, sizeof(u32)))) return rc0;
+        rk = ctx->rel_all_key.as<u64>(); rc_ = ctx->rel_all_cnt.as<u32>(); R = Rt;
     }
     if (R >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers on one context");
-    ctx->sz.distinct = D; ctx->sz.reliable = R; ctx->sz.nnzA_pre = sumcnt;
+    ctx->sz.reliable = R;
 
     // the lists hold h = mix64(k-mer): back to k-mers, then column ids = rank by k-mer value: sort (key, count) by key
-    if (R) { k_unmix<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_key.as<u64>(), R); CKL(); LAUNCHED(ctx); }
+    if (R) { k_unmix<<<nblk(R, 256), 256, 0, st>>>(rk, R); CKL(); LAUNCHED(ctx); }
     CK(ctx->rel_key_s.ensure(sizeof(u64) * std::max<u64>(R, 1))); CK(ctx->rel_cnt_s.ensure(sizeof(u32) * std::max<u64>(R, 1)));
-    int rc = sort_pairs(ctx, ctx->rel_key.as<u64>(), ctx->rel_key_s.as<u64>(), ctx->rel_cnt.as<u32>(), ctx->rel_cnt_s.as<u32>(), R, 64 - 2 * k, 64);
+    int rc = sort_pairs(ctx, rk, ctx->rel_key_s.as<u64>(), rc_, ctx->rel_cnt_s.as<u32>(), R, 64 - 2 * k, 64);
     if (rc) return rc;
     // k-mer -> column id table in HBM, fronted by a blocked Bloom filter sized to stay L2-resident
     u64 lslots = std::max<u64>(R + R / 2 + 64, 1024);
@@ -514,6 +658,59 @@ int elba_fe_count(elba_fe_ctx *ctx)
     return 0;
 }
 
+// Several GPUs: block (i, j) of B = A[R_i, :] (x) A[C_j, :]^T on rank i * pc + j, inner (k-mer) dimension unsplit, so every
+// nonzero is folded on exactly one GPU in the canonical order and no partial results are merged across GPUs (the
+// reference's Sparse SUMMA, src/SharedSeeds.cpp:7, broadcasts panels stage by stage and merges).  Every rank built the
+// rows of A of its own reads; one all-gather of those row blocks gives each GPU all of A (read-major, already sorted,
+// since the ranks hold consecutive read ranges), from which it slices R_i as the left CSR and re-sorts C_j as the
+// right CSC.
+static int gather_operands(elba_fe_ctx *ctx)
+{
+    cudaStream_t st = ctx->stream;
+    const int W = ctx->comm.nranks, me = ctx->comm.rank, pr = ctx->comm.grid_rows, pc = ctx->comm.grid_cols;
+    const u64 nnzA = ctx->sz.nnzA, R = ctx->sz.reliable; const u32 N = ctx->n;
+    std::vector<u64> nz;
+    int rc = allgather_u64(ctx, nnzA, nz); if (rc) return rc;
+    u64 tot = 0; for (u64 v : nz) tot += v;
+    CK(ctx->pack_key.ensure(8 * std::max<u64>(nnzA, 1)));
+    CK(ctx->g_key.ensure(8 * std::max<u64>(tot, 1))); CK(ctx->g_pos.ensure(4 * std::max<u64>(tot, 1)));
+    if (N) { k_pack_rows<<<nblk((u64)N * 32, 256), 256, 0, st>>>(ctx->a_rowptr.as<int64_t>(), ctx->a_col.as<u32>(), N, (u64)ctx->read_id_offset, ctx->pack_key.as<u64>()); CKL(); LAUNCHED(ctx); }
+    if ((rc = allgatherv(ctx, ctx->pack_key.p, ctx->g_key.p, nz, 8))) return rc;
+    if ((rc = allgatherv(ctx, ctx->a_pos.p, ctx->g_pos.p, nz, 4))) return rc;
+    ctx->panel_bytes = 12 * (tot - nnzA);
+
+    const int bi = me / pc, bj = me % pc;
+    int64_t row0, nr, col0, ncb;
+    block_extent((int64_t)ctx->N_total, pr, bi, row0, nr);
+    block_extent((int64_t)ctx->N_total, pc, bj, col0, ncb);
+    // left: rows R_i are one contiguous slice
+    CK(ctx->l_rowptr.ensure(8 * ((size_t)nr + 2))); CK(ctx->r_ptr.ensure(8 * ((size_t)ncb + 2)));
+    k_read_ptr<<<nblk((u64)nr + 1, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), tot, (u64)row0, (u64)nr, ctx->l_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
+    k_read_ptr<<<nblk((u64)ncb + 1, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), tot, (u64)col0, (u64)ncb, ctx->r_ptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
+    int64_t lb = 0, le = 0, rb = 0, re = 0;
+    CK(cudaMemcpyAsync(&lb, ctx->l_rowptr.as<int64_t>(), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&le, ctx->l_rowptr.as<int64_t>() + nr, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&rb, ctx->r_ptr.as<int64_t>(), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&re, ctx->r_ptr.as<int64_t>() + ncb, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const u64 ln = (u64)(le - lb), rn = (u64)(re - rb);
+    CK(ctx->l_col.ensure(4 * std::max<u64>(ln, 1)));
+    k_sub_base<<<nblk((u64)nr + 1, 256), 256, 0, st>>>(ctx->l_rowptr.as<int64_t>(), (u64)nr, lb); CKL(); LAUNCHED(ctx);
+    if (ln) { k_slice_left<<<nblk(ln, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), (u64)lb, ln, ctx->l_col.as<u32>()); CKL(); LAUNCHED(ctx); }
+    // right: rows C_j, re-sorted by (column, read)
+    const int cb = bits_for(std::max<u64>(R, 2)), rbits = bits_for(std::max<u64>((u64)ncb, 2));
+    CK(ctx->r_key.ensure(8 * std::max<u64>(rn, 1))); CK(ctx->r_key2.ensure(8 * std::max<u64>(rn, 1))); CK(ctx->r_pos.ensure(4 * std::max<u64>(rn, 1)));
+    CK(ctx->r_row.ensure(4 * std::max<u64>(rn, 1))); CK(ctx->r_colptr.ensure(8 * (R + 2)));
+    if (rn) { k_slice_right<<<nblk(rn, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), (u64)rb, rn, (u64)col0, rbits, ctx->r_key.as<u64>()); CKL(); LAUNCHED(ctx); }
+    if ((rc = sort_pairs(ctx, ctx->r_key.as<u64>(), ctx->r_key2.as<u64>(), ctx->g_pos.as<u32>() + rb, ctx->r_pos.as<u32>(), rn, 0, cb + rbits))) return rc;
+    k_segment_ptr<<<nblk(R + 1, 256), 256, 0, st>>>(ctx->r_key2.as<u64>(), rn, R, rbits, ctx->r_colptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
+    if (rn) { k_split_swap<<<nblk(rn, 256), 256, 0, st>>>(ctx->r_key2.as<u64>(), rn, rbits, cb, ctx->r_row.as<u32>(), nullptr); CKL(); LAUNCHED(ctx); }
+    ctx->op.l_rowptr = ctx->l_rowptr.as<int64_t>(); ctx->op.l_col = ctx->l_col.as<u32>(); ctx->op.l_pos = ctx->g_pos.as<u32>() + lb; ctx->op.l_rows = (u32)nr; ctx->op.l_nnz = ln;
+    ctx->op.r_colptr = ctx->r_colptr.as<int64_t>(); ctx->op.r_row = ctx->r_row.as<u32>(); ctx->op.r_pos = ctx->r_pos.as<u32>();
+    ctx->op.row0 = row0; ctx->op.col0 = col0;
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 int elba_fe_build_A(elba_fe_ctx *ctx)
 {
@@ -522,15 +719,18 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     CK(cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = ctx->stream;
     ReadsView rv = view(ctx);
-    const u64 R = ctx->sz.reliable, npre = ctx->sz.nnzA_pre; const u32 N = ctx->n;
+    const u64 R = ctx->sz.reliable; u64 npre = ctx->sz.nnzA_pre; const u32 N = ctx->n;
+    const int W = ctx->comm.nranks;
     CK(cudaEventRecord(ctx->ev[4], st));
     ctx->lev_used = 0;
     const int cb = bits_for(std::max<u64>(R, 2)), rb = bits_for(std::max<u64>(N, 2));
     ctx->col_bits = cb; ctx->read_bits = rb;
     u64 *d_ctr = ctx->ctr.as<u64>();
     CK(cudaMemsetAsync(d_ctr, 0, 64, st));
-    const u64 cap = std::max<u64>(npre, 1);
-    CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); CK(ctx->seed_key2.ensure(8 * cap)); CK(ctx->seed_pos2.ensure(4 * cap));
+    // one GPU: counting already told how many instances belong to reliable k-mers.  Several GPUs: that number is
+    // known per OWNER, not per reader, so the triple buffers are sized by the candidate count.
+    u64 cap = std::max<u64>(npre, 1);
+    if (W == 1) { CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); }
     // sweep 2: every instance of a reliable k-mer -> (read, column, pos)
     u64 emitted = 0;
     {
@@ -554,8 +754,9 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
                 CK(cudaStreamSynchronize(st));
                 ctx->sz.candidates = ncand;
                 if (ncand > ccap) { if (attempt == 2) return fail(ctx, ELBA_FE_ERR_CUDA, "candidate list overflow after resize"); ccap = ncand + ncand / 8 + chunk_slack; continue; }
+                if (W > 1) { cap = std::max<u64>(ncand, 1); CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); }
                 if (ncand) { k_resolve<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->cand.as<Candidate>(), ncand, ctx->lut.as<Slot>(), ctx->lut_slots,
-                                 ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, npre, cb); CKL(); LAUNCHED(ctx); }
+                                 ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, cap, cb); CKL(); LAUNCHED(ctx); }
                 break;
             }
         }
@@ -563,7 +764,15 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
         CK(cudaMemcpyAsync(&emitted, d_ctr, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
-    if (emitted != npre) { char b[160]; snprintf(b, sizeof b, "seed emission produced %llu triples, counting promised %llu", (unsigned long long)emitted, (unsigned long long)npre); return fail(ctx, ELBA_FE_ERR_CUDA, b); }
+    {
+        // every instance of a reliable k-mer must have been found again: emitted == what counting promised (summed over the GPUs)
+        u64 chk[2] = {emitted, npre};
+        if (W > 1) { int rc0 = allreduce_u64(ctx, chk, 2, ncclSum); if (rc0) return rc0; }
+        if (chk[0] != chk[1]) { char b[160]; snprintf(b, sizeof b, "seed emission produced %llu triples, counting promised %llu", (unsigned long long)chk[0], (unsigned long long)chk[1]); return fail(ctx, ELBA_FE_ERR_CUDA, b); }
+        npre = emitted;
+        CK(ctx->seed_key.ensure(8 * std::max<u64>(npre, 1))); CK(ctx->seed_pos.ensure(4 * std::max<u64>(npre, 1)));
+        CK(ctx->seed_key2.ensure(8 * std::max<u64>(npre, 1))); CK(ctx->seed_pos2.ensure(4 * std::max<u64>(npre, 1)));
+    }
 
     int rc;
     // sort by (read, column); merge duplicates keeping the largest position
@@ -578,7 +787,7 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     const u64 na = std::max<u64>(nnzA, 1);
     CK(ctx->a_key.ensure(8 * na)); CK(ctx->a_pos.ensure(4 * na)); CK(ctx->a_col.ensure(4 * na)); CK(ctx->a_rowptr.ensure(8 * ((size_t)N + 2)));
     CK(ctx->at_key.ensure(8 * na)); CK(ctx->at_key2.ensure(8 * na)); CK(ctx->at_pos2.ensure(4 * na)); CK(ctx->at_row.ensure(4 * na)); CK(ctx->at_pos.ensure(4 * na));
-    CK(ctx->at_colptr.ensure(8 * (R + 2))); CK(ctx->prod.ensure(8 * ((size_t)N + 1)));
+    CK(ctx->at_colptr.ensure(8 * (R + 2)));
     if (npre) { k_dedupe_write<<<nblk(npre, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), ctx->seed_pos2.as<u32>(), ctx->idx.as<u64>(), npre, ctx->a_key.as<u64>(), ctx->a_pos.as<u32>()); CKL(); LAUNCHED(ctx); }
     k_segment_ptr<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, N, cb, ctx->a_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
     if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, cb, rb, ctx->a_col.as<u32>(), ctx->at_key.as<u64>()); CKL(); LAUNCHED(ctx); }
@@ -586,9 +795,15 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     if ((rc = sort_pairs(ctx, ctx->at_key.as<u64>(), ctx->at_key2.as<u64>(), ctx->a_pos.as<u32>(), ctx->at_pos.as<u32>(), nnzA, 0, cb + rb))) return rc;
     k_segment_ptr<<<nblk(R + 1, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, R, rb, ctx->at_colptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
     if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, rb, cb, ctx->at_row.as<u32>(), nullptr); CKL(); LAUNCHED(ctx); }
+    // operands of B = A (x) A^T: one GPU multiplies A by its own transpose
+    ctx->op.l_rowptr = ctx->a_rowptr.as<int64_t>(); ctx->op.l_col = ctx->a_col.as<u32>(); ctx->op.l_pos = ctx->a_pos.as<u32>(); ctx->op.l_rows = N; ctx->op.l_nnz = nnzA;
+    ctx->op.r_colptr = ctx->at_colptr.as<int64_t>(); ctx->op.r_row = ctx->at_row.as<u32>(); ctx->op.r_pos = ctx->at_pos.as<u32>();
+    ctx->op.row0 = ctx->op.col0 = ctx->read_id_offset;
+    if (W > 1) { rc = gather_operands(ctx); if (rc) return rc; }
     // products per row, F
+    CK(ctx->prod.ensure(8 * ((size_t)ctx->op.l_rows + 1)));
     CK(cudaMemsetAsync(d_ctr, 0, 64, st));
-    if (N) { k_row_products<<<nblk((u64)N * 32, 256), 256, 0, st>>>(ctx->a_rowptr.as<int64_t>(), ctx->a_col.as<u32>(), ctx->at_colptr.as<int64_t>(), N, ctx->prod.as<u64>(), d_ctr); CKL(); LAUNCHED(ctx); }
+    if (ctx->op.l_rows) { k_row_products<<<nblk((u64)ctx->op.l_rows * 32, 256), 256, 0, st>>>(ctx->op.l_rowptr, ctx->op.l_col, ctx->op.r_colptr, ctx->op.l_rows, ctx->prod.as<u64>(), d_ctr); CKL(); LAUNCHED(ctx); }
     u64 F = 0;
     CK(cudaMemcpyAsync(&F, d_ctr, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[5], st));
@@ -605,7 +820,8 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
     if (ctx->phase < 3) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_spgemm: call elba_fe_build_A first");
     CK(cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = ctx->stream;
-    const u32 N = ctx->n; const u64 nnzA = ctx->sz.nnzA;
+    const u32 N = ctx->op.l_rows; const u64 nnzA = ctx->op.l_nnz;       // rows of this GPU's block of B
+    ctx->b_rows = N;
     CK(cudaEventRecord(ctx->ev[6], st));
     ctx->sev_used = 0;
     CK(ctx->row_off.ensure(8 * ((size_t)N + 1))); CK(ctx->row_nnz.ensure(4 * ((size_t)N + 1)));
@@ -620,8 +836,8 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
         CK(cudaMemsetAsync(d_ctr, 0, 64, st)); CK(cudaMemsetAsync(ctx->bins.p, 0, 64, st));
         u32 *d_bins = ctx->bins.as<u32>(); u64 *d_maxprod = reinterpret_cast<u64*>(d_bins + 4);
         SpgemmArgs A;
-        A.a_rowptr = ctx->a_rowptr.as<int64_t>(); A.a_col = ctx->a_col.as<u32>(); A.a_pos = ctx->a_pos.as<u32>();
-        A.at_colptr = ctx->at_colptr.as<int64_t>(); A.at_row = ctx->at_row.as<u32>(); A.at_pos = ctx->at_pos.as<u32>();
+        A.a_rowptr = ctx->op.l_rowptr; A.a_col = ctx->op.l_col; A.a_pos = ctx->op.l_pos;
+        A.at_colptr = ctx->op.r_colptr; A.at_row = ctx->op.r_row; A.at_pos = ctx->op.r_pos;
         A.nrows = N; A.seed_count = ctx->cfg.seed_count;
         A.t_col = ctx->t_col.as<u32>(); A.t_num = ctx->t_num.as<int32_t>(); A.t_seeds = ctx->t_seeds.as<u32>(); A.cap = cap;
         A.counters = d_ctr; A.row_off = ctx->row_off.as<u64>(); A.row_nnz = ctx->row_nnz.as<u32>();
@@ -706,12 +922,97 @@ int elba_fe_timings(elba_fe_ctx *ctx, elba_fe_timings_t *out)
     if (ctx->phase >= 4 && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->tm.spgemm_ms = ms;
     if (ctx->phase >= 2) { ctx->tm.count_kernel_ms = sum_pairs(ctx->kev, ctx->kev_used); ctx->tm.partition_ms = sum_pairs(ctx->pev, ctx->pev_used); }
     if (ctx->phase >= 3) ctx->tm.lookup_ms = sum_pairs(ctx->lev, ctx->lev_used);
+    if (ctx->phase >= 2 && ctx->comm.nranks > 1 && cudaEventElapsedTime(&ms, ctx->ev_x0, ctx->ev_x1) == cudaSuccess) ctx->tm.exchange_ms = ms;
+    ctx->tm.exchange_mbytes = (float)((double)ctx->exchange_bytes / 1e6); ctx->tm.panel_mbytes = (float)((double)ctx->panel_bytes / 1e6);
     if (ctx->phase >= 4) ctx->tm.spgemm_kernel_ms = sum_pairs(ctx->sev, ctx->sev_used);
     *out = ctx->tm;
     return 0;
 }
 
 int elba_fe_reset_timings(elba_fe_ctx *ctx) { if (!ctx) return ELBA_FE_ERR_INVALID; std::memset(&ctx->tm, 0, sizeof ctx->tm); return 0; }
+
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------
+int elba_fe_comm_get_id(elba_fe_comm_id *id)
+{
+    elba_fe_ctx *ctx = nullptr;
+    if (!id) return fail(nullptr, ELBA_FE_ERR_INVALID, "null argument");
+    static_assert(sizeof(elba_fe_comm_id) >= sizeof(ncclUniqueId), "elba_fe_comm_id must hold an ncclUniqueId");
+    std::string err;
+    NcclApi *api = nccl_api(err);
+    if (!api) return fail(nullptr, ELBA_FE_ERR_COMM, err);
+    ncclUniqueId nid;
+    ncclResult_t r = api->GetUniqueId(&nid);
+    if (r != ncclSuccess) return fail(nullptr, ELBA_FE_ERR_COMM, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
+    std::memset(id, 0, sizeof *id);
+    std::memcpy(id, &nid, sizeof nid);
+    (void)ctx;
+    return 0;
+}
+
+int elba_fe_comm_init(elba_fe_ctx *ctx, const elba_fe_comm_id *id, int rank, int nranks)
+{
+    if (!ctx || !id) return ELBA_FE_ERR_INVALID;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, ELBA_FE_ERR_INVALID, "bad rank / nranks");
+    if (nranks > 64) return fail(ctx, ELBA_FE_ERR_INVALID, "at most 64 ranks");
+    if (ctx->comm.comm) return fail(ctx, ELBA_FE_ERR_STATE, "communicator already initialised");
+    CK(cudaSetDevice(ctx->cfg.device));
+    ctx->comm.rank = rank; ctx->comm.nranks = nranks;
+    default_grid(nranks, ctx->comm.grid_rows, ctx->comm.grid_cols);
+    if (nranks == 1) return 0;
+    std::string err;
+    ctx->comm.api = nccl_api(err);
+    if (!ctx->comm.api) return fail(ctx, ELBA_FE_ERR_COMM, err);
+    ncclUniqueId nid;
+    std::memcpy(&nid, id, sizeof nid);
+    NC(ctx->comm.api->CommInitRank(&ctx->comm.comm, nranks, nid, rank));
+    return 0;
+}
+
+int elba_fe_comm_set_grid(elba_fe_ctx *ctx, int grid_rows, int grid_cols)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (grid_rows < 1 || grid_cols < 1 || grid_rows * grid_cols != ctx->comm.nranks) return fail(ctx, ELBA_FE_ERR_INVALID, "grid_rows * grid_cols must equal the number of ranks");
+    ctx->comm.grid_rows = grid_rows; ctx->comm.grid_cols = grid_cols;
+    return 0;
+}
+
+int elba_fe_comm_info(elba_fe_ctx *ctx, int *rank, int *nranks, int *grid_rows, int *grid_cols, int64_t *row0, int64_t *nrows, int64_t *col0, int64_t *ncols)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (rank) *rank = ctx->comm.rank; if (nranks) *nranks = ctx->comm.nranks;
+    if (grid_rows) *grid_rows = ctx->comm.grid_rows; if (grid_cols) *grid_cols = ctx->comm.grid_cols;
+    int64_t o, l;
+    const int64_t Nt = ctx->comm.nranks > 1 ? (int64_t)ctx->N_total : (int64_t)ctx->n;
+    if (ctx->comm.nranks > 1) block_extent(Nt, ctx->comm.grid_rows, ctx->comm.rank / ctx->comm.grid_cols, o, l); else { o = ctx->read_id_offset; l = ctx->n; }
+    if (row0) *row0 = o; if (nrows) *nrows = l;
+    if (ctx->comm.nranks > 1) block_extent(Nt, ctx->comm.grid_cols, ctx->comm.rank % ctx->comm.grid_cols, o, l); else { o = ctx->read_id_offset; l = ctx->n; }
+    if (col0) *col0 = o; if (ncols) *ncols = l;
+    return 0;
+}
+
+void elba_fe_block_extent(int64_t n, int parts, int idx, int64_t *offset, int64_t *length)
+{
+    int64_t o = 0, l = 0;
+    if (parts > 0 && idx >= 0 && idx < parts) block_extent(n, parts, idx, o, l);
+    if (offset) *offset = o; if (length) *length = l;
+}
+
+int elba_fe_sizes_global(elba_fe_ctx *ctx, elba_fe_sizes_t *out)
+{
+    if (!ctx || !out) return ELBA_FE_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = ctx->sz;
+    if (ctx->comm.nranks == 1) return 0;
+    // sums over the GPUs; reliable / partitions / table_slots are global already
+    u64 v[10] = { ctx->sz.nreads, ctx->sz.num_kmers, ctx->sz.distinct, ctx->sz.nnzA_pre, ctx->sz.nnzA, ctx->sz.products, ctx->sz.nnzB_pre, ctx->sz.nnzB,
+                  ctx->sz.candidates, ctx->sz.overflow_instances };
+    int rc = allreduce_u64(ctx, v, 10, ncclSum);
+    if (rc) return rc;
+    out->nreads = v[0]; out->num_kmers = v[1]; out->distinct = v[2]; out->nnzA_pre = v[3]; out->nnzA = v[4]; out->products = v[5];
+    out->nnzB_pre = v[6]; out->nnzB = v[7]; out->candidates = v[8]; out->overflow_instances = v[9];
+    return 0;
+}
 
 // ---- results ---------------------------------------------------------------------------------------
 #define D2H(dst, src, bytes) do { if ((bytes) && (dst)) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream)); } while (0)
@@ -750,7 +1051,7 @@ int elba_fe_get_B(elba_fe_ctx *ctx, int64_t *rowptr, uint32_t *col, int32_t *num
     if (ctx->phase < 4) return fail(ctx, ELBA_FE_ERR_STATE, "B not built");
     cudaEvent_t a = ctx->ev[0], b = ctx->ev[1];
     CK(cudaEventRecord(a, ctx->stream));
-    D2H(rowptr, ctx->b_rowptr.p, 8 * ((size_t)ctx->n + 1)); D2H(col, ctx->b_col.p, 4 * ctx->sz.nnzB);
+    D2H(rowptr, ctx->b_rowptr.p, 8 * ((size_t)ctx->b_rows + 1)); D2H(col, ctx->b_col.p, 4 * ctx->sz.nnzB);
     D2H(numshared, ctx->b_num.p, 4 * ctx->sz.nnzB); D2H(seeds, ctx->b_seeds.p, 16 * ctx->sz.nnzB);
     CK(cudaEventRecord(b, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -762,12 +1063,12 @@ int elba_fe_get_B_triples(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t 
 {
     if (!ctx) return ELBA_FE_ERR_INVALID;
     if (ctx->phase < 4) return fail(ctx, ELBA_FE_ERR_STATE, "B not built");
-    u64 nnz = ctx->sz.nnzB; u32 N = ctx->n;
+    u64 nnz = ctx->sz.nnzB; u32 N = ctx->b_rows;
     std::vector<int64_t> rp((size_t)N + 1); std::vector<u32> c32(nnz);
     int rc = elba_fe_get_B(ctx, rp.data(), c32.data(), numshared, seeds);
     if (rc) return rc;
-    // global ids: rows by the caller's read offset; columns are global already on one GPU (= local + offset)
-    for (u32 r = 0; r < N; ++r) for (int64_t p = rp[r]; p < rp[r + 1]; ++p) { if (row) row[p] = (int64_t)r + ctx->read_id_offset; if (col) col[p] = (int64_t)c32[p] + ctx->read_id_offset; }
+    // global ids: this GPU's block starts at (row0, col0); on one GPU both are the caller's read offset
+    for (u32 r = 0; r < N; ++r) for (int64_t p = rp[r]; p < rp[r + 1]; ++p) { if (row) row[p] = (int64_t)r + ctx->op.row0; if (col) col[p] = (int64_t)c32[p] + ctx->op.col0; }
     return 0;
 }
 

@@ -48,7 +48,8 @@ class Sizes(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("upload_ms", C.c_float), ("count_ms", C.c_float), ("build_ms", C.c_float), ("spgemm_ms", C.c_float),
                 ("download_ms", C.c_float), ("count_kernel_ms", C.c_float), ("spgemm_kernel_ms", C.c_float),
-                ("kernel_launches", C.c_uint32), ("partition_ms", C.c_float), ("lookup_ms", C.c_float), ("reserved", C.c_float * 6)]
+                ("kernel_launches", C.c_uint32), ("partition_ms", C.c_float), ("lookup_ms", C.c_float), ("exchange_ms", C.c_float),
+                ("exchange_mbytes", C.c_float), ("panel_mbytes", C.c_float), ("reserved", C.c_float * 3)]
 
     def as_dict(self):
         return {n: (int(getattr(self, n)) if n == "kernel_launches" else float(getattr(self, n))) for n, _ in self._fields_ if n != "reserved"}
@@ -61,6 +62,7 @@ ABI_SYMBOLS = (
     "elba_fe_synchronize", "elba_fe_sizes", "elba_fe_get_kmers", "elba_fe_get_A", "elba_fe_get_AT", "elba_fe_get_B",
     "elba_fe_get_B_triples", "elba_fe_device_B", "elba_fe_device_A", "elba_fe_hll", "elba_fe_bloom", "elba_fe_get_kmer_stream",
     "elba_fe_timings", "elba_fe_reset_timings",
+    "elba_fe_comm_get_id", "elba_fe_comm_init", "elba_fe_comm_set_grid", "elba_fe_comm_info", "elba_fe_block_extent", "elba_fe_sizes_global",
 )
 
 _lib = None
@@ -170,6 +172,34 @@ class Context:
         self._ck(self.L.elba_fe_sizes(self.h, C.byref(s)))
         return s.as_dict()
 
+    def sizes_global(self) -> dict:
+        s = Sizes()
+        self._ck(self.L.elba_fe_sizes_global(self.h, C.byref(s)))
+        return s.as_dict()
+
+    # -- several GPUs (one Context per process / GPU) ---------------------------------------------
+    @staticmethod
+    def comm_get_id() -> bytes:
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        rc = L.elba_fe_comm_get_id(buf)
+        if rc != 0:
+            raise FrontEndError(f"elba_fe_comm_get_id failed ({rc}): {L.elba_fe_last_error(None).decode()}")
+        return buf.raw
+
+    def comm_init(self, comm_id: bytes, rank: int, nranks: int, grid=None):
+        buf = C.create_string_buffer(bytes(comm_id), 128)
+        self._ck(self.L.elba_fe_comm_init(self.h, buf, C.c_int(rank), C.c_int(nranks)))
+        if grid is not None:
+            self._ck(self.L.elba_fe_comm_set_grid(self.h, C.c_int(grid[0]), C.c_int(grid[1])))
+
+    def comm_info(self) -> dict:
+        i = [C.c_int() for _ in range(4)]
+        e = [C.c_int64() for _ in range(4)]
+        self._ck(self.L.elba_fe_comm_info(self.h, *[C.byref(x) for x in i], *[C.byref(x) for x in e]))
+        return dict(rank=i[0].value, nranks=i[1].value, grid_rows=i[2].value, grid_cols=i[3].value,
+                    row0=e[0].value, nrows=e[1].value, col0=e[2].value, ncols=e[3].value)
+
     def timings(self) -> dict:
         t = Timings()
         self._ck(self.L.elba_fe_timings(self.h, C.byref(t)))
@@ -199,7 +229,7 @@ class Context:
 
     def B(self):
         s = self.sizes()
-        rp, col = np.zeros(s["nreads"] + 1, np.int64), np.zeros(s["nnzB"], np.uint32)
+        rp, col = np.zeros(self.comm_info()["nrows"] + 1, np.int64), np.zeros(s["nnzB"], np.uint32)
         num, seeds = np.zeros(s["nnzB"], np.int32), np.zeros((s["nnzB"], 4), np.uint32)
         self._ck(self.L.elba_fe_get_B(self.h, _p(rp), _p(col), _p(num), _p(seeds)))
         return rp, col, num, seeds

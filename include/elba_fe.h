@@ -106,6 +106,24 @@ int elba_fe_spgemm(elba_fe_ctx *ctx);
 int elba_fe_run(elba_fe_ctx *ctx);
 int elba_fe_synchronize(elba_fe_ctx *ctx);
 
+/* ---- several GPUs: one context per GPU / process --------------------------------------------------------
+ * Replaces the MPI collectives of the path with NCCL over NVLink: the personalised all-to-all of
+ * k-mers (src/KmerOps.cpp:151; the second exchange :274 is not needed), the k-mer id Allreduce/Exscan (:371-374) and
+ * the operand broadcasts of the Sparse SUMMA (src/SharedSeeds.cpp:7).  Call order on every rank:
+ *   create -> comm_init -> [comm_set_grid] -> upload_reads(own contiguous block of reads, read_id_offset = its first
+ *   global id; ranks hold consecutive ranges in rank order) -> count -> build_A -> spgemm   (all collective).
+ * After count every rank holds the WHOLE reliable k-mer list (get_kmers); A / A^T are the rows of the rank's own
+ * reads (global column ids); B is block (i, j) of the pr x pc grid, rank = i * pc + j, block extents as CombBLAS
+ * distributes them (n / parts, remainder to the last; src/DistributedFastaData.cpp:21-29).  Results do not depend
+ * on the number of GPUs.  NCCL (libnccl.so.2) is loaded at comm_init with more than one rank, never before. */
+typedef struct { char internal[128]; } elba_fe_comm_id;
+int  elba_fe_comm_get_id(elba_fe_comm_id *id);                  /* on one rank; ship the bytes to the others (MPI_Bcast, a file, torch.distributed) */
+int  elba_fe_comm_init(elba_fe_ctx *ctx, const elba_fe_comm_id *id, int rank, int nranks);
+int  elba_fe_comm_set_grid(elba_fe_ctx *ctx, int grid_rows, int grid_cols);   /* default: 1x1, 1x2, 2x2, 2x4, ... (rows <= cols, most square) */
+/* this rank's place: grid, and the extent of its block of B (rows [row0, row0+nrows), columns [col0, col0+ncols)) */
+int  elba_fe_comm_info(elba_fe_ctx *ctx, int *rank, int *nranks, int *grid_rows, int *grid_cols, int64_t *row0, int64_t *nrows, int64_t *col0, int64_t *ncols);
+void elba_fe_block_extent(int64_t n, int parts, int idx, int64_t *offset, int64_t *length);
+
 /* ---- sizes (valid after the phase that produces them; synchronizes the stream) ----------------------- */
 typedef struct {
     uint64_t nreads;        /* N (local) */
@@ -125,6 +143,8 @@ typedef struct {
     uint64_t reserved[2];
 } elba_fe_sizes_t;
 int elba_fe_sizes(elba_fe_ctx *ctx, elba_fe_sizes_t *out);
+/* the same summed over the GPUs (collective); equals elba_fe_sizes on one GPU */
+int elba_fe_sizes_global(elba_fe_ctx *ctx, elba_fe_sizes_t *out);
 
 /* ---- results to host (caller allocates from elba_fe_sizes) ------------------------------------------- */
 /* reliable k-mers ascending by 64-bit value (== column id order) and their counts */
@@ -133,7 +153,7 @@ int elba_fe_get_kmers(elba_fe_ctx *ctx, uint64_t *kmer /*R*/, uint32_t *count /*
 int elba_fe_get_A(elba_fe_ctx *ctx, int64_t *rowptr, uint32_t *col, uint32_t *pos);
 /* A^T (= A in CSC): colptr[R+1], row[nnzA] (local read ids ascending within a column), pos[nnzA] */
 int elba_fe_get_AT(elba_fe_ctx *ctx, int64_t *colptr, uint32_t *row, uint32_t *pos);
-/* B in CSR: rowptr[N+1], col[nnzB] ascending, numshared[nnzB], seeds[nnzB*4] = {s0.q, s0.t, s1.q, s1.t}
+/* B in CSR (several GPUs: this rank's block, nrows of elba_fe_comm_info, local row / column ids): rowptr[N+1], col[nnzB] ascending, numshared[nnzB], seeds[nnzB*4] = {s0.q, s0.t, s1.q, s1.t}
  * (SharedSeeds::seeds[2] + numshared, include/SharedSeeds.hpp:94-95; q = position in the row read, t = in the column read) */
 int elba_fe_get_B(elba_fe_ctx *ctx, int64_t *rowptr, uint32_t *col, int32_t *numshared, uint32_t *seeds);
 /* the same as (row, col, ...) triples with GLOBAL ids, the layout the SpParMat triple constructor takes */
@@ -165,7 +185,10 @@ typedef struct {
     uint32_t kernel_launches; /* kernels of this library launched since create/reset */
     float partition_ms;     /* histogram + scatter kernels */
     float lookup_ms;        /* second sweep (seed emission) kernel */
-    float reserved[6];
+    float exchange_ms;      /* several GPUs: the all-to-all of the k-mer partitions */
+    float exchange_mbytes;  /* MB this rank sent in it */
+    float panel_mbytes;     /* MB this rank received in the all-gather of A's row blocks */
+    float reserved[3];
 } elba_fe_timings_t;
 int elba_fe_timings(elba_fe_ctx *ctx, elba_fe_timings_t *out);
 int elba_fe_reset_timings(elba_fe_ctx *ctx);

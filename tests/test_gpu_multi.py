@@ -1,0 +1,36 @@
+"""Several GPUs (NCCL over NVLink): results must not depend on the number of GPUs or on the grid.
+Needs >= 2 GPUs on the box (gpurun --gpus N); skipped otherwise."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _launch(world, args, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py")] + [str(a) for a in args]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "MULTI-GPU PARITY OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world,grid", [(2, "-"), (2, "2x1"), (4, "-"), (4, "1x4"), (8, "-")])
+def test_multi_gpu_parity_fixture(world, grid):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _launch(world, ["reads_fa", 17, 2, 8, grid], 29611 + world)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_parity_synthetic_hifi(world):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _launch(world, ["synth:300000,500,12000,0.01", 31, 2, 4, "-", 16], 29631 + world)

@@ -201,6 +201,9 @@ def main():
     ctx = frontend.Context(frontend.Params(k=k, lower=lo, upper=up, device=local, num_partitions=args.partitions))
     # run the library on torch's current stream so that torch CUDA events bracket its kernels
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        from elba_b200 import distributed as D
+        D.bootstrap_comm(ctx, dist, device=dev)      # the library's own NCCL communicator (k-mer all-to-all, panel all-gather)
 
     def barrier():
         if dist is not None:
@@ -219,7 +222,7 @@ def main():
         s = ctx.sizes()
         n = s["nnzB"]
         if out_host.get("cap", -1) < n:
-            out_host["rp"] = torch.empty(nreads + 1, dtype=torch.int64).pin_memory()
+            out_host["rp"] = torch.empty(ctx.comm_info()["nrows"] + 1, dtype=torch.int64).pin_memory()
             out_host["col"] = torch.empty(max(n, 1), dtype=torch.int32).pin_memory()
             out_host["num"] = torch.empty(max(n, 1), dtype=torch.int32).pin_memory()
             out_host["seeds"] = torch.empty(max(n, 1) * 4, dtype=torch.int32).pin_memory()
@@ -252,40 +255,51 @@ def main():
     sampler.start()
     ms_res, tm = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop()
-    sizes = ctx.sizes()
+    sizes_local = ctx.sizes()
+    sizes = ctx.sizes_global()              # whole-job totals (collective)
     ms_e2e, tm_e2e = timed(step_e2e, max(2, args.steps // 2), 1)
     sizes_e2e = ctx.sizes()
+    info = ctx.comm_info()
 
-    # whole-job totals
-    tot = torch.tensor([nreads, M, sizes["nnzA"], sizes["products"], sizes["nnzB_pre"], sizes["nnzB"], sizes["reliable"]], device=dev, dtype=torch.float64)
+    # per-phase device times: the slowest rank
+    keys = sorted(a for a in tm if a.endswith("_ms"))
+    tvec = torch.tensor([tm[a] for a in keys], device=dev, dtype=torch.float64)
     if dist is not None:
-        dist.all_reduce(tot)
-    tot_reads, tot_M, tot_nnzA, tot_F, tot_nnzB_pre, tot_nnzB, tot_R = [float(x) for x in tot.tolist()]
+        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
+    tm.update({a: float(v) for a, v in zip(keys, tvec.tolist())})
+    io = torch.tensor([hbuf.numel() + 16 * nreads, 8 * (info["nrows"] + 1) + 24 * sizes_e2e["nnzB"]], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(io)
+    tot_reads, tot_M, tot_nnzA, tot_F, tot_nnzB_pre, tot_nnzB, tot_R = [float(sizes[a]) for a in ("nreads", "num_kmers", "nnzA", "products", "nnzB_pre", "nnzB", "reliable")]
+    M = int(tot_M)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         # counting = everything the reference does in get_kmer_count_map_keys/values: our count phase + the seed-emission sweep
         t_count = (tm["count_ms"] + tm["lookup_ms"]) / 1000.0
-        bytes_count = 28.5 * M                      # 8 + 20 + 2*0.25 bytes per k-mer instance
+        bytes_count = 28.5 * M / world              # 8 + 20 + 2*0.25 bytes per k-mer instance; per GPU
         ach = bytes_count / t_count / 1e9 if t_count > 0 else 0.0
         t_sp = tm["spgemm_kernel_ms"] / 1000.0
-        bytes_sp = 8.0 * sizes["products"] + 8.0 * sizes["nnzA"] + 28.0 * sizes["nnzB_pre"]
+        bytes_sp = 8.0 * sizes_local["products"] + 8.0 * sizes_local["nnzA"] + 28.0 * sizes_local["nnzB_pre"]      # rank 0's block
         ach_sp = bytes_sp / t_sp / 1e9 if t_sp > 0 else 0.0
         line = {
             "metric": METRIC, "value": tot_reads / (ms_res / 1000.0), "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic" if "shape" in w else "reference fixture",
             "config": {"workload": args.workload, "desc": w["desc"] + (f" (scaled x{args.scale})" if args.scale != 1.0 else ""), "k": k, "lower": lo, "upper": up,
                        "reads": int(tot_reads), "kmer_instances": int(tot_M), "reliable_kmers": int(tot_R), "nnzA": int(tot_nnzA), "products": int(tot_F),
-                       "nnzB": int(tot_nnzB), "partitions": sizes["partitions"], "l2_policy": "inputs larger than L2 / every step rewrites count tables and partition buffers",
+                       "nnzB": int(tot_nnzB), "partitions": sizes["partitions"], "grid": f"{info['grid_rows']}x{info['grid_cols']}", "l2_policy": "inputs larger than L2 / every step rewrites count tables and partition buffers",
                        "timing": "CUDA events on the launching stream around K steps, max over ranks; per-phase numbers from the library's own CUDA events on the same stream"},
             "phases_ms": {a: round(b, 4) for a, b in tm.items() if a.endswith("_ms")},
-            "roofline": {"bound": "hbm", "kernel": "counting phase (k_part_hist + k_part_scatter + k_count_array + k_emit_seeds)",
+            "roofline": {"bound": "hbm", "kernel": "counting phase per GPU (k_scatter1 + k_scatter2 + k_count_buckets + k_probe_filter + k_resolve and the glue between them)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes": bytes_count, "seconds": t_count},
+                         "algorithmic_bytes": bytes_count, "seconds": t_count,
+                         "kernels_ps_per_instance": {"k_scatter1": 1e9 * tm["partition_ms"] / max(M / world, 1), "k_scatter2+k_count_buckets": 1e9 * tm["count_kernel_ms"] / max(M / world, 1),
+                                                     "k_probe_filter+k_resolve": 1e9 * tm["lookup_ms"] / max(M / world, 1)},
+                         "budget_ps_per_instance_at_50pct": 1e12 * 28.5 / (0.5 * peak * 1e9)},
             "roofline_spgemm": {"bound": "hbm", "kernel": "k_spgemm_warp + k_spgemm_block", "achieved": ach_sp, "peak": peak, "unit": "GB/s", "frac": ach_sp / peak,
                                 "algorithmic_bytes": bytes_sp, "seconds": t_sp},
-            "e2e": {"value": tot_reads / (ms_e2e / 1000.0), "unit": "reads/s", "h2d_bytes_per_step": int(hbuf.numel() + 16 * nreads),
-                    "d2h_bytes_per_step": int(8 * (nreads + 1) + 24 * sizes_e2e["nnzB"]), "ms_per_step": ms_e2e},
+            "e2e": {"value": tot_reads / (ms_e2e / 1000.0), "unit": "reads/s", "h2d_bytes_per_step": int(io[0].item()),
+                    "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_e2e},
             "gpu_launches": int(tm["kernel_launches"]), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -32,6 +32,12 @@
 #include <mutex>
 #include <vector>
 
+/* The (rows, cols, vals) SpParMat constructor merges duplicate coordinates with maximum<NT> (x < y ? y : x) when
+ * SumDuplicates is false (src/KmerOps.cpp:400 relies on it for A; include/Overlap.hpp:76-78 defines operator< so that
+ * src/PairwiseAlignment.cpp:97-103 can build R the same way).  B has no duplicate coordinates, so the order is never
+ * consulted; it only has to exist for the constructor to instantiate. */
+static inline bool operator<(const SharedSeeds& a, const SharedSeeds& b) { return a.getnumshared() < b.getnumshared(); }
+
 namespace
 {
 

@@ -19,6 +19,8 @@
 #include <pthread.h>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdlib>
 #include <vector>
 
@@ -106,6 +108,17 @@ inline void fold_ranks(std::vector<uint8_t>& tmp, int upto, int n, MPI_Datatype 
 static inline int MPI_Comm_rank(MPI_Comm, int *r) { *r = fake_mpi::t_rank; return 0; }
 static inline int MPI_Comm_size(MPI_Comm, int *s) { *s = fake_mpi::nranks(); return 0; }
 static inline int MPI_Barrier(MPI_Comm) { fake_mpi::barrier(); return 0; }
+static inline int MPI_Abort(MPI_Comm, int code) { std::fprintf(stderr, "MPI_Abort(%d)\n", code); std::abort(); return 0; }
+/* root's buffer to every rank-thread */
+static inline int MPI_Bcast(void *buf, int n, MPI_Datatype t, int root, MPI_Comm)
+{
+    using namespace fake_mpi;
+    if (nranks() == 1) return 0;
+    g_world->p0[t_rank] = buf; barrier();
+    if (t_rank != root) std::memcpy(buf, g_world->p0[root], (size_t)n * dtsize(t));
+    barrier();
+    return 0;
+}
 static inline double MPI_Wtime()
 {
     struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);

@@ -57,3 +57,21 @@ def test_parameter_validation_is_in_the_library():
         h = ctypes.c_void_p()
         assert L.elba_fe_create(ctypes.byref(cfg), ctypes.byref(h)) == -1, bad
         assert L.elba_fe_last_error(None)
+
+
+@pytest.mark.reference
+def test_cpp_shim_compiles_against_the_reference_headers():
+    """elba_b200/host/elba_fe_shim.cpp re-implements the reference's five driver functions on the C ABI.  It must
+    compile against the reference's OWN headers, unmodified (KmerOps.hpp, SharedSeeds.hpp, DnaBuffer.hpp, Kmer.hpp),
+    with the MPI / CombBLAS stand-ins of the test tree on the include path (neither library exists in this image).
+    Build container only: /root/reference is not on the GPU box."""
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "include", "KmerOps.hpp")):
+        pytest.skip("reference tree not present")
+    for k, lo, up in ((31, 15, 35), (17, 2, 8)):
+        cmd = ["g++", "-fsyntax-only", "-std=c++17", f"-DKMER_SIZE={k}", f"-DLOWER_KMER_FREQ={lo}", f"-DUPPER_KMER_FREQ={up}", "-DLOG_LEVEL=0",
+               "-I", os.path.join(ROOT, "oracle", "stubs"), "-I", os.path.join(ref, "include"), "-I", os.path.join(ref, "src"),
+               "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "elba_b200", "host", "elba_fe_shim.cpp")]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-3000:]

@@ -6,6 +6,7 @@
 #include "sketch.cuh"
 #include "matrix_build.cuh"
 #include "spgemm.cuh"
+#include "superkmer.cuh"
 #include "comm.cuh"
 #include <cub/cub.cuh>
 #include <string>
@@ -56,6 +57,8 @@ struct elba_fe_ctx
     DevBuf table, cand, ctr, partbuf, phist, pcursor, rel_key, rel_cnt, rel_key_s, rel_cnt_s, lut, filter;
     DevBuf plan, bfill, ovf, scratch[2];
     u64 ovf_cap = 0;
+    DevBuf skm_slab, skm_fill, skm_ovf;      // super-k-mer path: record slabs, per-bucket fill, overflow records
+    u64 skm_ovf_cap = 0;
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_x0 = nullptr, ev_x1 = nullptr;
     u64 exchange_bytes = 0, panel_bytes = 0;
     u64 scratch_mb = 64;
@@ -220,6 +223,7 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaFuncSetAttribute(k_scatter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_scatter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_count_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS));
+    cudaFuncSetAttribute(k_skm_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
     *out = ctx;
     return 0;
 }
@@ -235,7 +239,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
         &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->bins, &ctx->small_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
-        &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1],
+        &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
         &ctx->r_key, &ctx->r_key2, &ctx->r_pos, &ctx->r_colptr, &ctx->r_row, &ctx->r_ptr };
     for (DevBuf *b : all) b->release();
@@ -364,6 +368,81 @@ static int count_with_global_table(elba_fe_ctx *ctx, const std::vector<std::pair
     return 0;
 }
 
+// Counting through super-k-mers (superkmer.cuh), one GPU: reads -> 16-byte records in minimizer buckets -> one CTA per
+// bucket counts in shared memory.  Appends the reliable {h, count} to rel_key / rel_cnt exactly as the hash path does.
+// retry: the overflow list was too small (its exact size is known now).
+static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &retry)
+{
+    cudaStream_t st = ctx->stream;
+    ReadsView rv = view(ctx);
+    const int k = ctx->cfg.k; const u32 lower = ctx->cfg.lower, upper = ctx->cfg.upper;
+    const u64 Ms = ctx->Ms;
+    u64 *d_ctr = ctx->ctr.as<u64>(); u32 *d_err = reinterpret_cast<u32*>(d_ctr + 3);
+    retry = false;
+    // buckets: mean fill BUCKET_CAP / 2.5 (a bucket is a handful of genomic super-k-mers times the coverage: CV ~ 0.4)
+    u64 mean_inst = BUCKET_CAP * 2 / 5;
+    if (const char *e = getenv("ELBA_FE_SKM_MEAN")) { long v = atol(e); if (v >= 64 && v <= (long)BUCKET_CAP) mean_inst = (u64)v; }
+    u64 NB = std::max<u64>(1, (Ms + mean_inst - 1) / mean_inst);
+    if (ctx->cfg.num_partitions > 1) NB = std::max<u64>(NB, (u64)ctx->cfg.num_partitions);
+    if (NB >= (1ull << 31)) return fail(ctx, ELBA_FE_ERR_INVALID, "too many minimizer buckets for one context");
+    // records per bucket: a chunk of 32 window starts holds 32 * 2 / (W + 1) minimizer runs plus the one its start cuts
+    const double avg_run = 32.0 / (64.0 / (double)(Wm + 1) + 1.0);
+    double slack = 2.5;
+    if (const char *e = getenv("ELBA_FE_SKM_SLACK")) { double v = atof(e); if (v >= 1.0 && v <= 16.0) slack = v; }
+    u64 rcap = (u64)((double)Ms / (double)NB / avg_run * slack) + 32;
+    rcap = std::min<u64>(rcap, SC_MAXREC);
+    ctx->sz.partitions = NB; ctx->sz.table_slots = BUCKET_SLOTS;
+    const u64 ovf_cap = std::max<u64>(ctx->skm_ovf_cap, std::max<u64>(Ms / 64, 1u << 16));
+    CK(ctx->skm_slab.ensure(sizeof(SkmRec) * NB * rcap)); CK(ctx->skm_fill.ensure(sizeof(u32) * NB)); CK(ctx->skm_ovf.ensure(sizeof(SkmRec) * ovf_cap));
+    ctx->skm_ovf_cap = ovf_cap;
+    CK(cudaMemsetAsync(ctx->skm_fill.p, 0, sizeof(u32) * NB, st));
+    RecSink sink; sink.slab = ctx->skm_slab.as<SkmRec>(); sink.fill = ctx->skm_fill.as<u32>(); sink.rcap = (u32)rcap; sink.NB = (u32)NB;
+    sink.ovf = ctx->skm_ovf.as<SkmRec>(); sink.ovf_cursor = d_ctr + 5; sink.ovf_inst = d_ctr + 6; sink.ovf_cap = ovf_cap;
+    const u32 nmax = skm_nmax(k);
+    EventPair &pp = next_pair(ctx->pev, ctx->pev_used);
+    CK(cudaEventRecord(pp.a, st));
+    if (ctx->nchunks)
+    {
+        const u32 g1 = (u32)std::min<u64>((ctx->nchunks + SK_THREADS - 1) / SK_THREADS, (u64)grid_for(ctx, 4));
+        switch (Wm)
+        {
+            case 8:  k_skm_scatter<8><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink); break;
+            case 12: k_skm_scatter<12><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink); break;
+            case 16: k_skm_scatter<16><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink); break;
+            case 17: k_skm_scatter<17><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink); break;
+            default: return fail(ctx, ELBA_FE_ERR_INVALID, "no super-k-mer kernel for this minimizer window");
+        }
+        CKL(); LAUNCHED(ctx);
+    }
+    CK(cudaEventRecord(pp.b, st));
+    RecSlabs in; in.base = ctx->skm_slab.as<SkmRec>(); in.slab_stride = 0; in.fill = ctx->skm_fill.as<u32>(); in.fill_stride = 0; in.W = 1; in.rcap = (u32)rcap;
+    RecOverflow ovf; ovf.list = ctx->skm_ovf.as<SkmRec>(); ovf.cursor = d_ctr + 5; ovf.inst = d_ctr + 6; ovf.cap = ovf_cap;
+    EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
+    CK(cudaEventRecord(ep.a, st));
+    k_skm_count<<<(u32)std::min<u64>(NB, (u64)grid_for(ctx, 2)), SC_THREADS, SC_SMEM, st>>>(in, (u32)NB, k, ovf, lower, upper,
+        ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
+    CKL(); LAUNCHED(ctx);
+    CK(cudaEventRecord(ep.b, st));
+    u64 o[2] = {0, 0};
+    CK(cudaMemcpyAsync(o, d_ctr + 5, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const u64 novf = o[0], ninst = o[1];
+    if (novf > ovf_cap) { ctx->skm_ovf_cap = novf + (novf >> 3); retry = true; return 0; }
+    ctx->sz.slow_partitions = 0; ctx->sz.overflow_instances = ninst;
+    if (novf)
+    {
+        const u64 slots = std::max<u64>(2 * ninst + 64, 1024);
+        if (slots >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "the overflow of the minimizer buckets needs a count table of more than 2^32 slots");
+        CK(ctx->table.ensure(sizeof(Slot) * slots));
+        k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), slots, EMPTY_H); CKL(); LAUNCHED(ctx);
+        TableRef T{ctx->table.as<Slot>(), (u32)slots};
+        k_skm_count_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->skm_ovf.as<SkmRec>(), novf, k, T, d_err, d_ctr + 2); CKL(); LAUNCHED(ctx);
+        k_table_collect<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
+        CKL(); LAUNCHED(ctx);
+    }
+    return 0;
+}
+
 int elba_fe_count(elba_fe_ctx *ctx)
 {
     if (!ctx) return ELBA_FE_ERR_INVALID;
@@ -400,6 +479,10 @@ int elba_fe_count(elba_fe_ctx *ctx)
     const bool direct = W == 1 && ((P1 == 1) || (P1 == 0 && Ms <= 65536));
     if (P1 == 0) P1 = (u32)std::min<u64>(MAX_P1, std::max<u64>(1, (Ms_total + PART_TARGET - 1) / PART_TARGET));
     if (direct) P1 = 1;
+    // k >= 20, one GPU, every window start: super-k-mers in minimizer buckets (superkmer.cuh); else the two-level hash partition
+    int skm_m = 0, skm_W = 0;
+    bool use_skm = !direct && W == 1 && stride == 1 && skm_geometry(k, skm_m, skm_W);
+    if (const char *e = getenv("ELBA_FE_COUNT_PATH")) { if (!std::strcmp(e, "hash")) use_skm = false; }
     if (W > 1) { P1 = (P1 + W - 1) / W * W; if (P1 > MAX_P1) P1 = MAX_P1 / W * W; }      // every rank owns P1 / W partitions
     const u32 Pown = P1 / (u32)W;
     ctx->sz.partitions = P1;
@@ -427,6 +510,17 @@ int elba_fe_count(elba_fe_ctx *ctx)
             CK(cudaEventRecord(ep.b, st));
             k_table_collect<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
             CKL(); LAUNCHED(ctx);
+        }
+        else if (use_skm)
+        {
+            bool again = false;
+            int rc0 = count_superkmers(ctx, skm_m, skm_W, rel_cap, again);
+            if (rc0) return rc0;
+            if (again)
+            {
+                if (attempt == 3) return fail(ctx, ELBA_FE_ERR_CUDA, "overflow list resize did not converge");
+                continue;
+            }
         }
         else
         {

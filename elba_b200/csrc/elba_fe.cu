@@ -59,6 +59,7 @@ struct elba_fe_ctx
     u64 ovf_cap = 0;
     DevBuf skm_slab, skm_fill, skm_ovf;      // super-k-mer path: record slabs, per-bucket fill, overflow records
     u64 skm_ovf_cap = 0;
+    bool seeds_fused = false; u64 nseeds_fused = 0;      // counting already wrote the seed list (ctx->cand) of this pass
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_x0 = nullptr, ev_x1 = nullptr;
     u64 exchange_bytes = 0, panel_bytes = 0;
     u64 scratch_mb = 64;
@@ -223,7 +224,10 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaFuncSetAttribute(k_scatter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_scatter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_count_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS));
-    cudaFuncSetAttribute(k_skm_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+    cudaFuncSetAttribute(k_skm_count<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+    cudaFuncSetAttribute(k_skm_count<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+    cudaFuncSetAttribute(k_skm_count<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+    cudaFuncSetAttribute(k_skm_count<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
     *out = ctx;
     return 0;
 }
@@ -369,8 +373,9 @@ static int count_with_global_table(elba_fe_ctx *ctx, const std::vector<std::pair
 }
 
 // Counting through super-k-mers (superkmer.cuh), one GPU: reads -> 16-byte records in minimizer buckets -> one CTA per
-// bucket counts in shared memory.  Appends the reliable {h, count} to rel_key / rel_cnt exactly as the hash path does.
-// retry: the overflow list was too small (its exact size is known now).
+// bucket counts in shared memory.  Appends the reliable {h, count} to rel_key / rel_cnt exactly as the hash path does,
+// and (fused pass 2) every instance of a reliable k-mer to the seed list ctx->cand, so build_A has no second sweep.
+// retry: the overflow list or the seed list was too small (their exact sizes are known now).
 static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &retry)
 {
     cudaStream_t st = ctx->stream;
@@ -379,6 +384,9 @@ static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &
     const u64 Ms = ctx->Ms;
     u64 *d_ctr = ctx->ctr.as<u64>(); u32 *d_err = reinterpret_cast<u32*>(d_ctr + 3);
     retry = false;
+    bool fuse = true; int threads = 512;
+    if (const char *e = getenv("ELBA_FE_FUSE")) fuse = atoi(e) != 0;
+    if (const char *e = getenv("ELBA_FE_SKM_THREADS")) { if (atoi(e) == 256) threads = 256; }
     // buckets: mean fill BUCKET_CAP / 2.5 (a bucket is a handful of genomic super-k-mers times the coverage: CV ~ 0.4)
     u64 mean_inst = BUCKET_CAP * 2 / 5;
     if (const char *e = getenv("ELBA_FE_SKM_MEAN")) { long v = atol(e); if (v >= 64 && v <= (long)BUCKET_CAP) mean_inst = (u64)v; }
@@ -393,8 +401,16 @@ static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &
     rcap = std::min<u64>(rcap, SC_MAXREC);
     ctx->sz.partitions = NB; ctx->sz.table_slots = BUCKET_SLOTS;
     const u64 ovf_cap = std::max<u64>(ctx->skm_ovf_cap, std::max<u64>(Ms / 64, 1u << 16));
-    CK(ctx->skm_slab.ensure(sizeof(SkmRec) * NB * rcap)); CK(ctx->skm_fill.ensure(sizeof(u32) * NB)); CK(ctx->skm_ovf.ensure(sizeof(SkmRec) * ovf_cap));
+    CK(ctx->skm_slab.ensure(sizeof(SkmRec) * NB * rcap)); CK(ctx->skm_fill.ensure(sizeof(u32) * NB));
+    CK(ctx->skm_ovf.ensure(sizeof(SkmRec) * ovf_cap));
     ctx->skm_ovf_cap = ovf_cap;
+    // seed list: {k-mer, pos, read} of every instance of a reliable k-mer; the size of the last pass, else a guess
+    u64 seed_guess = Ms / 16 + (1u << 20);
+    if (const char *e = getenv("ELBA_FE_SEED_CAP")) { long long v = atoll(e); if (v >= 1) seed_guess = (u64)v; }      // tests: force the resize
+    const u64 seed_cap = fuse ? std::max<u64>(ctx->cand_cap, seed_guess) : std::max<u64>(ctx->cand_cap, 1);
+    CK(ctx->cand.ensure(sizeof(Candidate) * seed_cap));
+    ctx->cand_cap = seed_cap;
+    SeedSink seeds; seeds.out = ctx->cand.as<Candidate>(); seeds.cursor = d_ctr + 7; seeds.cap = seed_cap;
     CK(cudaMemsetAsync(ctx->skm_fill.p, 0, sizeof(u32) * NB, st));
     RecSink sink; sink.slab = ctx->skm_slab.as<SkmRec>(); sink.fill = ctx->skm_fill.as<u32>(); sink.rcap = (u32)rcap; sink.NB = (u32)NB;
     sink.ovf = ctx->skm_ovf.as<SkmRec>(); sink.ovf_cursor = d_ctr + 5; sink.ovf_inst = d_ctr + 6; sink.ovf_cap = ovf_cap;
@@ -404,23 +420,42 @@ static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &
     if (ctx->nchunks)
     {
         const u32 g1 = (u32)std::min<u64>((ctx->nchunks + SK_THREADS - 1) / SK_THREADS, (u64)grid_for(ctx, 4));
+        const u64 iters = (ctx->nchunks + (u64)g1 * SK_THREADS - 1) / ((u64)g1 * SK_THREADS);
+        int contig = 1, nr = SK_NR;
+        if (const char *e = getenv("ELBA_FE_SKM_ORDER")) contig = std::strcmp(e, "strided") != 0;
+        if (const char *e = getenv("ELBA_FE_SKM_NR")) nr = atoi(e);
+        const u64 it1 = contig ? iters : (ctx->nchunks + (u64)g1 * SK_THREADS - 1) / ((u64)g1 * SK_THREADS);
         switch (Wm)
         {
-            case 8:  k_skm_scatter<8><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink); break;
-            case 12: k_skm_scatter<12><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink); break;
-            case 16: k_skm_scatter<16><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink); break;
-            case 17: k_skm_scatter<17><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink); break;
+            case 8:  k_skm_scatter<8, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig); break;
+            case 12: k_skm_scatter<12, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig); break;
+            case 16: if (nr == 1) k_skm_scatter<16, 1><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig);
+                     else k_skm_scatter<16, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig);
+                     break;
+            case 17: k_skm_scatter<17, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig); break;
             default: return fail(ctx, ELBA_FE_ERR_INVALID, "no super-k-mer kernel for this minimizer window");
         }
         CKL(); LAUNCHED(ctx);
     }
     CK(cudaEventRecord(pp.b, st));
-    RecSlabs in; in.base = ctx->skm_slab.as<SkmRec>(); in.slab_stride = 0; in.fill = ctx->skm_fill.as<u32>(); in.fill_stride = 0; in.W = 1; in.rcap = (u32)rcap;
+    RecSlabs in; in.slab = ctx->skm_slab.as<SkmRec>(); in.fill = ctx->skm_fill.as<u32>(); in.rcap = (u32)rcap;
     RecOverflow ovf; ovf.list = ctx->skm_ovf.as<SkmRec>(); ovf.cursor = d_ctr + 5; ovf.inst = d_ctr + 6; ovf.cap = ovf_cap;
     EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
     CK(cudaEventRecord(ep.a, st));
-    k_skm_count<<<(u32)std::min<u64>(NB, (u64)grid_for(ctx, 2)), SC_THREADS, SC_SMEM, st>>>(in, (u32)NB, k, ovf, lower, upper,
-        ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
+    {
+        const u32 gc = (u32)std::min<u64>(NB, (u64)grid_for(ctx, 2));
+        u64 *oh = ctx->rel_key.as<u64>(); u32 *oc = ctx->rel_cnt.as<u32>();
+        if (threads == 256)
+        {
+            if (fuse) k_skm_count<256, true><<<gc, 256, SC_SMEM, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
+            else      k_skm_count<256, false><<<gc, 256, SC_SMEM, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
+        }
+        else
+        {
+            if (fuse) k_skm_count<512, true><<<gc, 512, SC_SMEM, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
+            else      k_skm_count<512, false><<<gc, 512, SC_SMEM, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
+        }
+    }
     CKL(); LAUNCHED(ctx);
     CK(cudaEventRecord(ep.b, st));
     u64 o[2] = {0, 0};
@@ -437,8 +472,24 @@ static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &
         k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), slots, EMPTY_H); CKL(); LAUNCHED(ctx);
         TableRef T{ctx->table.as<Slot>(), (u32)slots};
         k_skm_count_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->skm_ovf.as<SkmRec>(), novf, k, T, d_err, d_ctr + 2); CKL(); LAUNCHED(ctx);
+        if (fuse) { k_skm_emit_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->skm_ovf.as<SkmRec>(), novf, k, T, lower, upper, seeds); CKL(); LAUNCHED(ctx); }
         k_table_collect<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
         CKL(); LAUNCHED(ctx);
+    }
+    ctx->seeds_fused = false;
+    if (fuse)
+    {
+        u64 h[2] = {0, 0};                                            // [0] sum of reliable counts, [1] seeds appended
+        CK(cudaMemcpyAsync(&h[0], d_ctr + 1, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h[1], d_ctr + 7, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h[1] > seed_cap) { ctx->cand_cap = h[1] + (h[1] >> 4) + 1024; retry = true; return 0; }
+        if (h[0] != h[1])
+        {
+            char b[160]; snprintf(b, sizeof b, "fused seed emission wrote %llu instances, the counts promise %llu", (unsigned long long)h[1], (unsigned long long)h[0]);
+            return fail(ctx, ELBA_FE_ERR_CUDA, b);
+        }
+        ctx->seeds_fused = true; ctx->nseeds_fused = h[1];
     }
     return 0;
 }
@@ -452,6 +503,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
     cudaStream_t st = ctx->stream;
     ReadsView rv = view(ctx);
     CK(cudaEventRecord(ctx->ev[2], st));
+    ctx->seeds_fused = false;
 
     // counters: [0] R cursor, [1] sum of reliable counts, [2] distinct, [3] (u32) table-overflow flag, [4] (u32) level-1 overflow flag
     CK(ctx->ctr.ensure(64));
@@ -743,10 +795,11 @@ int elba_fe_count(elba_fe_ctx *ctx)
     u64 fwords = std::max<u64>((R * bits_per_key + 63) / 64, 1024);
     CK(ctx->filter.ensure(8 * fwords));
     ctx->filter_words = (u32)fwords;
-    CK(cudaMemsetAsync(ctx->filter.p, 0, 8 * fwords, st));
+    const bool need_filter = !ctx->seeds_fused;          // the filter fronts sweep 2, which the fused seed list replaces
+    if (need_filter) CK(cudaMemsetAsync(ctx->filter.p, 0, 8 * fwords, st));
     k_table_clear<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->lut.as<Slot>(), lslots, EMPTY_KEY); CKL(); LAUNCHED(ctx);
     if (R) { k_lookup_build<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), (u32)R, ctx->lut.as<Slot>(), ctx->lut_slots,
-                                                       ctx->filter.as<u64>(), ctx->filter_words); CKL(); LAUNCHED(ctx); }
+                                                       need_filter ? ctx->filter.as<u64>() : nullptr, ctx->filter_words); CKL(); LAUNCHED(ctx); }
     CK(cudaEventRecord(ctx->ev[3], st));
     ctx->phase = 2;
     return 0;
@@ -830,7 +883,15 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     {
         EventPair &lp = next_pair(ctx->lev, ctx->lev_used);
         CK(cudaEventRecord(lp.a, st));
-        if (ctx->nchunks && R)
+        if (ctx->seeds_fused)
+        {
+            // counting already listed every instance of a reliable k-mer (superkmer.cuh): only the column ids are missing
+            const u64 ncand = ctx->nseeds_fused;
+            ctx->sz.candidates = ncand;
+            if (ncand) { k_resolve<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->cand.as<Candidate>(), ncand, ctx->lut.as<Slot>(), ctx->lut_slots,
+                             ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, cap, cb); CKL(); LAUNCHED(ctx); }
+        }
+        else if (ctx->nchunks && R)
         {
             // candidates = true instances + filter false positives (a few % of all instances); exact size after one try
             const u64 chunk_slack = (u64)grid_for(ctx, 2) * (PF_THREADS / 32) * PF_CHUNK;     // every warp may leave one chunk partly used

@@ -200,7 +200,7 @@ __global__ void k_lookup_build(const u64 *__restrict__ keys, const u32 *__restri
     if (i >= R) return;
     u64 x = keys[i];
     u64 h = mix64(x);
-    atomicOr(&filter[filter_word(h, fwords)], filter_bits(h));
+    if (filter) atomicOr(&filter[filter_word(h, fwords)], filter_bits(h));
     u32 s = lut_slot(h, lslots);
     while (true)
     {

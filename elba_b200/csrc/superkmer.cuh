@@ -33,9 +33,31 @@
 
 namespace elba {
 
-// 16-byte record: x = bases 0..31 of the run (base 0 at bits 63..62), y = bases 32..60 left-aligned | (n - 1) in the
-// low 5 bits.  A run of n k-mers holds n + k - 1 <= 61 bases, hence n <= min(32, 62 - k).
-typedef ulonglong2 SkmRec;
+// 32-byte record = one DRAM sector, written by ONE 256-bit store (STG.E.ENL2.256): x = bases 0..31 of the run (base 0 at
+// bits 63..62), y = bases 32..60 left-aligned | (n - 1) in the low 5 bits, meta = (local read << 32) | position of the
+// run's first window start (what pass 2 of the reference carries per instance, src/KmerOps.cpp:224-262).  A run of n
+// k-mers holds n + k - 1 <= 61 bases, hence n <= min(32, 62 - k).
+// Measured (profiles/r1_v6_scatter_records.md): with 16-byte records plus a separate 8-byte meta array the scatter is
+// bound by partially written sectors (L2 fills them from DRAM and writes them back more than once: 3.5 GB read +
+// 6.7 GB written for 3.6 GB of payload); a whole aligned sector per record needs no fill and is written once.
+struct __align__(32) SkmRec { u64 x, y, meta, spare; };
+struct SkmBases { u64 x, y; };
+
+__device__ __forceinline__ void skm_store(SkmRec *p, u64 x, u64 y, u64 meta)
+{
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" :: "l"(p), "l"(x), "l"(y), "l"(meta), "l"(0ull) : "memory");
+}
+__device__ __forceinline__ SkmBases skm_load_bases(const SkmRec *p)
+{
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    SkmBases b; b.x = v.x; b.y = v.y; return b;
+}
+__device__ __forceinline__ SkmRec skm_load(const SkmRec *p)
+{
+    SkmRec r;
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(r.x), "=l"(r.y), "=l"(r.meta), "=l"(r.spare) : "l"(p));
+    return r;
+}
 
 __host__ __device__ __forceinline__ u32 skm_nmax(int k) { return (u32)(62 - k < 32 ? 62 - k : 32); }
 
@@ -63,9 +85,9 @@ __device__ __forceinline__ u32 skm_bucket(u32 v, u32 NB)
     return __umulhi(v, NB);
 }
 
-// Where records go.  Bucket b (global numbering, NB of them) owns slab[b * rcap ...]; fill[b] counts every record
-// offered to it (records beyond rcap go to the overflow list, and k_skm_count then sends the rest of that bucket
-// there too, so that all instances of a k-mer are counted in one place).
+// Where records go.  Bucket b (NB of them) owns slab[b * rcap ...]; fill[b] counts every record offered to it (records
+// beyond rcap go to the overflow list, and k_skm_count then sends the rest of that bucket there too, so that all
+// instances of a k-mer are counted in one place).
 struct RecSink
 {
     SkmRec *slab; u32 *fill; u32 rcap; u32 NB;
@@ -73,9 +95,13 @@ struct RecSink
 };
 
 static constexpr int SK_THREADS = 256;
+static constexpr int SK_NR = 2;                       // records whose bucket reservations are in flight together
 
-template <int W>
-__global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int k, int m, u32 nmax, RecSink sink)
+// contig: CTA c walks the chunks [c * iters * SK_THREADS, (c + 1) * iters * SK_THREADS) in order, so a thread's next chunk
+// is SK_THREADS chunks further in the same or the next read: the read is found once by binary search and then followed.
+// Otherwise the grid strides over the chunks together and every chunk is located by its own binary search.
+template <int W, int NR>
+__global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int k, int m, u32 nmax, RecSink sink, u64 iters, int contig)
 {
     static_assert(W >= 1 && W <= 17, "the m-mers of a chunk must fit the 64 loaded bases");
     __shared__ u32 s_mn[CHUNK * SK_THREADS];          // minimizer of window start s of this thread's chunk: [s][tid]
@@ -85,12 +111,26 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
     const u32 tid = threadIdx.x;
     const u32 maskL = (m >= 16) ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> (2 * m));
     const u32 vs = 2u * (u32)(16 - m);
-    const u64 step = (u64)gridDim.x * SK_THREADS;
-    for (u64 g = (u64)blockIdx.x * SK_THREADS + tid; g < rv.nchunks; g += step)
+    u64 g = contig ? (u64)blockIdx.x * iters * SK_THREADS + tid : (u64)blockIdx.x * SK_THREADS + tid;
+    const u64 gstep = contig ? (u64)SK_THREADS : (u64)gridDim.x * SK_THREADS;
+    if (g >= rv.nchunks) return;
+    u32 read = find_read(rv.chunk_start, rv.n, g);
+    u64 cs0 = __ldg(rv.chunk_start + read), cs1 = __ldg(rv.chunk_start + read + 1);
+    u64 roff = __ldg(rv.off + read);
+    u32 rnk = __ldg(rv.len + read) - (u32)k + 1;
+    for (u64 it = 0; it < iters && g < rv.nchunks; ++it, g += gstep)
     {
-        ChunkInfo ci;
-        locate_chunk(rv, g, k, ci);
-        const u64 a = __ldg(rv.off + ci.read) + (ci.p0 >> 2);
+        if (g >= cs1)
+        {
+            if (contig) { do { ++read; cs1 = __ldg(rv.chunk_start + read + 1); } while (g >= cs1); }     // reads without chunks are stepped over
+            else { read = find_read(rv.chunk_start, rv.n, g); cs1 = __ldg(rv.chunk_start + read + 1); }
+            cs0 = __ldg(rv.chunk_start + read);
+            roff = __ldg(rv.off + read);
+            rnk = __ldg(rv.len + read) - (u32)k + 1;
+        }
+        const u32 p0 = (u32)(g - cs0) * CHUNK;
+        const u32 nk = min((u32)CHUNK, rnk - p0);
+        const u64 a = roff + (p0 >> 2);
         u64 w0, w1;
         load_bases64(rv.buf, a, w0, w1);
         // forward words T (base 16 i .. 16 i + 15 in T[i]) and the reverse complement of the 64-base window, shifted
@@ -130,35 +170,49 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
             bmask |= (x != prev ? 1u : 0u) << s;
             prev = x;
         }
-        const u32 nk = ci.nk;
         bmask &= (nk >= 32u) ? 0xFFFFFFFFu : ((1u << nk) - 1u);
-        // one record per run of equal minimizers
+        const u64 meta0 = ((u64)read << 32) | p0;
+        // one record per run of equal minimizers; the bucket reservations of SK_NR records are issued back to back
         while (bmask)
         {
-            const u32 s0 = __ffs(bmask) - 1;
-            bmask &= bmask - 1;
-            u32 n = (bmask ? (u32)__ffs(bmask) - 1u : nk) - s0;
-            if (n > nmax) { n = nmax; bmask |= 1u << (s0 + n); }
-            const u32 b = skm_bucket(s_mn[s0 * SK_THREADS + tid], sink.NB);
-            const u32 sh = 2 * s0;
-            SkmRec rec;
-            rec.x = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
-            rec.y = ((w1 << sh) & ~31ull) | (u64)(n - 1);
-            const u32 slot = atomicAdd(sink.fill + b, 1u);
-            if (slot < sink.rcap) sink.slab[(u64)b * sink.rcap + slot] = rec;
-            else
+            u32 b[NR], n[NR], slot[NR], s0[NR]; bool ok[NR]; SkmBases rec[NR];
+#pragma unroll
+            for (int i = 0; i < NR; ++i)
             {
-                const u64 o = atomicAdd(sink.ovf_cursor, 1ull);
-                atomicAdd(sink.ovf_inst, (u64)n);
-                if (o < sink.ovf_cap) sink.ovf[o] = rec;
+                ok[i] = bmask != 0;
+                if (ok[i])
+                {
+                    s0[i] = __ffs(bmask) - 1;
+                    bmask &= bmask - 1;
+                    n[i] = (bmask ? (u32)__ffs(bmask) - 1u : nk) - s0[i];
+                    if (n[i] > nmax) { n[i] = nmax; bmask |= 1u << (s0[i] + n[i]); }
+                    b[i] = skm_bucket(s_mn[s0[i] * SK_THREADS + tid], sink.NB);
+                    const u32 sh = 2 * s0[i];
+                    rec[i].x = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
+                    rec[i].y = ((w1 << sh) & ~31ull) | (u64)(n[i] - 1);
+                }
             }
+#pragma unroll
+            for (int i = 0; i < NR; ++i) if (ok[i]) slot[i] = atomicAdd(sink.fill + b[i], 1u);
+#pragma unroll
+            for (int i = 0; i < NR; ++i)
+                if (ok[i])
+                {
+                    if (slot[i] < sink.rcap) skm_store(sink.slab + ((u64)b[i] * sink.rcap + slot[i]), rec[i].x, rec[i].y, meta0 + s0[i]);
+                    else
+                    {
+                        const u64 o = atomicAdd(sink.ovf_cursor, 1ull);
+                        atomicAdd(sink.ovf_inst, (u64)n[i]);
+                        if (o < sink.ovf_cap) skm_store(sink.ovf + o, rec[i].x, rec[i].y, meta0 + s0[i]);
+                    }
+                }
         }
     }
 }
 
 // ---- counting ----------------------------------------------------------------------------------
 // k-mer j of a record, left-aligned
-__device__ __forceinline__ u64 skm_kmer(const SkmRec &rec, u32 j, u64 kmask)
+__device__ __forceinline__ u64 skm_kmer(const SkmBases &rec, u32 j, u64 kmask)
 {
     const u32 sh = 2 * j;
     const u64 f = sh ? ((rec.x << sh) | (rec.y >> (64 - sh))) : rec.x;
@@ -171,19 +225,18 @@ __device__ __forceinline__ u64 canonical_of(u64 fwd, int lsh)
     return fwd < rc ? fwd : rc;
 }
 
-// Records of the buckets this GPU counts: W slabs (one per source GPU; W = 1 on one GPU).  Slab j holds bucket b at
-// base[j * slab_stride + b * rcap ...] with fill[j * fill_stride + b] records offered.
-struct RecSlabs { const SkmRec *base; u64 slab_stride; const u32 *fill; u32 fill_stride; u32 W; u32 rcap; };
+// Records of the buckets this GPU counts: bucket b holds min(fill[b], rcap) records at slab[b * rcap ...].
+struct RecSlabs { const SkmRec *slab; const u32 *fill; u32 rcap; };
 struct RecOverflow { SkmRec *list; u64 *cursor; u64 *inst; u64 cap; };
+// Where the instances of reliable k-mers go (pass 2 of the reference, KmerOps.cpp:283-318, fused into counting):
+// {canonical k-mer, pos, local read} per instance; *cursor ends as their number even if cap was too small.
+struct SeedSink { Candidate *out; u64 *cursor; u64 cap; };
 
-static constexpr int SC_THREADS = 512;
-static constexpr int SC_PER = BUCKET_CAP / SC_THREADS;       // 12 instances per thread at most
-static constexpr int SC_GROUP = 6;                           // instances whose CAS are in flight together
 static constexpr u32 SC_MAXREC = 2048;                       // records of one bucket indexed in shared memory
-static constexpr int SC_RPT = SC_MAXREC / SC_THREADS;
-static constexpr int SC_SLOTS_PER = BUCKET_SLOTS / SC_THREADS;
-static constexpr u32 SC_MAXW = 64;
 static constexpr size_t SC_SMEM = (sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS + sizeof(u32) * (SC_MAXREC + 1);
+static constexpr u32 SC_OWNER = 0x8000u;                     // bit of an instance's slot code: this thread claimed the slot
+static_assert(BUCKET_SLOTS <= SC_OWNER, "slot codes are 16 bits");
+static_assert(BUCKET_CAP < 65536, "per-bucket tallies are packed in 16 bits");
 
 template <int NWARPS>
 __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *s_warp /*[NWARPS + 1]*/)
@@ -206,112 +259,140 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *s_warp /*[NWARPS
     return s_warp[w] + incl - v;
 }
 
-__device__ __forceinline__ const SkmRec *skm_rec_ptr(const RecSlabs &in, u32 b, u32 r, const u32 *s_cum)
+// The same scan over two 16-bit tallies packed in one word (low: reliable k-mers this thread claimed, high: instances
+// of reliable k-mers), with the two global reservations made by the lane that sees the totals: s_base[0] / [1].
+template <int NWARPS>
+__device__ __forceinline__ u32 block_scan_reserve(u32 v, u32 *s_warp, u64 *s_base, u64 *rel_cursor, u64 *seed_cursor)
 {
-    u32 j = 0;
-    while (r >= s_cum[j + 1]) ++j;
-    return in.base + (u64)j * in.slab_stride + (u64)b * in.rcap + (r - s_cum[j]);
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += t; }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0)
+    {
+        u32 x = lane < NWARPS ? s_warp[lane] : 0, ix = x;
+#pragma unroll
+        for (int o = 1; o < NWARPS; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, ix, o); if (lane >= (u32)o) ix += t; }
+        if (lane < NWARPS) s_warp[lane] = ix - x;
+        if (lane == NWARPS - 1)
+        {
+            const u32 nrel = ix & 0xFFFFu, nseed = ix >> 16;
+            s_base[0] = nrel ? atomicAdd(rel_cursor, (u64)nrel) : 0ull;
+            s_base[1] = nseed ? atomicAdd(seed_cursor, (u64)nseed) : 0ull;
+        }
+    }
+    __syncthreads();
+    return s_warp[w] + incl - v;
 }
 
-// counters: [0] reliable cursor, [1] sum of reliable counts, [2] distinct
-__global__ void __launch_bounds__(SC_THREADS, 2) k_skm_count(RecSlabs in, u32 nb, int k, RecOverflow ovf, u32 lower, u32 upper,
-                                                             u64 *__restrict__ out_h, u32 *__restrict__ out_cnt,
-                                                             u64 *__restrict__ counters, u64 cap)
+// counters: [0] reliable cursor, [1] sum of reliable counts, [2] distinct.
+// One CTA per bucket.  Every thread takes an equal range of consecutive instances (prefix sum over the records' n, one
+// binary search), counts them in the shared-memory table and remembers, per instance, the slot it ended in and
+// whether its CAS claimed that slot.  The claiming instance is the k-mer's one representative: it appends {h, count}
+// to the reliable list, so the table is never scanned; with EMIT every instance whose slot holds a reliable count
+// also appends its {k-mer, pos, read} to the seed list.
+template <int THREADS, bool EMIT>
+__global__ void __launch_bounds__(THREADS, 2) k_skm_count(RecSlabs in, u32 nb, int k, RecOverflow ovf, u32 lower, u32 upper,
+                                                          u64 *__restrict__ out_h, u32 *__restrict__ out_cnt,
+                                                          u64 *__restrict__ counters, u64 cap, SeedSink seeds)
 {
+    constexpr int NW = THREADS / 32;
+    constexpr int PER = BUCKET_CAP / THREADS;                 // instances per thread at most
+    constexpr int RPT = SC_MAXREC / THREADS;
+    constexpr int KEY_V = BUCKET_SLOTS / 2 / THREADS, CNT_V = BUCKET_SLOTS / 4 / THREADS;
+    static_assert(BUCKET_CAP % THREADS == 0 && PER % 2 == 0 && SC_MAXREC % THREADS == 0 && CNT_V >= 1, "geometry");
     extern __shared__ __align__(16) unsigned char s_raw[];
     u64 *s_key = reinterpret_cast<u64*>(s_raw);                       // [BUCKET_SLOTS]
     u32 *s_cnt = reinterpret_cast<u32*>(s_key + BUCKET_SLOTS);        // [BUCKET_SLOTS]
     u32 *s_start = s_cnt + BUCKET_SLOTS;                              // [SC_MAXREC + 1] first instance of record r
-    __shared__ u32 s_warp[SC_THREADS / 32 + 1];
-    __shared__ u32 s_cum[SC_MAXW + 1];
-    __shared__ u32 s_taint;
-    __shared__ u64 s_base;
-    const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    __shared__ u32 s_warp[NW + 1];
+    __shared__ u64 s_base[2];
+    const u32 tid = threadIdx.x, lane = tid & 31;
     const int lsh = 2 * (32 - k);
     const u64 kmask = (k == 32) ? ~0ull : (~0ull << lsh);
     u32 my_distinct = 0; u64 my_sum = 0;
     for (u32 b = blockIdx.x; b < nb; b += gridDim.x)
     {
-        if (tid == 0)
-        {
-            u32 cum = 0, taint = 0;
-            s_cum[0] = 0;
-            for (u32 j = 0; j < in.W; ++j)
-            {
-                const u32 f = __ldg(in.fill + (size_t)j * in.fill_stride + b);
-                taint |= f > in.rcap;
-                cum += min(f, in.rcap);
-                s_cum[j + 1] = cum;
-            }
-            s_taint = taint | (cum > SC_MAXREC);
-        }
-        __syncthreads();
-        const u32 nrec = s_cum[in.W];
-        bool spill = s_taint != 0;
+        const u32 f = __ldg(in.fill + b);
+        const u32 nrec = min(f, in.rcap);
+        const SkmRec *__restrict__ recs = in.slab + (u64)b * in.rcap;
+        bool spill = f > in.rcap || nrec > SC_MAXREC;                  // uniform across the CTA
         u32 total = 0;
         if (!spill)
         {
-            // instances per record -> first instance of every record
-            u32 nn[SC_RPT]; u32 sum = 0;
+            // clear the table (the previous bucket ended with a barrier)
 #pragma unroll
-            for (int i = 0; i < SC_RPT; ++i)
+            for (int j = 0; j < KEY_V; ++j)
             {
-                const u32 r = tid * SC_RPT + i;
-                nn[i] = r < nrec ? ((u32)__ldg(&skm_rec_ptr(in, b, r, s_cum)->y) & 31u) + 1u : 0u;
+                ulonglong2 e; e.x = EMPTY_H; e.y = EMPTY_H;
+                reinterpret_cast<ulonglong2*>(s_key)[j * THREADS + tid] = e;
+            }
+#pragma unroll
+            for (int j = 0; j < CNT_V; ++j) reinterpret_cast<uint4*>(s_cnt)[j * THREADS + tid] = make_uint4(0, 0, 0, 0);
+            // instances per record -> first instance of every record
+            u32 nn[RPT]; u32 sum = 0;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+            {
+                const u32 r = tid * RPT + i;
+                nn[i] = r < nrec ? ((u32)__ldg(&recs[r].y) & 31u) + 1u : 0u;
                 sum += nn[i];
             }
-            u32 run = block_exclusive_scan<SC_THREADS / 32>(sum, s_warp);
+            u32 run = block_exclusive_scan<NW>(sum, s_warp);
 #pragma unroll
-            for (int i = 0; i < SC_RPT; ++i) { const u32 r = tid * SC_RPT + i; if (r <= nrec) s_start[r] = run; run += nn[i]; }
-            total = s_warp[SC_THREADS / 32];
+            for (int i = 0; i < RPT; ++i) { const u32 r = tid * RPT + i; if (r <= nrec) s_start[r] = run; run += nn[i]; }
+            total = s_warp[NW];
             spill = total > BUCKET_CAP;
         }
-        if (spill)                                                     // uniform across the CTA
+        if (spill)
         {
-            if (tid == 0) s_base = atomicAdd(ovf.cursor, (u64)nrec);
+            if (tid == 0) s_base[0] = atomicAdd(ovf.cursor, (u64)nrec);
             __syncthreads();
             u32 ninst = 0;
-            for (u32 r = tid; r < nrec; r += SC_THREADS)
+            for (u32 r = tid; r < nrec; r += THREADS)
             {
-                const SkmRec rec = __ldg(skm_rec_ptr(in, b, r, s_cum));
+                const SkmRec rec = skm_load(recs + r);
                 ninst += ((u32)rec.y & 31u) + 1u;
-                const u64 o = s_base + r;
-                if (o < ovf.cap) ovf.list[o] = rec;
+                const u64 o = s_base[0] + r;
+                if (o < ovf.cap) skm_store(ovf.list + o, rec.x, rec.y, rec.meta);
             }
             for (int o = 16; o; o >>= 1) ninst += __shfl_xor_sync(0xffffffffu, ninst, o);
             if (lane == 0 && ninst) atomicAdd(ovf.inst, (u64)ninst);
             __syncthreads();
             continue;
         }
-        // clear the table
-#pragma unroll
-        for (int j = 0; j < SC_SLOTS_PER / 2; ++j)
-        {
-            ulonglong2 e; e.x = EMPTY_H; e.y = EMPTY_H;
-            reinterpret_cast<ulonglong2*>(s_key)[j * SC_THREADS + tid] = e;
-        }
-#pragma unroll
-        for (int j = 0; j < SC_SLOTS_PER / 4; ++j) reinterpret_cast<uint4*>(s_cnt)[j * SC_THREADS + tid] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        // this thread's instances: [i0, i0 + nv), consecutive, starting inside record r at k-mer j
-        const u32 c = (total + SC_THREADS - 1) / SC_THREADS;
+        __syncthreads();                                               // table cleared, s_start complete
+        // this thread's instances: [i0, i0 + nv), consecutive, starting inside record r0 at k-mer j0
+        const u32 c = (total + THREADS - 1) / THREADS;                 // uniform across the CTA
         const u32 i0 = tid * c;
         const u32 nv = i0 < total ? min(c, total - i0) : 0u;
+        u32 r0 = 0, j0 = 0;
+        u32 code[PER / 2];                                             // two 16-bit slot codes per word
         if (nv)
         {
             u32 lo = 0, hi = nrec;                                     // s_start[lo] <= i0 < s_start[hi]
             while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (s_start[mid] <= i0) lo = mid; else hi = mid; }
-            u32 r = lo, j = i0 - s_start[lo];
-            SkmRec rec = __ldg(skm_rec_ptr(in, b, r, s_cum));
-            SkmRec nxt = rec;
-            if (r + 1 < nrec) nxt = __ldg(skm_rec_ptr(in, b, r + 1, s_cum));
-            u32 n = ((u32)rec.y & 31u) + 1u;
-#pragma unroll
-            for (int g = 0; g < SC_PER; g += SC_GROUP)
+            r0 = lo; j0 = i0 - s_start[lo];
+        }
+        {
+            u32 r = r0, j = j0, n = 0;
+            SkmBases rec, nxt;
+            rec.x = rec.y = 0; nxt = rec;
+            if (nv)
             {
-                u64 H[SC_GROUP]; u32 S[SC_GROUP]; u64 P[SC_GROUP];
+                rec = skm_load_bases(recs + r); nxt = rec;
+                if (r + 1 < nrec) nxt = skm_load_bases(recs + r + 1);
+                n = ((u32)rec.y & 31u) + 1u;
+            }
 #pragma unroll
-                for (int q = 0; q < SC_GROUP; ++q)
+            for (int g = 0; g < PER; g += 2)
+            {
+                if ((u32)g >= c) break;                                // uniform
+                u64 H[2]; u32 S[2]; u64 P[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
                 {
                     H[q] = EMPTY_H;
                     if ((u32)(g + q) < nv)
@@ -319,17 +400,18 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_skm_count(RecSlabs in, u32 nb
                         if (j == n)
                         {
                             ++r; j = 0; rec = nxt; n = ((u32)rec.y & 31u) + 1u;
-                            if (r + 1 < nrec) nxt = __ldg(skm_rec_ptr(in, b, r + 1, s_cum));
+                            if (r + 1 < nrec) nxt = skm_load_bases(recs + r + 1);
                         }
                         H[q] = mix64(canonical_of(skm_kmer(rec, j, kmask), lsh));
                         ++j;
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < SC_GROUP; ++q)
+                for (int q = 0; q < 2; ++q)
                     if (H[q] != EMPTY_H) { S[q] = (u32)H[q] & (BUCKET_SLOTS - 1); P[q] = atomicCAS(&s_key[S[q]], EMPTY_H, H[q]); }
+                u32 cw = 0;
 #pragma unroll
-                for (int q = 0; q < SC_GROUP; ++q)
+                for (int q = 0; q < 2; ++q)
                     if (H[q] != EMPTY_H)
                     {
                         u32 s = S[q], stepp = 0; u64 pv = P[q];
@@ -339,33 +421,67 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_skm_count(RecSlabs in, u32 nb
                             pv = atomicCAS(&s_key[s], EMPTY_H, H[q]);
                         }
                         atomicAdd(&s_cnt[s], 1u);
+                        cw |= (s | (pv == EMPTY_H ? SC_OWNER : 0u)) << (16 * q);
                     }
+                code[g / 2] = cw;
             }
         }
-        __syncthreads();
-        // reliable k-mers of this bucket: count, reserve once per CTA, write
-        u32 rel = 0, nrel = 0;
+        __syncthreads();                                               // every count is final
+        // tallies of this thread: k-mers it claimed (distinct), reliable ones among them, instances of reliable k-mers
+        u32 tally2 = 0;
 #pragma unroll
-        for (int j = 0; j < SC_SLOTS_PER; ++j)
+        for (int g = 0; g < PER; ++g)
         {
-            const u32 cc = s_cnt[j * SC_THREADS + tid];
-            if (cc) { ++my_distinct; if (cc >= lower && cc <= upper) { rel |= 1u << j; ++nrel; my_sum += cc; } }
+            if ((u32)g >= c) break;
+            if ((u32)g < nv)
+            {
+                const u32 cd = (code[g / 2] >> (16 * (g & 1))) & 0xFFFFu;
+                const u32 cc = s_cnt[cd & (BUCKET_SLOTS - 1)];
+                const bool own = (cd & SC_OWNER) != 0, rel = cc >= lower && cc <= upper;
+                my_distinct += own ? 1u : 0u;
+                if (rel) tally2 += 0x10000u + (own ? 1u : 0u);
+            }
         }
-        const u32 excl = block_exclusive_scan<SC_THREADS / 32>(nrel, s_warp);
-        if (tid == 0) { const u32 tot = s_warp[SC_THREADS / 32]; s_base = tot ? atomicAdd(&counters[0], (u64)tot) : 0ull; }
-        __syncthreads();
-        if (nrel)
+        my_sum += tally2 >> 16;
+        const u32 excl = block_scan_reserve<NW>(tally2, s_warp, s_base, &counters[0], seeds.cursor);
+        if (tally2)
         {
-            u64 o = s_base + excl;
+            u64 o_rel = s_base[0] + (excl & 0xFFFFu), o_seed = s_base[1] + (excl >> 16);
+            u32 r = r0, j = j0;
+            SkmBases rec = skm_load_bases(recs + r);
+            u32 n = ((u32)rec.y & 31u) + 1u;
 #pragma unroll
-            for (int j = 0; j < SC_SLOTS_PER; ++j)
-                if (rel & (1u << j)) { if (o < cap) { out_h[o] = s_key[j * SC_THREADS + tid]; out_cnt[o] = s_cnt[j * SC_THREADS + tid]; } ++o; }
+            for (int g = 0; g < PER; ++g)
+            {
+                if ((u32)g >= c) break;
+                if ((u32)g < nv)
+                {
+                    if (j == n) { ++r; j = 0; rec = skm_load_bases(recs + r); n = ((u32)rec.y & 31u) + 1u; }
+                    const u32 cd = (code[g / 2] >> (16 * (g & 1))) & 0xFFFFu;
+                    const u32 s = cd & (BUCKET_SLOTS - 1);
+                    const u32 cc = s_cnt[s];
+                    if (cc >= lower && cc <= upper)
+                    {
+                        if (cd & SC_OWNER) { if (o_rel < cap) { out_h[o_rel] = s_key[s]; out_cnt[o_rel] = cc; } ++o_rel; }
+                        if (EMIT)
+                        {
+                            if (o_seed < seeds.cap)
+                            {
+                                const u64 mt = __ldg(&recs[r].meta);
+                                Candidate cnd; cnd.kmer = canonical_of(skm_kmer(rec, j, kmask), lsh); cnd.pos = (u32)mt + j; cnd.read = (u32)(mt >> 32);
+                                seeds.out[o_seed] = cnd;
+                            }
+                            ++o_seed;
+                        }
+                    }
+                    ++j;
+                }
+            }
         }
-        __syncthreads();
+        __syncthreads();                                               // the table and s_base are reused by the next bucket
     }
     for (int o = 16; o; o >>= 1) { my_distinct += __shfl_xor_sync(0xffffffffu, my_distinct, o); my_sum += __shfl_xor_sync(0xffffffffu, my_sum, o); }
     if (lane == 0) { if (my_distinct) atomicAdd(&counters[2], (u64)my_distinct); if (my_sum) atomicAdd(&counters[1], my_sum); }
-    (void)w;
 }
 
 // exact fallback: the k-mers of a list of records into the global table of kmer_count.cuh
@@ -382,12 +498,47 @@ __global__ void __launch_bounds__(256) k_skm_count_global(const SkmRec *__restri
         const u64 i = it * step + (u64)blockIdx.x * blockDim.x + threadIdx.x;
         if (i < nrec)
         {
-            const SkmRec rec = list[i];
+            const SkmBases rec = skm_load_bases(list + i);
             const u32 n = ((u32)rec.y & 31u) + 1u;
             for (u32 j = 0; j < n; ++j) nd += table_insert(T, mix64(canonical_of(skm_kmer(rec, j, kmask), lsh)), 1u, err);
         }
     }
     tally(distinct, nd);
+}
+
+// pass 2 of the same fallback, before the table is collected and reset: every instance of the listed records whose
+// k-mer ended with a reliable count appends its {k-mer, pos, read} to the seed list (rare path: one atomic per hit)
+__global__ void __launch_bounds__(256) k_skm_emit_global(const SkmRec *__restrict__ list, u64 nrec, int k,
+                                                         TableRef T, u32 lower, u32 upper, SeedSink seeds)
+{
+    const int lsh = 2 * (32 - k);
+    const u64 kmask = (k == 32) ? ~0ull : (~0ull << lsh);
+    const u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += step)
+    {
+        const SkmBases rec = skm_load_bases(list + i);
+        const u64 mt = __ldg(&list[i].meta);
+        const u32 n = ((u32)rec.y & 31u) + 1u;
+        for (u32 j = 0; j < n; ++j)
+        {
+            const u64 x = canonical_of(skm_kmer(rec, j, kmask), lsh);
+            const u64 h = mix64(x);
+            u32 s = slot_of(h, T.slots);
+            u32 cc = 0;
+            for (u32 probes = 0; probes <= MAX_PROBES; ++probes)
+            {
+                const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(T.tab + s));
+                if (v.x == h) { cc = (u32)v.y; break; }
+                if (v.x == EMPTY_H) break;
+                s = (s + 1 == T.slots) ? 0 : s + 1;
+            }
+            if (cc >= lower && cc <= upper)
+            {
+                const u64 o = atomicAdd(seeds.cursor, 1ull);
+                if (o < seeds.cap) { Candidate cnd; cnd.kmer = x; cnd.pos = (u32)mt + j; cnd.read = (u32)(mt >> 32); seeds.out[o] = cnd; }
+            }
+        }
+    }
 }
 
 } // namespace elba

@@ -104,3 +104,36 @@ def test_ragged_reads_k31():
         ref = O.run(dna, k, 2, 8)
         out = _run_cuda(dna, k, 2, 8, parts=5)
         _compare(out, ref, f"ragged k={k}")
+
+
+def test_fused_seed_list_variants(hifi):
+    """Pass 2 fused into counting (the default), the separate second sweep (ELBA_FE_FUSE=0) and the 256-thread CTA
+    shape must give the same bits; with the fused list build_A sees exactly nnzA_pre candidates (no filter false positives)."""
+    from oracle import oracle as O
+    ref = O.run(hifi, 31, 2, 4)
+    out = _run_cuda(hifi, 31, 2, 4)
+    _compare(out, ref, "fused")
+    assert out["sizes"]["candidates"] == ref.nnzA_pre
+    with _env(ELBA_FE_FUSE="0"):
+        out = _run_cuda(hifi, 31, 2, 4)
+    _compare(out, ref, "second sweep")
+    assert out["sizes"]["candidates"] >= ref.nnzA_pre
+    for fuse in ("1", "0"):
+        with _env(ELBA_FE_SKM_THREADS="256", ELBA_FE_FUSE=fuse):
+            out = _run_cuda(hifi, 27, 2, 6)
+        _compare(out, O.run(hifi, 27, 2, 6), f"256 threads fuse={fuse}")
+
+
+def test_fused_seed_list_resize_and_overflow_buckets(hifi):
+    """A seed list that is too small is resized to its exact size and the count redone; buckets that spill to the
+    global table emit their seeds from there (k_skm_emit_global).  Most instances are reliable here (L=2, U=60)."""
+    from oracle import oracle as O
+    ref = O.run(hifi, 31, 2, 60)
+    assert ref.nnzA_pre > 1_000_000
+    with _env(ELBA_FE_SEED_CAP="1000"):
+        out = _run_cuda(hifi, 31, 2, 60)
+    _compare(out, ref, "seed list resize")
+    with _env(ELBA_FE_SKM_SLACK="1.0", ELBA_FE_SEED_CAP="5000"):
+        out = _run_cuda(hifi, 31, 2, 60)
+    _compare(out, ref, "seed list resize + record overflow")
+    assert out["sizes"]["overflow_instances"] > 100_000

@@ -30,8 +30,10 @@ struct DevBuf
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        // a buffer that has to grow grows with headroom: sizes that wobble from pass to pass (chunked lists) must not
+        // cost a cudaFree + cudaMalloc (a device-wide synchronisation) per pass
         size_t want = (bytes + 255) & ~size_t(255);
+        if (p) { cudaFree(p); p = nullptr; cap = 0; want = (want + want / 8 + 255) & ~size_t(255); }
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want; else p = nullptr;
         return e;
@@ -60,6 +62,7 @@ struct elba_fe_ctx
     DevBuf skm_slab, skm_fill, skm_ovf;      // super-k-mer path: record slabs, per-bucket fill, overflow records
     u64 skm_ovf_cap = 0;
     bool seeds_fused = false; u64 nseeds_fused = 0;      // counting already wrote the seed list (ctx->cand) of this pass
+    u64 skm_reliable = 0;                                // super-k-mer path: reliable k-mers among the (holey) list entries handed out
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_x0 = nullptr, ev_x1 = nullptr;
     u64 exchange_bytes = 0, panel_bytes = 0;
     u64 scratch_mb = 64;
@@ -224,10 +227,10 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaFuncSetAttribute(k_scatter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_scatter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_count_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS));
-    cudaFuncSetAttribute(k_skm_count<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
-    cudaFuncSetAttribute(k_skm_count<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
-    cudaFuncSetAttribute(k_skm_count<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
-    cudaFuncSetAttribute(k_skm_count<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+    cudaFuncSetAttribute(k_skm_count<512, 8192, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_count_smem(8192, 512));
+    cudaFuncSetAttribute(k_skm_count<512, 8192, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_count_smem(8192, 512));
+    cudaFuncSetAttribute(k_skm_count<256, 4096, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_count_smem(4096, 256));
+    cudaFuncSetAttribute(k_skm_count<256, 4096, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_count_smem(4096, 256));
     *out = ctx;
     return 0;
 }
@@ -384,12 +387,13 @@ static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &
     const u64 Ms = ctx->Ms;
     u64 *d_ctr = ctx->ctr.as<u64>(); u32 *d_err = reinterpret_cast<u32*>(d_ctr + 3);
     retry = false;
-    bool fuse = true; int threads = 512;
+    bool fuse = true, small = false;
     if (const char *e = getenv("ELBA_FE_FUSE")) fuse = atoi(e) != 0;
-    if (const char *e = getenv("ELBA_FE_SKM_THREADS")) { if (atoi(e) == 256) threads = 256; }
-    // buckets: mean fill BUCKET_CAP / 2.5 (a bucket is a handful of genomic super-k-mers times the coverage: CV ~ 0.4)
-    u64 mean_inst = BUCKET_CAP * 2 / 5;
-    if (const char *e = getenv("ELBA_FE_SKM_MEAN")) { long v = atol(e); if (v >= 64 && v <= (long)BUCKET_CAP) mean_inst = (u64)v; }
+    if (const char *e = getenv("ELBA_FE_SKM_GEOM")) small = !std::strcmp(e, "small");      // 4 CTAs x 256 threads x 4096 slots per SM instead of 2 x 512 x 8192
+    const u32 slots = small ? 4096u : 8192u, bcap = skm_bucket_cap(slots);
+    // buckets: mean fill capacity / 2.5 (a bucket is a handful of genomic super-k-mers times the coverage: CV ~ 0.4)
+    u64 mean_inst = bcap * 2 / 5;
+    if (const char *e = getenv("ELBA_FE_SKM_MEAN")) { long v = atol(e); if (v >= 64 && v <= (long)bcap) mean_inst = (u64)v; }
     u64 NB = std::max<u64>(1, (Ms + mean_inst - 1) / mean_inst);
     if (ctx->cfg.num_partitions > 1) NB = std::max<u64>(NB, (u64)ctx->cfg.num_partitions);
     if (NB >= (1ull << 31)) return fail(ctx, ELBA_FE_ERR_INVALID, "too many minimizer buckets for one context");
@@ -399,20 +403,21 @@ static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &
     if (const char *e = getenv("ELBA_FE_SKM_SLACK")) { double v = atof(e); if (v >= 1.0 && v <= 16.0) slack = v; }
     u64 rcap = (u64)((double)Ms / (double)NB / avg_run * slack) + 32;
     rcap = std::min<u64>(rcap, SC_MAXREC);
-    ctx->sz.partitions = NB; ctx->sz.table_slots = BUCKET_SLOTS;
+    ctx->sz.partitions = NB; ctx->sz.table_slots = slots;
     const u64 ovf_cap = std::max<u64>(ctx->skm_ovf_cap, std::max<u64>(Ms / 64, 1u << 16));
-    CK(ctx->skm_slab.ensure(sizeof(SkmRec) * NB * rcap)); CK(ctx->skm_fill.ensure(sizeof(u32) * NB));
+    CK(ctx->skm_slab.ensure(sizeof(SkmRec) * NB * rcap)); CK(ctx->skm_fill.ensure(sizeof(u64) * NB));
     CK(ctx->skm_ovf.ensure(sizeof(SkmRec) * ovf_cap));
     ctx->skm_ovf_cap = ovf_cap;
     // seed list: {k-mer, pos, read} of every instance of a reliable k-mer; the size of the last pass, else a guess
-    u64 seed_guess = Ms / 16 + (1u << 20);
+    const u64 gc_max = (u64)grid_for(ctx, 4);                         // CTAs of k_skm_count: each may leave one chunk partly used
+    u64 seed_guess = Ms / 16 + (1u << 20) + gc_max * SEED_CHUNK;
     if (const char *e = getenv("ELBA_FE_SEED_CAP")) { long long v = atoll(e); if (v >= 1) seed_guess = (u64)v; }      // tests: force the resize
     const u64 seed_cap = fuse ? std::max<u64>(ctx->cand_cap, seed_guess) : std::max<u64>(ctx->cand_cap, 1);
     CK(ctx->cand.ensure(sizeof(Candidate) * seed_cap));
     ctx->cand_cap = seed_cap;
     SeedSink seeds; seeds.out = ctx->cand.as<Candidate>(); seeds.cursor = d_ctr + 7; seeds.cap = seed_cap;
-    CK(cudaMemsetAsync(ctx->skm_fill.p, 0, sizeof(u32) * NB, st));
-    RecSink sink; sink.slab = ctx->skm_slab.as<SkmRec>(); sink.fill = ctx->skm_fill.as<u32>(); sink.rcap = (u32)rcap; sink.NB = (u32)NB;
+    CK(cudaMemsetAsync(ctx->skm_fill.p, 0, sizeof(u64) * NB, st));
+    RecSink sink; sink.slab = ctx->skm_slab.as<SkmRec>(); sink.fill = ctx->skm_fill.as<u64>(); sink.rcap = (u32)rcap; sink.NB = (u32)NB;
     sink.ovf = ctx->skm_ovf.as<SkmRec>(); sink.ovf_cursor = d_ctr + 5; sink.ovf_inst = d_ctr + 6; sink.ovf_cap = ovf_cap;
     const u32 nmax = skm_nmax(k);
     EventPair &pp = next_pair(ctx->pev, ctx->pev_used);
@@ -438,28 +443,32 @@ static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &
         CKL(); LAUNCHED(ctx);
     }
     CK(cudaEventRecord(pp.b, st));
-    RecSlabs in; in.slab = ctx->skm_slab.as<SkmRec>(); in.fill = ctx->skm_fill.as<u32>(); in.rcap = (u32)rcap;
+    RecSlabs in; in.slab = ctx->skm_slab.as<SkmRec>(); in.fill = ctx->skm_fill.as<u64>(); in.rcap = (u32)rcap;
     RecOverflow ovf; ovf.list = ctx->skm_ovf.as<SkmRec>(); ovf.cursor = d_ctr + 5; ovf.inst = d_ctr + 6; ovf.cap = ovf_cap;
     EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
     CK(cudaEventRecord(ep.a, st));
     {
-        const u32 gc = (u32)std::min<u64>(NB, (u64)grid_for(ctx, 2));
         u64 *oh = ctx->rel_key.as<u64>(); u32 *oc = ctx->rel_cnt.as<u32>();
-        if (threads == 256)
+        if (small)
         {
-            if (fuse) k_skm_count<256, true><<<gc, 256, SC_SMEM, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
-            else      k_skm_count<256, false><<<gc, 256, SC_SMEM, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
+            const u32 gc = (u32)std::min<u64>(NB, (u64)grid_for(ctx, 4));
+            const size_t sm = skm_count_smem(4096, 256);
+            if (fuse) k_skm_count<256, 4096, 4, true><<<gc, 256, sm, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
+            else      k_skm_count<256, 4096, 4, false><<<gc, 256, sm, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
         }
         else
         {
-            if (fuse) k_skm_count<512, true><<<gc, 512, SC_SMEM, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
-            else      k_skm_count<512, false><<<gc, 512, SC_SMEM, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
+            const u32 gc = (u32)std::min<u64>(NB, (u64)grid_for(ctx, 2));
+            const size_t sm = skm_count_smem(8192, 512);
+            if (fuse) k_skm_count<512, 8192, 2, true><<<gc, 512, sm, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
+            else      k_skm_count<512, 8192, 2, false><<<gc, 512, sm, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
         }
     }
     CKL(); LAUNCHED(ctx);
     CK(cudaEventRecord(ep.b, st));
-    u64 o[2] = {0, 0};
+    u64 o[2] = {0, 0}, slots_before = 0;
     CK(cudaMemcpyAsync(o, d_ctr + 5, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&slots_before, d_ctr, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const u64 novf = o[0], ninst = o[1];
     if (novf > ovf_cap) { ctx->skm_ovf_cap = novf + (novf >> 3); retry = true; return 0; }
@@ -477,19 +486,24 @@ static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &
         CKL(); LAUNCHED(ctx);
     }
     ctx->seeds_fused = false;
-    if (fuse)
     {
-        u64 h[2] = {0, 0};                                            // [0] sum of reliable counts, [1] seeds appended
-        CK(cudaMemcpyAsync(&h[0], d_ctr + 1, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&h[1], d_ctr + 7, 8, cudaMemcpyDeviceToHost, st));
+        // [0] list entries handed out (chunks with holes + what the fallback appended), [1] sum of reliable counts,
+        // [2] seed entries handed out, [3] reliable k-mers the bucket kernel found
+        u64 h[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(&h[0], d_ctr, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h[2], d_ctr + 7, 16, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (h[1] > seed_cap) { ctx->cand_cap = h[1] + (h[1] >> 4) + 1024; retry = true; return 0; }
-        if (h[0] != h[1])
+        ctx->skm_reliable = h[3] + (h[0] - slots_before);
+        if (fuse)
         {
-            char b[160]; snprintf(b, sizeof b, "fused seed emission wrote %llu instances, the counts promise %llu", (unsigned long long)h[1], (unsigned long long)h[0]);
-            return fail(ctx, ELBA_FE_ERR_CUDA, b);
+            if (h[2] > seed_cap) { ctx->cand_cap = h[2] + (h[2] >> 4) + 1024; retry = true; return 0; }
+            if (h[2] < h[1])
+            {
+                char b[160]; snprintf(b, sizeof b, "fused seed emission handed out %llu entries, the counts promise %llu", (unsigned long long)h[2], (unsigned long long)h[1]);
+                return fail(ctx, ELBA_FE_ERR_CUDA, b);
+            }
+            ctx->seeds_fused = true; ctx->nseeds_fused = h[2];
         }
-        ctx->seeds_fused = true; ctx->nseeds_fused = h[1];
     }
     return 0;
 }
@@ -506,7 +520,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
     ctx->seeds_fused = false;
 
     // counters: [0] R cursor, [1] sum of reliable counts, [2] distinct, [3] (u32) table-overflow flag, [4] (u32) level-1 overflow flag
-    CK(ctx->ctr.ensure(64));
+    CK(ctx->ctr.ensure(128));
     u64 *d_ctr = ctx->ctr.as<u64>();
     u32 *d_err = reinterpret_cast<u32*>(d_ctr + 3);
     u32 *d_flag1 = reinterpret_cast<u32*>(d_ctr + 4);
@@ -541,12 +555,13 @@ int elba_fe_count(elba_fe_ctx *ctx)
 
     u64 rel_cap = Ms_max / lower + 1;
     if (rel_cap * 12 > (1ull << 30)) rel_cap = std::max<u64>(ctx->rel_cap, std::max<u64>(Ms_max / 8, (1ull << 30) / 12));
+    if (use_skm) rel_cap += (u64)grid_for(ctx, 4) * REL_CHUNK;           // the bucket kernel hands the list out in chunks
     u64 R = 0, sumcnt = 0, D = 0;
     for (int attempt = 0; attempt < 4; ++attempt)
     {
         CK(ctx->rel_key.ensure(sizeof(u64) * rel_cap)); CK(ctx->rel_cnt.ensure(sizeof(u32) * rel_cap));
         ctx->rel_cap = rel_cap;
-        CK(cudaMemsetAsync(ctx->ctr.p, 0, 64, st));
+        CK(cudaMemsetAsync(ctx->ctr.p, 0, 128, st));
         ctx->kev_used = 0; ctx->pev_used = 0;
         if (direct)
         {
@@ -765,6 +780,9 @@ int elba_fe_count(elba_fe_ctx *ctx)
     }
     (void)me;
     ctx->sz.distinct = D; ctx->sz.nnzA_pre = sumcnt;
+    // super-k-mer path: the list has holes (h = EMPTY_H -> k-mer = all ones, sorted behind every k-mer); R_list entries, R k-mers
+    u64 R_list = R;
+    if (use_skm) R = ctx->skm_reliable;
 
     // ---- several GPUs: every rank needs the whole reliable list (column ids are ranks among ALL reliable k-mers)
     u64 *rk = ctx->rel_key.as<u64>(); u32 *rc_ = ctx->rel_cnt.as<u32>();
@@ -776,15 +794,15 @@ int elba_fe_count(elba_fe_ctx *ctx)
         CK(ctx->rel_all_key.ensure(sizeof(u64) * std::max<u64>(Rt, 1))); CK(ctx->rel_all_cnt.ensure(sizeof(u32) * std::max<u64>(Rt, 1)));
         if ((rc0 = allgatherv(ctx, ctx->rel_key.p, ctx->rel_all_key.p, Rr, sizeof(u64)))) return rc0;
         if ((rc0 = allgatherv(ctx, ctx->rel_cnt.p, ctx->rel_all_cnt.p, Rr, sizeof(u32)))) return rc0;
-        rk = ctx->rel_all_key.as<u64>(); rc_ = ctx->rel_all_cnt.as<u32>(); R = Rt;
+        rk = ctx->rel_all_key.as<u64>(); rc_ = ctx->rel_all_cnt.as<u32>(); R = Rt; R_list = Rt;
     }
     if (R >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers on one context");
     ctx->sz.reliable = R;
 
     // the lists hold h = mix64(k-mer): back to k-mers, then column ids = rank by k-mer value: sort (key, count) by key
-    if (R) { k_unmix<<<nblk(R, 256), 256, 0, st>>>(rk, R); CKL(); LAUNCHED(ctx); }
-    CK(ctx->rel_key_s.ensure(sizeof(u64) * std::max<u64>(R, 1))); CK(ctx->rel_cnt_s.ensure(sizeof(u32) * std::max<u64>(R, 1)));
-    int rc = sort_pairs(ctx, rk, ctx->rel_key_s.as<u64>(), rc_, ctx->rel_cnt_s.as<u32>(), R, 64 - 2 * k, 64);
+    if (R_list) { k_unmix<<<nblk(R_list, 256), 256, 0, st>>>(rk, R_list); CKL(); LAUNCHED(ctx); }
+    CK(ctx->rel_key_s.ensure(sizeof(u64) * std::max<u64>(R_list, 1))); CK(ctx->rel_cnt_s.ensure(sizeof(u32) * std::max<u64>(R_list, 1)));
+    int rc = sort_pairs(ctx, rk, ctx->rel_key_s.as<u64>(), rc_, ctx->rel_cnt_s.as<u32>(), R_list, 64 - 2 * k, 64);    // the first R of R_list are k-mers
     if (rc) return rc;
     // k-mer -> column id table in HBM, fronted by a blocked Bloom filter sized to stay L2-resident
     u64 lslots = std::max<u64>(R + R / 2 + 64, 1024);

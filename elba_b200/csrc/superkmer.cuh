@@ -40,12 +40,15 @@ namespace elba {
 // Measured (profiles/r1_v6_scatter_records.md): with 16-byte records plus a separate 8-byte meta array the scatter is
 // bound by partially written sectors (L2 fills them from DRAM and writes them back more than once: 3.5 GB read +
 // 6.7 GB written for 3.6 GB of payload); a whole aligned sector per record needs no fill and is written once.
+// spare = (first instance of the run inside its bucket << 8) | n: both come out of the ONE 64-bit atomic that reserves the
+// record's slot (fill word: records offered in the low half, instances offered in the high half), so slot order and
+// instance order agree and the count kernel needs no prefix sum over the records.
 struct __align__(32) SkmRec { u64 x, y, meta, spare; };
 struct SkmBases { u64 x, y; };
 
-__device__ __forceinline__ void skm_store(SkmRec *p, u64 x, u64 y, u64 meta)
+__device__ __forceinline__ void skm_store(SkmRec *p, u64 x, u64 y, u64 meta, u64 spare)
 {
-    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" :: "l"(p), "l"(x), "l"(y), "l"(meta), "l"(0ull) : "memory");
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" :: "l"(p), "l"(x), "l"(y), "l"(meta), "l"(spare) : "memory");
 }
 __device__ __forceinline__ SkmBases skm_load_bases(const SkmRec *p)
 {
@@ -90,7 +93,7 @@ __device__ __forceinline__ u32 skm_bucket(u32 v, u32 NB)
 // instances of a k-mer are counted in one place).
 struct RecSink
 {
-    SkmRec *slab; u32 *fill; u32 rcap; u32 NB;
+    SkmRec *slab; u64 *fill; u32 rcap; u32 NB;
     SkmRec *ovf; u64 *ovf_cursor; u64 *ovf_inst; u64 ovf_cap;
 };
 
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
         // one record per run of equal minimizers; the bucket reservations of SK_NR records are issued back to back
         while (bmask)
         {
-            u32 b[NR], n[NR], slot[NR], s0[NR]; bool ok[NR]; SkmBases rec[NR];
+            u32 b[NR], n[NR], s0[NR]; u64 fw[NR]; bool ok[NR]; SkmBases rec[NR];
 #pragma unroll
             for (int i = 0; i < NR; ++i)
             {
@@ -193,17 +196,19 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
                 }
             }
 #pragma unroll
-            for (int i = 0; i < NR; ++i) if (ok[i]) slot[i] = atomicAdd(sink.fill + b[i], 1u);
+            for (int i = 0; i < NR; ++i) if (ok[i]) fw[i] = atomicAdd(sink.fill + b[i], ((u64)n[i] << 32) | 1ull);
 #pragma unroll
             for (int i = 0; i < NR; ++i)
                 if (ok[i])
                 {
-                    if (slot[i] < sink.rcap) skm_store(sink.slab + ((u64)b[i] * sink.rcap + slot[i]), rec[i].x, rec[i].y, meta0 + s0[i]);
+                    const u32 slot = (u32)fw[i];
+                    const u64 spare = ((fw[i] >> 32) << 8) | n[i];
+                    if (slot < sink.rcap) skm_store(sink.slab + ((u64)b[i] * sink.rcap + slot), rec[i].x, rec[i].y, meta0 + s0[i], spare);
                     else
                     {
                         const u64 o = atomicAdd(sink.ovf_cursor, 1ull);
                         atomicAdd(sink.ovf_inst, (u64)n[i]);
-                        if (o < sink.ovf_cap) skm_store(sink.ovf + o, rec[i].x, rec[i].y, meta0 + s0[i]);
+                        if (o < sink.ovf_cap) skm_store(sink.ovf + o, rec[i].x, rec[i].y, meta0 + s0[i], spare);
                     }
                 }
         }
@@ -225,18 +230,23 @@ __device__ __forceinline__ u64 canonical_of(u64 fwd, int lsh)
     return fwd < rc ? fwd : rc;
 }
 
-// Records of the buckets this GPU counts: bucket b holds min(fill[b], rcap) records at slab[b * rcap ...].
-struct RecSlabs { const SkmRec *slab; const u32 *fill; u32 rcap; };
+// Records of the buckets this GPU counts: bucket b holds min(records offered, rcap) records at slab[b * rcap ...];
+// fill[b] = (instances offered << 32) | records offered.
+struct RecSlabs { const SkmRec *slab; const u64 *fill; u32 rcap; };
 struct RecOverflow { SkmRec *list; u64 *cursor; u64 *inst; u64 cap; };
 // Where the instances of reliable k-mers go (pass 2 of the reference, KmerOps.cpp:283-318, fused into counting):
-// {canonical k-mer, pos, local read} per instance; *cursor ends as their number even if cap was too small.
+// {canonical k-mer, pos, local read} per instance.  Like the reliable list it is handed out in chunks that a CTA fills
+// on its own (one global atomic per SEED_CHUNK entries, off the critical path); unused entries are holes
+// (k-mer = EMPTY_KEY / h = EMPTY_H).  *cursor ends as the number of entries handed out even if cap was too small.
 struct SeedSink { Candidate *out; u64 *cursor; u64 cap; };
 
-static constexpr u32 SC_MAXREC = 2048;                       // records of one bucket indexed in shared memory
-static constexpr size_t SC_SMEM = (sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS + sizeof(u32) * (SC_MAXREC + 1);
+static constexpr u32 SC_MAXREC = 2048;                       // records of one bucket a CTA indexes
 static constexpr u32 SC_OWNER = 0x8000u;                     // bit of an instance's slot code: this thread claimed the slot
-static_assert(BUCKET_SLOTS <= SC_OWNER, "slot codes are 16 bits");
-static_assert(BUCKET_CAP < 65536, "per-bucket tallies are packed in 16 bits");
+static constexpr u32 SEED_CHUNK = 16384, REL_CHUNK = 16384;  // >= bucket capacity: one bucket always fits the rest of a fresh chunk
+static constexpr u32 SC_NOPAD = 0xFFFFFFFFu;
+// geometry of the bucket kernel: SLOTS-slot table, at most SLOTS * 3 / 4 instances per bucket (the table can never fill)
+__host__ __device__ constexpr u32 skm_bucket_cap(u32 slots) { return slots / 4 * 3; }
+__host__ __device__ constexpr size_t skm_count_smem(u32 slots, u32 threads) { return (sizeof(u64) + sizeof(u32)) * slots + sizeof(u32) * threads; }
 
 template <int NWARPS>
 __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *s_warp /*[NWARPS + 1]*/)
@@ -259,123 +269,132 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *s_warp /*[NWARPS
     return s_warp[w] + incl - v;
 }
 
-// The same scan over two 16-bit tallies packed in one word (low: reliable k-mers this thread claimed, high: instances
-// of reliable k-mers), with the two global reservations made by the lane that sees the totals: s_base[0] / [1].
-template <int NWARPS>
-__device__ __forceinline__ u32 block_scan_reserve(u32 v, u32 *s_warp, u64 *s_base, u64 *rel_cursor, u64 *seed_cursor)
-{
-    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    u32 incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += t; }
-    if (lane == 31) s_warp[w] = incl;
-    __syncthreads();
-    if (w == 0)
-    {
-        u32 x = lane < NWARPS ? s_warp[lane] : 0, ix = x;
-#pragma unroll
-        for (int o = 1; o < NWARPS; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, ix, o); if (lane >= (u32)o) ix += t; }
-        if (lane < NWARPS) s_warp[lane] = ix - x;
-        if (lane == NWARPS - 1)
-        {
-            const u32 nrel = ix & 0xFFFFu, nseed = ix >> 16;
-            s_base[0] = nrel ? atomicAdd(rel_cursor, (u64)nrel) : 0ull;
-            s_base[1] = nseed ? atomicAdd(seed_cursor, (u64)nseed) : 0ull;
-        }
-    }
-    __syncthreads();
-    return s_warp[w] + incl - v;
-}
-
-// counters: [0] reliable cursor, [1] sum of reliable counts, [2] distinct.
-// One CTA per bucket.  Every thread takes an equal range of consecutive instances (prefix sum over the records' n, one
-// binary search), counts them in the shared-memory table and remembers, per instance, the slot it ended in and
-// whether its CAS claimed that slot.  The claiming instance is the k-mer's one representative: it appends {h, count}
-// to the reliable list, so the table is never scanned; with EMIT every instance whose slot holds a reliable count
-// also appends its {k-mer, pos, read} to the seed list.
-template <int THREADS, bool EMIT>
-__global__ void __launch_bounds__(THREADS, 2) k_skm_count(RecSlabs in, u32 nb, int k, RecOverflow ovf, u32 lower, u32 upper,
+// counters: [0] reliable-list entries handed out (with holes), [1] sum of reliable counts, [2] distinct, [8] reliable k-mers.
+// One CTA per bucket, THREE barriers per bucket (ncu of the previous version: 36 % of the warp time was spent at its
+// seven barriers, behind two block scans and a global reservation per bucket).
+//   * The bucket's instance total and every record's first instance come from the scatter's fill word, so the c
+//     consecutive instances of thread t start in the record that covers instance t * c: the record's owner writes
+//     that into s_first[t].  No prefix sum.
+//   * Every thread counts its instances in the shared-memory table and remembers, per instance, the slot it ended in
+//     and whether its CAS claimed that slot.  The claiming instance is the k-mer's one representative: it appends
+//     {h, count} to the reliable list, so the table is never scanned; with EMIT every instance whose slot holds a
+//     reliable count also appends its {k-mer, pos, read} to the seed list.
+//   * Both lists are written into CTA-private chunks (offsets by shared-memory atomics); the fill word of the bucket
+//     after the next and the records of the next bucket are requested while this bucket is counted.
+template <int THREADS, int SLOTS, int MINB, bool EMIT>
+__global__ void __launch_bounds__(THREADS, MINB) k_skm_count(RecSlabs in, u32 nb, int k, RecOverflow ovf, u32 lower, u32 upper,
                                                           u64 *__restrict__ out_h, u32 *__restrict__ out_cnt,
                                                           u64 *__restrict__ counters, u64 cap, SeedSink seeds)
 {
-    constexpr int NW = THREADS / 32;
-    constexpr int PER = BUCKET_CAP / THREADS;                 // instances per thread at most
+    constexpr u32 CAP = skm_bucket_cap(SLOTS);
+    constexpr int PER = CAP / THREADS;                        // instances per thread at most
     constexpr int RPT = SC_MAXREC / THREADS;
-    constexpr int KEY_V = BUCKET_SLOTS / 2 / THREADS, CNT_V = BUCKET_SLOTS / 4 / THREADS;
-    static_assert(BUCKET_CAP % THREADS == 0 && PER % 2 == 0 && SC_MAXREC % THREADS == 0 && CNT_V >= 1, "geometry");
+    constexpr int KEY_V = SLOTS / 2 / THREADS, CNT_V = SLOTS / 4 / THREADS;
+    static_assert(CAP % THREADS == 0 && PER % 2 == 0 && SC_MAXREC % THREADS == 0 && CNT_V >= 1 && (SLOTS & (SLOTS - 1)) == 0, "geometry");
+    static_assert(SLOTS <= SC_OWNER && CAP < 65536 && CAP <= SEED_CHUNK && CAP <= REL_CHUNK, "slot codes and per-bucket tallies are 16 bits; a bucket fits a chunk");
     extern __shared__ __align__(16) unsigned char s_raw[];
-    u64 *s_key = reinterpret_cast<u64*>(s_raw);                       // [BUCKET_SLOTS]
-    u32 *s_cnt = reinterpret_cast<u32*>(s_key + BUCKET_SLOTS);        // [BUCKET_SLOTS]
-    u32 *s_start = s_cnt + BUCKET_SLOTS;                              // [SC_MAXREC + 1] first instance of record r
-    __shared__ u32 s_warp[NW + 1];
-    __shared__ u64 s_base[2];
+    u64 *s_key = reinterpret_cast<u64*>(s_raw);                       // [SLOTS]
+    u32 *s_cnt = reinterpret_cast<u32*>(s_key + SLOTS);        // [SLOTS]
+    u32 *s_first = s_cnt + SLOTS;                              // [THREADS] (record << 5 | k-mer in it) of thread t's first instance
+    __shared__ u64 s_spill_base, s_rel_base, s_seed_base, s_pad_rel_base, s_pad_seed_base;
+    __shared__ u32 s_rel_used, s_seed_used, s_pad_rel_from, s_pad_seed_from;
     const u32 tid = threadIdx.x, lane = tid & 31;
+    const u32 G = gridDim.x;
     const int lsh = 2 * (32 - k);
     const u64 kmask = (k == 32) ? ~0ull : (~0ull << lsh);
-    u32 my_distinct = 0; u64 my_sum = 0;
-    for (u32 b = blockIdx.x; b < nb; b += gridDim.x)
+    u32 my_distinct = 0, my_rel = 0; u64 my_sum = 0;
+    if (tid == 0) { s_rel_used = REL_CHUNK; s_seed_used = SEED_CHUNK; s_rel_base = 0; s_seed_base = 0; }     // no chunk yet
+    // software pipeline over this CTA's buckets: fill word two buckets ahead, round-0 record words one bucket ahead
+    u32 b = blockIdx.x;
+    u64 fw_cur = b < nb ? __ldg(in.fill + b) : 0ull;
+    u64 fw_nxt = (u64)b + G < nb ? __ldg(in.fill + b + G) : 0ull;
+    u64 sp_cur = (b < nb && tid < min((u32)fw_cur, in.rcap)) ? __ldg(&in.slab[(u64)b * in.rcap + tid].spare) : 0ull;
+    u64 fw_nn = 0, sp_nxt = 0;
+    __syncthreads();
+    for (; b < nb; b += G, fw_cur = fw_nxt, fw_nxt = fw_nn, sp_cur = sp_nxt)
     {
-        const u32 f = __ldg(in.fill + b);
+        fw_nn = (u64)b + 2ull * G < nb ? __ldg(in.fill + b + 2u * G) : 0ull;
+        sp_nxt = ((u64)b + G < nb && tid < min((u32)fw_nxt, in.rcap)) ? __ldg(&in.slab[(u64)(b + G) * in.rcap + tid].spare) : 0ull;
+        const u32 f = (u32)fw_cur, total = (u32)(fw_cur >> 32);
         const u32 nrec = min(f, in.rcap);
         const SkmRec *__restrict__ recs = in.slab + (u64)b * in.rcap;
-        bool spill = f > in.rcap || nrec > SC_MAXREC;                  // uniform across the CTA
-        u32 total = 0;
-        if (!spill)
-        {
-            // clear the table (the previous bucket ended with a barrier)
-#pragma unroll
-            for (int j = 0; j < KEY_V; ++j)
-            {
-                ulonglong2 e; e.x = EMPTY_H; e.y = EMPTY_H;
-                reinterpret_cast<ulonglong2*>(s_key)[j * THREADS + tid] = e;
-            }
-#pragma unroll
-            for (int j = 0; j < CNT_V; ++j) reinterpret_cast<uint4*>(s_cnt)[j * THREADS + tid] = make_uint4(0, 0, 0, 0);
-            // instances per record -> first instance of every record
-            u32 nn[RPT]; u32 sum = 0;
-#pragma unroll
-            for (int i = 0; i < RPT; ++i)
-            {
-                const u32 r = tid * RPT + i;
-                nn[i] = r < nrec ? ((u32)__ldg(&recs[r].y) & 31u) + 1u : 0u;
-                sum += nn[i];
-            }
-            u32 run = block_exclusive_scan<NW>(sum, s_warp);
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) { const u32 r = tid * RPT + i; if (r <= nrec) s_start[r] = run; run += nn[i]; }
-            total = s_warp[NW];
-            spill = total > BUCKET_CAP;
-        }
+        const bool spill = f > in.rcap || nrec > SC_MAXREC || total > CAP;      // uniform across the CTA
         if (spill)
         {
-            if (tid == 0) s_base[0] = atomicAdd(ovf.cursor, (u64)nrec);
+            if (tid == 0) s_spill_base = atomicAdd(ovf.cursor, (u64)nrec);
             __syncthreads();
             u32 ninst = 0;
             for (u32 r = tid; r < nrec; r += THREADS)
             {
                 const SkmRec rec = skm_load(recs + r);
                 ninst += ((u32)rec.y & 31u) + 1u;
-                const u64 o = s_base[0] + r;
-                if (o < ovf.cap) skm_store(ovf.list + o, rec.x, rec.y, rec.meta);
+                const u64 o = s_spill_base + r;
+                if (o < ovf.cap) skm_store(ovf.list + o, rec.x, rec.y, rec.meta, rec.spare);
             }
             for (int o = 16; o; o >>= 1) ninst += __shfl_xor_sync(0xffffffffu, ninst, o);
             if (lane == 0 && ninst) atomicAdd(ovf.inst, (u64)ninst);
             __syncthreads();
             continue;
         }
-        __syncthreads();                                               // table cleared, s_start complete
-        // this thread's instances: [i0, i0 + nv), consecutive, starting inside record r0 at k-mer j0
+        // room for this bucket in the CTA's output chunks (worst case: every instance reliable and distinct)
+        if (tid == 0)
+        {
+            u32 pr = SC_NOPAD, ps = SC_NOPAD;
+            if (s_rel_used + total > REL_CHUNK)
+            {
+                s_pad_rel_base = s_rel_base; pr = s_rel_used;
+                s_rel_base = atomicAdd(&counters[0], (u64)REL_CHUNK); s_rel_used = 0;
+            }
+            if (EMIT && s_seed_used + total > SEED_CHUNK)
+            {
+                s_pad_seed_base = s_seed_base; ps = s_seed_used;
+                s_seed_base = atomicAdd(seeds.cursor, (u64)SEED_CHUNK); s_seed_used = 0;
+            }
+            s_pad_rel_from = pr; s_pad_seed_from = ps;
+        }
+        // clear the table (the previous bucket ended with a barrier)
+#pragma unroll
+        for (int j = 0; j < KEY_V; ++j)
+        {
+            ulonglong2 e; e.x = EMPTY_H; e.y = EMPTY_H;
+            reinterpret_cast<ulonglong2*>(s_key)[j * THREADS + tid] = e;
+        }
+#pragma unroll
+        for (int j = 0; j < CNT_V; ++j) reinterpret_cast<uint4*>(s_cnt)[j * THREADS + tid] = make_uint4(0, 0, 0, 0);
+        // every thread takes c consecutive instances; the record that holds instance t * c tells thread t where to start
         const u32 c = (total + THREADS - 1) / THREADS;                 // uniform across the CTA
+        {
+            const u32 inv = c > 1 ? 0xFFFFFFFFu / c + 1u : 0u;         // ceil(2^32 / c): x / c == umulhi(x, inv) for x * c < 2^32
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+            {
+                if ((u32)(i * THREADS) >= nrec) break;                 // uniform
+                const u32 r = i * THREADS + tid;
+                if (r < nrec)
+                {
+                    const u64 sp = i == 0 ? sp_cur : __ldg(&recs[r].spare);
+                    const u32 a = (u32)(sp >> 8), e = a + ((u32)sp & 0xFFu) - 1u;
+                    const u32 t_lo = c > 1 ? __umulhi(a + c - 1, inv) : a, t_hi = c > 1 ? __umulhi(e, inv) : e;
+                    for (u32 t = t_lo; t <= t_hi; ++t) s_first[t] = (r << 5) | (t * c - a);
+                }
+            }
+        }
+        __syncthreads();                                               // (1) table cleared, s_first and the chunk bases set
+        {
+            const u32 pr = s_pad_rel_from, ps = s_pad_seed_from;       // a chunk was closed: its unused tail becomes holes
+            if (pr != SC_NOPAD)
+                for (u32 i = pr + tid; i < REL_CHUNK; i += THREADS) { const u64 o = s_pad_rel_base + i; if (o < cap) out_h[o] = EMPTY_H; }
+            if (EMIT && ps != SC_NOPAD)
+            {
+                Candidate hole; hole.kmer = EMPTY_KEY; hole.pos = 0; hole.read = 0;
+                for (u32 i = ps + tid; i < SEED_CHUNK; i += THREADS) { const u64 o = s_pad_seed_base + i; if (o < seeds.cap) seeds.out[o] = hole; }
+            }
+        }
         const u32 i0 = tid * c;
         const u32 nv = i0 < total ? min(c, total - i0) : 0u;
         u32 r0 = 0, j0 = 0;
         u32 code[PER / 2];                                             // two 16-bit slot codes per word
-        if (nv)
-        {
-            u32 lo = 0, hi = nrec;                                     // s_start[lo] <= i0 < s_start[hi]
-            while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (s_start[mid] <= i0) lo = mid; else hi = mid; }
-            r0 = lo; j0 = i0 - s_start[lo];
-        }
+        if (nv) { const u32 fs = s_first[tid]; r0 = fs >> 5; j0 = fs & 31u; }
         {
             u32 r = r0, j = j0, n = 0;
             SkmBases rec, nxt;
@@ -408,7 +427,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_skm_count(RecSlabs in, u32 nb, i
                 }
 #pragma unroll
                 for (int q = 0; q < 2; ++q)
-                    if (H[q] != EMPTY_H) { S[q] = (u32)H[q] & (BUCKET_SLOTS - 1); P[q] = atomicCAS(&s_key[S[q]], EMPTY_H, H[q]); }
+                    if (H[q] != EMPTY_H) { S[q] = (u32)H[q] & (SLOTS - 1); P[q] = atomicCAS(&s_key[S[q]], EMPTY_H, H[q]); }
                 u32 cw = 0;
 #pragma unroll
                 for (int q = 0; q < 2; ++q)
@@ -417,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_skm_count(RecSlabs in, u32 nb, i
                         u32 s = S[q], stepp = 0; u64 pv = P[q];
                         while (pv != EMPTY_H && pv != H[q])            // triangular probing: every slot once; total <= 0.75 * slots
                         {
-                            s = (s + ++stepp) & (BUCKET_SLOTS - 1);
+                            s = (s + ++stepp) & (SLOTS - 1);
                             pv = atomicCAS(&s_key[s], EMPTY_H, H[q]);
                         }
                         atomicAdd(&s_cnt[s], 1u);
@@ -426,7 +445,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_skm_count(RecSlabs in, u32 nb, i
                 code[g / 2] = cw;
             }
         }
-        __syncthreads();                                               // every count is final
+        __syncthreads();                                               // (2) every count is final
         // tallies of this thread: k-mers it claimed (distinct), reliable ones among them, instances of reliable k-mers
         u32 tally2 = 0;
 #pragma unroll
@@ -436,17 +455,17 @@ __global__ void __launch_bounds__(THREADS, 2) k_skm_count(RecSlabs in, u32 nb, i
             if ((u32)g < nv)
             {
                 const u32 cd = (code[g / 2] >> (16 * (g & 1))) & 0xFFFFu;
-                const u32 cc = s_cnt[cd & (BUCKET_SLOTS - 1)];
+                const u32 cc = s_cnt[cd & (SLOTS - 1)];
                 const bool own = (cd & SC_OWNER) != 0, rel = cc >= lower && cc <= upper;
                 my_distinct += own ? 1u : 0u;
                 if (rel) tally2 += 0x10000u + (own ? 1u : 0u);
             }
         }
-        my_sum += tally2 >> 16;
-        const u32 excl = block_scan_reserve<NW>(tally2, s_warp, s_base, &counters[0], seeds.cursor);
         if (tally2)
         {
-            u64 o_rel = s_base[0] + (excl & 0xFFFFu), o_seed = s_base[1] + (excl >> 16);
+            my_sum += tally2 >> 16; my_rel += tally2 & 0xFFFFu;
+            u64 o_rel = s_rel_base + ((tally2 & 0xFFFFu) ? atomicAdd(&s_rel_used, tally2 & 0xFFFFu) : 0u);
+            u64 o_seed = EMIT ? s_seed_base + atomicAdd(&s_seed_used, tally2 >> 16) : 0ull;
             u32 r = r0, j = j0;
             SkmBases rec = skm_load_bases(recs + r);
             u32 n = ((u32)rec.y & 31u) + 1u;
@@ -458,7 +477,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_skm_count(RecSlabs in, u32 nb, i
                 {
                     if (j == n) { ++r; j = 0; rec = skm_load_bases(recs + r); n = ((u32)rec.y & 31u) + 1u; }
                     const u32 cd = (code[g / 2] >> (16 * (g & 1))) & 0xFFFFu;
-                    const u32 s = cd & (BUCKET_SLOTS - 1);
+                    const u32 s = cd & (SLOTS - 1);
                     const u32 cc = s_cnt[s];
                     if (cc >= lower && cc <= upper)
                     {
@@ -478,10 +497,27 @@ __global__ void __launch_bounds__(THREADS, 2) k_skm_count(RecSlabs in, u32 nb, i
                 }
             }
         }
-        __syncthreads();                                               // the table and s_base are reused by the next bucket
+        __syncthreads();                                               // (3) the table and the chunk state are reused by the next bucket
     }
-    for (int o = 16; o; o >>= 1) { my_distinct += __shfl_xor_sync(0xffffffffu, my_distinct, o); my_sum += __shfl_xor_sync(0xffffffffu, my_sum, o); }
-    if (lane == 0) { if (my_distinct) atomicAdd(&counters[2], (u64)my_distinct); if (my_sum) atomicAdd(&counters[1], my_sum); }
+    // the unused tails of the CTA's last chunks are holes
+    __syncthreads();
+    for (u32 i = s_rel_used + tid; i < REL_CHUNK; i += THREADS) { const u64 o = s_rel_base + i; if (o < cap) out_h[o] = EMPTY_H; }
+    if (EMIT)
+    {
+        Candidate hole; hole.kmer = EMPTY_KEY; hole.pos = 0; hole.read = 0;
+        for (u32 i = s_seed_used + tid; i < SEED_CHUNK; i += THREADS) { const u64 o = s_seed_base + i; if (o < seeds.cap) seeds.out[o] = hole; }
+    }
+    for (int o = 16; o; o >>= 1)
+    {
+        my_distinct += __shfl_xor_sync(0xffffffffu, my_distinct, o); my_rel += __shfl_xor_sync(0xffffffffu, my_rel, o);
+        my_sum += __shfl_xor_sync(0xffffffffu, my_sum, o);
+    }
+    if (lane == 0)
+    {
+        if (my_distinct) atomicAdd(&counters[2], (u64)my_distinct);
+        if (my_sum) atomicAdd(&counters[1], my_sum);
+        if (my_rel) atomicAdd(&counters[8], (u64)my_rel);
+    }
 }
 
 // exact fallback: the k-mers of a list of records into the global table of kmer_count.cuh

@@ -107,21 +107,26 @@ def test_ragged_reads_k31():
 
 
 def test_fused_seed_list_variants(hifi):
-    """Pass 2 fused into counting (the default), the separate second sweep (ELBA_FE_FUSE=0) and the 256-thread CTA
-    shape must give the same bits; with the fused list build_A sees exactly nnzA_pre candidates (no filter false positives)."""
+    """Pass 2 fused into counting (the default), the separate second sweep (ELBA_FE_FUSE=0) and the small bucket geometry
+    (4096-slot tables, 256 threads) must give the same bits; with the fused list build_A sees exactly nnzA_pre candidates (no filter false positives)."""
     from oracle import oracle as O
     ref = O.run(hifi, 31, 2, 4)
     out = _run_cuda(hifi, 31, 2, 4)
     _compare(out, ref, "fused")
-    assert out["sizes"]["candidates"] == ref.nnzA_pre
+    assert ref.nnzA_pre <= out["sizes"]["candidates"] <= ref.nnzA_pre + 296 * 16384      # chunked list: holes, no false positives
     with _env(ELBA_FE_FUSE="0"):
         out = _run_cuda(hifi, 31, 2, 4)
     _compare(out, ref, "second sweep")
     assert out["sizes"]["candidates"] >= ref.nnzA_pre
     for fuse in ("1", "0"):
-        with _env(ELBA_FE_SKM_THREADS="256", ELBA_FE_FUSE=fuse):
+        with _env(ELBA_FE_SKM_GEOM="small", ELBA_FE_FUSE=fuse):
             out = _run_cuda(hifi, 27, 2, 6)
-        _compare(out, O.run(hifi, 27, 2, 6), f"256 threads fuse={fuse}")
+        _compare(out, O.run(hifi, 27, 2, 6), f"4096-slot tables, 256 threads, fuse={fuse}")
+        assert out["sizes"]["table_slots"] == 4096
+    with _env(ELBA_FE_SKM_GEOM="small", ELBA_FE_SKM_MEAN="3072", ELBA_FE_SKM_SLACK="4.0"):
+        out = _run_cuda(hifi, 31, 2, 4)
+    _compare(out, ref, "4096-slot tables, instance overflow")
+    assert out["sizes"]["overflow_instances"] > 100_000
 
 
 def test_fused_seed_list_resize_and_overflow_buckets(hifi):

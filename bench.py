@@ -35,6 +35,17 @@ DEFAULT_WORKLOAD = "celegans40x_hifi"     # the config BASELINE.json quotes at 1
 METRIC = "reads/s through k-mer count + A*A^T SpGEMM"
 
 
+def ncu_traffic(workload: str):
+    """DRAM bytes per launch of the counting chain's kernels from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json, written by tools/ncu_traffic.py from dram__bytes_read.sum + dram__bytes_write.sum); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(workload)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -282,6 +293,22 @@ def main():
         t_sp = tm["spgemm_kernel_ms"] / 1000.0
         bytes_sp = 8.0 * sizes_local["products"] + 8.0 * sizes_local["nnzA"] + 28.0 * sizes_local["nnzB_pre"]      # rank 0's block
         ach_sp = bytes_sp / t_sp / 1e9 if t_sp > 0 else 0.0
+        Mg = max(M / world, 1)
+        skm = sizes["table_slots"] in (4096, 8192) and k >= 20 and world == 1       # the super-k-mer path ran (superkmer.cuh)
+        names = (("k_skm_scatter", "k_skm_count", "k_resolve") if skm else ("k_scatter1", "k_scatter2+k_count_buckets", "k_probe_filter+k_resolve"))
+        chain = ("k_skm_scatter -> k_skm_count (pass 2 fused: reliable list + seed list) -> k_unmix, radix sort, k_lookup_build -> k_resolve" if skm else
+                 "k_scatter1 -> k_scatter2 -> k_count_buckets -> k_unmix, radix sort, k_lookup_build -> k_probe_filter -> k_resolve")
+        kt = {names[0]: tm["partition_ms"], names[1]: tm["count_kernel_ms"], names[2]: tm["lookup_ms"]}
+        kt["glue (sorts, column table, fallbacks, host syncs)"] = max(0.0, 1000.0 * t_count - sum(kt.values()))
+        traffic = ncu_traffic(args.workload) if world == 1 and args.scale == 1.0 else None
+        roofline = {"bound": "hbm", "kernel": "counting chain per GPU = everything the reference does in get_kmer_count_map_keys/values: " + chain,
+                    "dominant_kernel": max(kt, key=kt.get), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": (traffic or {}).get("chain_dram_bytes"), "traffic_source": (traffic or {}).get("source"), "traffic_per_kernel": (traffic or {}).get("kernels"),
+                    "peak_source": peak_src, "algorithmic_bytes": bytes_count, "algorithmic_bytes_per_instance": 28.5, "seconds": t_count,
+                    "kernels_ms": {a: round(b, 4) for a, b in kt.items()},
+                    "kernels_share_of_step": {a: round(b / ms_res, 4) for a, b in kt.items()},
+                    "kernels_ps_per_instance": {a: 1e9 * b / Mg for a, b in kt.items()},
+                    "budget_ps_per_instance_at_50pct": 1e12 * 28.5 / (0.5 * peak * 1e9)}
         line = {
             "metric": METRIC, "value": tot_reads / (ms_res / 1000.0), "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic" if "shape" in w else "reference fixture",
@@ -290,12 +317,7 @@ def main():
                        "nnzB": int(tot_nnzB), "partitions": sizes["partitions"], "grid": f"{info['grid_rows']}x{info['grid_cols']}", "l2_policy": "inputs larger than L2 / every step rewrites count tables and partition buffers",
                        "timing": "CUDA events on the launching stream around K steps, max over ranks; per-phase numbers from the library's own CUDA events on the same stream"},
             "phases_ms": {a: round(b, 4) for a, b in tm.items() if a.endswith("_ms")},
-            "roofline": {"bound": "hbm", "kernel": "counting phase per GPU (k_scatter1 + k_scatter2 + k_count_buckets + k_probe_filter + k_resolve and the glue between them)",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes": bytes_count, "seconds": t_count,
-                         "kernels_ps_per_instance": {"k_scatter1": 1e9 * tm["partition_ms"] / max(M / world, 1), "k_scatter2+k_count_buckets": 1e9 * tm["count_kernel_ms"] / max(M / world, 1),
-                                                     "k_probe_filter+k_resolve": 1e9 * tm["lookup_ms"] / max(M / world, 1)},
-                         "budget_ps_per_instance_at_50pct": 1e12 * 28.5 / (0.5 * peak * 1e9)},
+            "roofline": roofline,
             "roofline_spgemm": {"bound": "hbm", "kernel": "k_spgemm_warp + k_spgemm_block", "achieved": ach_sp, "peak": peak, "unit": "GB/s", "frac": ach_sp / peak,
                                 "algorithmic_bytes": bytes_sp, "seconds": t_sp},
             "e2e": {"value": tot_reads / (ms_e2e / 1000.0), "unit": "reads/s", "h2d_bytes_per_step": int(io[0].item()),

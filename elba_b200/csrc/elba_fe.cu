@@ -71,7 +71,7 @@ struct elba_fe_ctx
     DevBuf seed_key, seed_pos, seed_key2, seed_pos2, idx, a_key, a_rowptr, a_col, a_pos, at_key, at_key2, at_pos2, at_colptr, at_row, at_pos, prod;
     int col_bits = 1, read_bits = 1;
     // B
-    DevBuf t_col, t_num, t_seeds, row_off, row_nnz, bins, small_rows, big_rows, ovf_rows, gscratch, b_rowptr, b_col, b_num, b_seeds;
+    DevBuf t_col, t_num, t_seeds, row_off, row_nnz, bins, small_rows, mid_rows, big_rows, ovf_rows, gscratch, b_rowptr, b_col, b_num, b_seeds;
     u64 b_cap_hint = 0;
     DevBuf cubtmp, hll_regs, bloom;
     // multi-GPU
@@ -244,7 +244,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut, &ctx->filter,
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
-        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->bins, &ctx->small_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
+        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
@@ -998,7 +998,7 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
     CK(cudaEventRecord(ctx->ev[6], st));
     ctx->sev_used = 0;
     CK(ctx->row_off.ensure(8 * ((size_t)N + 1))); CK(ctx->row_nnz.ensure(4 * ((size_t)N + 1)));
-    CK(ctx->small_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->big_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->ovf_rows.ensure(4 * ((size_t)N + 1)));
+    CK(ctx->small_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->mid_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->big_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->ovf_rows.ensure(4 * ((size_t)N + 1)));
     CK(ctx->bins.ensure(64)); CK(ctx->b_rowptr.ensure(8 * ((size_t)N + 2)));
     u64 cap = std::max<u64>(ctx->b_cap_hint, std::max<u64>(nnzA + N, 1024));
     u64 *d_ctr = ctx->ctr.as<u64>();
@@ -1016,11 +1016,12 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
         A.counters = d_ctr; A.row_off = ctx->row_off.as<u64>(); A.row_nnz = ctx->row_nnz.as<u32>();
         if (N)
         {
-            k_spgemm_bin<<<nblk(N, 256), 256, 0, st>>>(ctx->prod.as<u64>(), N, ctx->small_rows.as<u32>(), ctx->big_rows.as<u32>(), d_bins, A.row_off, A.row_nnz, d_maxprod);
+            k_spgemm_bin<<<nblk(N, 256), 256, 0, st>>>(ctx->prod.as<u64>(), N, ctx->small_rows.as<u32>(), ctx->mid_rows.as<u32>(), ctx->big_rows.as<u32>(), d_bins, A.row_off, A.row_nnz, d_maxprod);
             CKL(); LAUNCHED(ctx);
             EventPair &sp = next_pair(ctx->sev, ctx->sev_used);
             CK(cudaEventRecord(sp.a, st));
             k_spgemm_warp<<<grid_for(ctx, 4), 32 * SPG_WARPS_PER_CTA, 0, st>>>(A, ctx->small_rows.as<u32>(), d_bins); CKL(); LAUNCHED(ctx);
+            k_spgemm_mid<<<grid_for(ctx, 11), SPG_MID_THREADS, 0, st>>>(A, ctx->mid_rows.as<u32>(), d_bins + 2); CKL(); LAUNCHED(ctx);
             k_spgemm_block<<<grid_for(ctx, 4), SPG_BLOCK_THREADS, 0, st>>>(A, ctx->big_rows.as<u32>(), d_bins + 1, ctx->ovf_rows.as<u32>()); CKL(); LAUNCHED(ctx);
             CK(cudaEventRecord(sp.b, st));
         }

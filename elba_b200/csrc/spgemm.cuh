@@ -11,7 +11,8 @@
 //
 // Row i: for every nonzero (c, pos_i) of A(i,:), for every (j, pos_j) of column c of A (<= UPPER entries),
 // hash j into the row's table.  Rows are binned by their product count: a warp per light row
-// (256-slot table), a CTA per heavy row (2048 slots), a global-memory table for rows that overflow that.
+// (256-slot table), two warps per medium row (1024 slots, 11 rows in flight per SM), a CTA per heavy row (2048
+// slots), a global-memory table for rows that overflow that.
 #pragma once
 #include "common.cuh"
 
@@ -20,6 +21,9 @@ namespace elba {
 static constexpr u32 EMPTY32 = 0xFFFFFFFFu;
 static constexpr u32 SPG_WARP_TS = 256;      // slots per warp-row table
 static constexpr u32 SPG_WARP_MAXPROD = 128; // rows with <= this many products go to the warp kernel
+static constexpr u32 SPG_MID_TS = 1024;      // slots per row table of the two-warp kernel
+static constexpr u32 SPG_MID_MAXPROD = 704;  // <= 75 % of SPG_MID_TS distinct columns even if every product is one: never overflows
+static constexpr int SPG_MID_THREADS = 64;
 static constexpr u32 SPG_BLOCK_TS = 2048;    // slots per CTA-row table
 static constexpr int SPG_BLOCK_THREADS = 256;
 static constexpr int SPG_WARPS_PER_CTA = 8;
@@ -101,23 +105,47 @@ __device__ bool spgemm_row(const SpgemmArgs &A, u32 row, u32 tid, u32 nth,
         if (keys[s] != EMPTY32 && cnt[s] >= 2) { u32 i = atomicAdd((u32*)&ctl[1], 1u); sortbuf[i] = s; }
     group_sync<BLOCK>();
     const u32 n = ctl[1];
-    u32 m = 1; while (m < n) m <<= 1;
-    for (u32 i = n + tid; i < m; i += nth) sortbuf[i] = EMPTY32;
-    group_sync<BLOCK>();
-    // bitonic sort of slot indices by column id
-    for (u32 size = 2; size <= m; size <<= 1)
-        for (u32 stride = size >> 1; stride > 0; stride >>= 1)
+    if (n <= 32)
+    {
+        // the common case (a row keeps a handful of columns): one warp sorts in registers, no barrier per stage
+        if (tid < 32)
         {
-            for (u32 i = tid; i < (m >> 1); i += nth)
-            {
-                u32 lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-                u32 a = sortbuf[lo], b = sortbuf[hi];
-                u32 ka = a == EMPTY32 ? EMPTY32 : keys[a], kb = b == EMPTY32 ? EMPTY32 : keys[b];
-                bool up = (lo & size) == 0;
-                if ((ka > kb) == up) { sortbuf[lo] = b; sortbuf[hi] = a; }
-            }
-            group_sync<BLOCK>();
+            u32 v = tid < n ? sortbuf[tid] : EMPTY32;
+            u32 kx = tid < n ? keys[v] : EMPTY32;
+#pragma unroll
+            for (u32 size = 2; size <= 32; size <<= 1)
+#pragma unroll
+                for (u32 stride = size >> 1; stride > 0; stride >>= 1)
+                {
+                    const u32 ok = __shfl_xor_sync(0xffffffffu, kx, stride), ov = __shfl_xor_sync(0xffffffffu, v, stride);
+                    const bool up = (tid & size) == 0, low = (tid & stride) == 0;
+                    const bool take = (low == up) ? (ok < kx) : (ok > kx);      // column ids of one row are distinct
+                    if (take) { kx = ok; v = ov; }
+                }
+            if (tid < n) sortbuf[tid] = v;
         }
+        group_sync<BLOCK>();
+    }
+    else
+    {
+        u32 m = 1; while (m < n) m <<= 1;
+        for (u32 i = n + tid; i < m; i += nth) sortbuf[i] = EMPTY32;
+        group_sync<BLOCK>();
+        // bitonic sort of slot indices by column id
+        for (u32 size = 2; size <= m; size <<= 1)
+            for (u32 stride = size >> 1; stride > 0; stride >>= 1)
+            {
+                for (u32 i = tid; i < (m >> 1); i += nth)
+                {
+                    u32 lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                    u32 a = sortbuf[lo], b = sortbuf[hi];
+                    u32 ka = a == EMPTY32 ? EMPTY32 : keys[a], kb = b == EMPTY32 ? EMPTY32 : keys[b];
+                    bool up = (lo & size) == 0;
+                    if ((ka > kb) == up) { sortbuf[lo] = b; sortbuf[hi] = a; }
+                }
+                group_sync<BLOCK>();
+            }
+    }
     if (tid == 0)
     {
         u64 off = n ? atomicAdd(&A.counters[0], (u64)n) : 0;
@@ -147,8 +175,8 @@ __device__ bool spgemm_row(const SpgemmArgs &A, u32 row, u32 tid, u32 nth,
 }
 
 // bin rows by product count
-__global__ void k_spgemm_bin(const u64 *__restrict__ prod, u32 nrows, u32 *__restrict__ small_rows, u32 *__restrict__ big_rows,
-                             u32 *__restrict__ nbins /*[0] small, [1] big*/, u64 *__restrict__ row_off, u32 *__restrict__ row_nnz,
+__global__ void k_spgemm_bin(const u64 *__restrict__ prod, u32 nrows, u32 *__restrict__ small_rows, u32 *__restrict__ mid_rows, u32 *__restrict__ big_rows,
+                             u32 *__restrict__ nbins /*[0] small, [1] big, [2] mid; [4..5] max products (u64)*/, u64 *__restrict__ row_off, u32 *__restrict__ row_nnz,
                              u64 *__restrict__ maxprod)
 {
     u32 r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,6 +184,7 @@ __global__ void k_spgemm_bin(const u64 *__restrict__ prod, u32 nrows, u32 *__res
     u64 p = prod[r];
     if (p == 0) { row_off[r] = 0; row_nnz[r] = 0; return; }
     if (p <= SPG_WARP_MAXPROD) small_rows[atomicAdd(&nbins[0], 1u)] = r;
+    else if (p <= SPG_MID_MAXPROD) mid_rows[atomicAdd(&nbins[2], 1u)] = r;
     else { big_rows[atomicAdd(&nbins[1], 1u)] = r; atomicMax(maxprod, p); }
 }
 
@@ -183,6 +212,17 @@ __global__ void __launch_bounds__(SPG_BLOCK_THREADS) k_spgemm_block(SpgemmArgs A
                                    s_tab + 3 * SPG_BLOCK_TS, s_tab + 4 * SPG_BLOCK_TS, SPG_BLOCK_TS, s_ctl);
         if (!ok && threadIdx.x == 0) overflow_rows[atomicAdd(&A.counters[2], 1ull)] = row;
     }
+}
+
+// two warps per medium row: the table can never overflow (products <= SPG_MID_MAXPROD)
+__global__ void __launch_bounds__(SPG_MID_THREADS) k_spgemm_mid(SpgemmArgs A, const u32 *__restrict__ rows, const u32 *__restrict__ nrows_p)
+{
+    __shared__ u32 s_tab[5 * SPG_MID_TS];
+    __shared__ u32 s_ctl[8];
+    u32 n = *nrows_p;
+    for (u32 i = blockIdx.x; i < n; i += gridDim.x)
+        spgemm_row<true>(A, rows[i], threadIdx.x, SPG_MID_THREADS, s_tab, s_tab + SPG_MID_TS, s_tab + 2 * SPG_MID_TS,
+                         s_tab + 3 * SPG_MID_TS, s_tab + 4 * SPG_MID_TS, SPG_MID_TS, s_ctl);
 }
 
 // rows whose distinct-column count exceeded the shared-memory table: one global-memory table per CTA

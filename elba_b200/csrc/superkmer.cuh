@@ -10,18 +10,20 @@
 //   k_skm_scatter   thread = 32 consecutive window starts of one read.  The 32 + W - 1 canonical m-mers are cut out of
 //                   the 2-bit words with funnel shifts (no rolling chain), hashed with one IMAD, and the sliding
 //                   minimum over W of them comes from log2(W) + 1 rounds of pairwise mins in registers.  A run of
-//                   k-mers with one minimizer becomes ONE 16-byte record {up to 61 bases, n - 1} appended to the
-//                   bucket of that minimizer: one global atomic and one 16-byte store per ~7 instances instead of a
-//                   staged 8-byte store per instance.  A k-mer and its reverse complement hold the same canonical
-//                   m-mers, so every instance of a canonical k-mer lands in the same bucket.
-//   k_skm_count     one CTA per bucket (~2400 instances, at most BUCKET_CAP): instances are dealt to the threads in
-//                   equal consecutive ranges (prefix sum of the records' n, one binary search per thread), each k-mer
-//                   is cut out of its record, canonicalised, mixed (h = mix64) and counted in the 8192-slot
-//                   shared-memory table: the CAS of a group of instances is issued back to back before any result is
-//                   looked at (no load-then-CAS chain, no divergent loop on the common path).  Reliable {h, count}
-//                   are appended exactly as k_count_buckets does.
-//   k_skm_count_global   the exact fallback (global table of kmer_count.cuh) for records of buckets that overflowed
-//                   their record capacity or BUCKET_CAP instances (skewed minimizers, repeats).
+//                   k-mers with one minimizer becomes ONE 32-byte record {up to 61 bases, n - 1, read, pos, offset of
+//                   the run inside its bucket} appended to the bucket of that minimizer: one 64-bit global atomic and
+//                   one 256-bit store of a whole sector per ~7 instances instead of a staged 8-byte store per
+//                   instance.  A k-mer and its reverse complement hold the same canonical m-mers, so every instance
+//                   of a canonical k-mer lands in the same bucket.  The record carries what BOTH exchanges of the
+//                   reference carry (k-mer; k-mer + read + pos, KmerOps.cpp:105,224).
+//   k_skm_count     one CTA per bucket (~2400 instances, at most 6144): every thread takes an equal range of consecutive
+//                   instances (offsets come from the scatter's fill word: no prefix sum), cuts each k-mer out of its
+//                   record, canonicalises it, mixes it (h = mix64) and counts it in the 8192-slot shared-memory table.
+//                   Reliable {h, count} are appended by the instance that claimed the slot; every instance of a
+//                   reliable k-mer appends its {k-mer, pos, read} to the seed list: pass 2 of the reference
+//                   (KmerOps.cpp:283-318) without a second sweep over the reads.
+//   k_skm_count_global / k_skm_emit_global   the exact fallback (global table of kmer_count.cuh) for records of buckets
+//                   that overflowed their record capacity or 6144 instances (skewed minimizers, repeats).
 //
 // Level 2 of the old scheme does not exist: the minimizer space (4^m / 2, m >= 13) is fine enough to cut buckets of a few
 // thousand instances in one pass.  That is not true for k < 20 (m would be too short for large genomes or W too small

@@ -294,9 +294,10 @@ def main():
         bytes_sp = 8.0 * sizes_local["products"] + 8.0 * sizes_local["nnzA"] + 28.0 * sizes_local["nnzB_pre"]      # rank 0's block
         ach_sp = bytes_sp / t_sp / 1e9 if t_sp > 0 else 0.0
         Mg = max(M / world, 1)
-        skm = sizes["table_slots"] in (4096, 8192) and k >= 20 and world == 1       # the super-k-mer path ran (superkmer.cuh)
+        skm = sizes["table_slots"] in (4096, 8192) and k >= 20 and sizes["partitions"] > 4096       # the super-k-mer path ran (superkmer.cuh)
         names = (("k_skm_scatter", "k_skm_count", "k_resolve") if skm else ("k_scatter1", "k_scatter2+k_count_buckets", "k_probe_filter+k_resolve"))
-        chain = ("k_skm_scatter -> k_skm_count (pass 2 fused: reliable list + seed list) -> k_unmix, radix sort, k_lookup_build -> k_resolve" if skm else
+        chain = (("all-gather of the 2-bit reads -> " if world > 1 else "") +
+                 "k_skm_scatter -> k_skm_count (pass 2 fused: reliable list + seed list) -> k_unmix, radix sort, k_lookup_build -> k_resolve" if skm else
                  "k_scatter1 -> k_scatter2 -> k_count_buckets -> k_unmix, radix sort, k_lookup_build -> k_probe_filter -> k_resolve")
         kt = {names[0]: tm["partition_ms"], names[1]: tm["count_kernel_ms"], names[2]: tm["lookup_ms"]}
         kt["glue (sorts, column table, fallbacks, host syncs)"] = max(0.0, 1000.0 * t_count - sum(kt.values()))

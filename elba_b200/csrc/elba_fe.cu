@@ -63,6 +63,9 @@ struct elba_fe_ctx
     u64 skm_ovf_cap = 0;
     bool seeds_fused = false; u64 nseeds_fused = 0;      // counting already wrote the seed list (ctx->cand) of this pass
     u64 skm_reliable = 0;                                // super-k-mer path: reliable k-mers among the (holey) list entries handed out
+    // several GPUs, super-k-mer path: every GPU holds all reads (all-gathered arena) and counts the buckets it owns
+    DevBuf gr_packed, gr_off, gr_len64, gr_len32, gr_chunk, gr_kmer, gr_nks, all_key, all_pos;
+    u64 gr_n = 0, gr_nchunks = 0, gr_M = 0; int64_t gr_read0 = 0; bool seeds_global = false;
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_x0 = nullptr, ev_x1 = nullptr;
     u64 exchange_bytes = 0, panel_bytes = 0;
     u64 scratch_mb = 64;
@@ -71,6 +74,7 @@ struct elba_fe_ctx
     DevBuf seed_key, seed_pos, seed_key2, seed_pos2, idx, a_key, a_rowptr, a_col, a_pos, at_key, at_key2, at_pos2, at_colptr, at_row, at_pos, prod;
     int col_bits = 1, read_bits = 1;
     // B
+    DevBuf sp_ptr, sp_ent;               // the right operand as the SpGEMM reads it (k_spgemm_operand)
     DevBuf t_col, t_num, t_seeds, row_off, row_nnz, bins, small_rows, mid_rows, big_rows, ovf_rows, gscratch, b_rowptr, b_col, b_num, b_seeds;
     u64 b_cap_hint = 0;
     DevBuf cubtmp, hll_regs, bloom;
@@ -79,7 +83,7 @@ struct elba_fe_ctx
     u64 N_total = 0;
     DevBuf recvbuf, recvcnt, tmp64, rel_all_key, rel_all_cnt, g_key, g_pos, pack_key, l_rowptr, l_col, r_key, r_key2, r_pos, r_colptr, r_row, r_ptr;
     // SpGEMM operands: left rows (CSR) x right rows by column (CSC); one GPU: A and its transpose
-    struct { const int64_t *l_rowptr; const u32 *l_col, *l_pos; u32 l_rows; u64 l_nnz; const int64_t *r_colptr; const u32 *r_row, *r_pos; int64_t row0, col0; } op;
+    struct { const int64_t *l_rowptr; const u32 *l_col, *l_pos; u32 l_rows; u64 l_nnz; const int64_t *r_colptr; const u32 *r_row, *r_pos; u64 r_nnz; int64_t row0, col0; } op;
     u32 b_rows = 0;
     elba_fe_sizes_t sz;
     elba_fe_timings_t tm;
@@ -244,7 +248,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut, &ctx->filter,
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
-        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
+        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->gr_packed, &ctx->gr_off, &ctx->gr_len64, &ctx->gr_len32, &ctx->gr_chunk, &ctx->gr_kmer, &ctx->gr_nks, &ctx->all_key, &ctx->all_pos, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
@@ -379,12 +383,70 @@ static int count_with_global_table(elba_fe_ctx *ctx, const std::vector<std::pair
 // bucket counts in shared memory.  Appends the reliable {h, count} to rel_key / rel_cnt exactly as the hash path does,
 // and (fused pass 2) every instance of a reliable k-mer to the seed list ctx->cand, so build_A has no second sweep.
 // retry: the overflow list or the seed list was too small (their exact sizes are known now).
-static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &retry)
+// What the super-k-mer path counts: one GPU: its own reads, all buckets.  Several GPUs: ALL reads, the buckets of this rank.
+struct SkmPlan { ReadsView rv; u64 Ms; u32 read_base; int nranks, rank; };
+
+static __global__ void k_add_u64(u64 *__restrict__ v, u64 n, u64 add)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += add;
+}
+
+static int allgather_u64(elba_fe_ctx *ctx, u64 mine, std::vector<u64> &all);
+static int allgatherv(elba_fe_ctx *ctx, const void *send, void *recv, const std::vector<u64> &count, size_t esize);
+
+// Several GPUs: all-gather the 2-bit arenas (0.25 B per base) and the read tables; the ranks hold consecutive blocks of reads,
+// so the gathered index of a read is its global id minus the first rank's offset.  ok = false: the blocks are not consecutive.
+static int gather_reads(elba_fe_ctx *ctx, SkmPlan &plan, bool &ok)
 {
     cudaStream_t st = ctx->stream;
-    ReadsView rv = view(ctx);
+    const int W = ctx->comm.nranks;
+    std::vector<u64> nr, nb, ro;
+    int rc;
+    if ((rc = allgather_u64(ctx, ctx->n, nr))) return rc;
+    if ((rc = allgather_u64(ctx, ctx->packed_bytes, nb))) return rc;
+    if ((rc = allgather_u64(ctx, (u64)ctx->read_id_offset, ro))) return rc;
+    u64 Nt = 0, Bt = 0; ok = true;
+    for (int r = 0; r < W; ++r) { if (ro[r] != ro[0] + Nt) ok = false; Nt += nr[r]; Bt += nb[r]; }
+    if (ro[0] + Nt >= 0xFFFFFFF0ull) ok = false;             // global read ids travel as 32 bits in the records
+    if (!ok) return 0;
+    CK(ctx->gr_packed.ensure(Bt + 64)); CK(ctx->gr_off.ensure(8 * (Nt + 1))); CK(ctx->gr_len64.ensure(8 * (Nt + 1)));
+    CK(ctx->gr_len32.ensure(4 * (Nt + 1))); CK(ctx->gr_chunk.ensure(8 * (Nt + 1))); CK(ctx->gr_kmer.ensure(8 * (Nt + 1))); CK(ctx->gr_nks.ensure(8 * (Nt + 1)));
+    CK(cudaMemsetAsync(ctx->gr_packed.as<uint8_t>() + Bt, 0, 64, st));
+    if ((rc = allgatherv(ctx, ctx->packed.p, ctx->gr_packed.p, nb, 1))) return rc;
+    if ((rc = allgatherv(ctx, ctx->off.p, ctx->gr_off.p, nr, 8))) return rc;
+    if ((rc = allgatherv(ctx, ctx->len64.p, ctx->gr_len64.p, nr, 8))) return rc;
+    u64 rbase = 0, bbase = 0;
+    for (int r = 0; r < W; ++r)
+    {
+        if (r && nr[r]) { k_add_u64<<<nblk(nr[r], 256), 256, 0, st>>>(ctx->gr_off.as<u64>() + rbase, nr[r], bbase); CKL(); LAUNCHED(ctx); }
+        rbase += nr[r]; bbase += nb[r];
+    }
+    const u32 n = (u32)Nt;
+    k_prep_reads<<<nblk((u64)n + 1, 256), 256, 0, st>>>(ctx->gr_len64.as<u64>(), n, ctx->cfg.k, ctx->cfg.stride,
+        ctx->gr_len32.as<u32>(), ctx->gr_chunk.as<u64>(), ctx->gr_kmer.as<u64>(), ctx->gr_nks.as<u64>());
+    CKL(); LAUNCHED(ctx);
+    if ((rc = exclusive_scan_inplace(ctx, ctx->gr_chunk.as<u64>(), (u64)n + 1))) return rc;
+    if ((rc = exclusive_scan_inplace(ctx, ctx->gr_kmer.as<u64>(), (u64)n + 1))) return rc;
+    u64 tot[2];
+    CK(cudaMemcpyAsync(&tot[0], ctx->gr_chunk.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&tot[1], ctx->gr_kmer.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->gr_n = Nt; ctx->gr_nchunks = tot[0]; ctx->gr_M = tot[1]; ctx->gr_read0 = (int64_t)ro[0];
+    plan.rv.buf = ctx->gr_packed.as<uint8_t>(); plan.rv.off = ctx->gr_off.as<u64>(); plan.rv.len = ctx->gr_len32.as<u32>();
+    plan.rv.chunk_start = ctx->gr_chunk.as<u64>(); plan.rv.kmer_start = ctx->gr_kmer.as<u64>(); plan.rv.n = n; plan.rv.nchunks = tot[0];
+    plan.Ms = tot[1]; plan.read_base = (u32)ro[0]; plan.nranks = W; plan.rank = ctx->comm.rank;
+    ctx->exchange_bytes = Bt - ctx->packed_bytes + 16 * (Nt - ctx->n);
+    return 0;
+}
+
+static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm, u64 rel_cap, bool &retry)
+{
+    cudaStream_t st = ctx->stream;
+    const ReadsView rv = plan.rv;
     const int k = ctx->cfg.k; const u32 lower = ctx->cfg.lower, upper = ctx->cfg.upper;
-    const u64 Ms = ctx->Ms;
+    const u64 Ms = plan.Ms;                                 // instances of ALL the reads in rv: decides the bucket geometry
+    const u64 Ms_own = Ms / (u64)plan.nranks + 1;           // what this GPU expects to count: decides the list capacities
     u64 *d_ctr = ctx->ctr.as<u64>(); u32 *d_err = reinterpret_cast<u32*>(d_ctr + 3);
     retry = false;
     bool fuse = true, small = false;
@@ -394,42 +456,45 @@ static int count_superkmers(elba_fe_ctx *ctx, int m, int Wm, u64 rel_cap, bool &
     // buckets: mean fill capacity / 2.5 (a bucket is a handful of genomic super-k-mers times the coverage: CV ~ 0.4)
     u64 mean_inst = bcap * 2 / 5;
     if (const char *e = getenv("ELBA_FE_SKM_MEAN")) { long v = atol(e); if (v >= 64 && v <= (long)bcap) mean_inst = (u64)v; }
-    u64 NB = std::max<u64>(1, (Ms + mean_inst - 1) / mean_inst);
-    if (ctx->cfg.num_partitions > 1) NB = std::max<u64>(NB, (u64)ctx->cfg.num_partitions);
-    if (NB >= (1ull << 31)) return fail(ctx, ELBA_FE_ERR_INVALID, "too many minimizer buckets for one context");
+    u64 NBg = std::max<u64>(1, (Ms + mean_inst - 1) / mean_inst);
+    if (ctx->cfg.num_partitions > 1) NBg = std::max<u64>(NBg, (u64)ctx->cfg.num_partitions);
+    const u64 NB = (NBg + plan.nranks - 1) / plan.nranks;   // buckets of this GPU: [rank * NB, (rank + 1) * NB) of NBg
+    NBg = NB * (u64)plan.nranks;
+    if (NBg >= (1ull << 31)) return fail(ctx, ELBA_FE_ERR_INVALID, "too many minimizer buckets for one context");
     // records per bucket: a chunk of 32 window starts holds 32 * 2 / (W + 1) minimizer runs plus the one its start cuts
     const double avg_run = 32.0 / (64.0 / (double)(Wm + 1) + 1.0);
     double slack = 2.5;
     if (const char *e = getenv("ELBA_FE_SKM_SLACK")) { double v = atof(e); if (v >= 1.0 && v <= 16.0) slack = v; }
-    u64 rcap = (u64)((double)Ms / (double)NB / avg_run * slack) + 32;
+    u64 rcap = (u64)((double)Ms / (double)NBg / avg_run * slack) + 32;
     rcap = std::min<u64>(rcap, SC_MAXREC);
-    ctx->sz.partitions = NB; ctx->sz.table_slots = slots;
-    const u64 ovf_cap = std::max<u64>(ctx->skm_ovf_cap, std::max<u64>(Ms / 64, 1u << 16));
+    ctx->sz.partitions = NBg; ctx->sz.table_slots = slots;
+    const u64 ovf_cap = std::max<u64>(ctx->skm_ovf_cap, std::max<u64>(Ms_own / 64, 1u << 16));
     CK(ctx->skm_slab.ensure(sizeof(SkmRec) * NB * rcap)); CK(ctx->skm_fill.ensure(sizeof(u64) * NB));
     CK(ctx->skm_ovf.ensure(sizeof(SkmRec) * ovf_cap));
     ctx->skm_ovf_cap = ovf_cap;
     // seed list: {k-mer, pos, read} of every instance of a reliable k-mer; the size of the last pass, else a guess
     const u64 gc_max = (u64)grid_for(ctx, 4);                         // CTAs of k_skm_count: each may leave one chunk partly used
-    u64 seed_guess = Ms / 16 + (1u << 20) + gc_max * SEED_CHUNK;
+    u64 seed_guess = Ms_own / 16 + (1u << 20) + gc_max * SEED_CHUNK;
     if (const char *e = getenv("ELBA_FE_SEED_CAP")) { long long v = atoll(e); if (v >= 1) seed_guess = (u64)v; }      // tests: force the resize
     const u64 seed_cap = fuse ? std::max<u64>(ctx->cand_cap, seed_guess) : std::max<u64>(ctx->cand_cap, 1);
     CK(ctx->cand.ensure(sizeof(Candidate) * seed_cap));
     ctx->cand_cap = seed_cap;
     SeedSink seeds; seeds.out = ctx->cand.as<Candidate>(); seeds.cursor = d_ctr + 7; seeds.cap = seed_cap;
     CK(cudaMemsetAsync(ctx->skm_fill.p, 0, sizeof(u64) * NB, st));
-    RecSink sink; sink.slab = ctx->skm_slab.as<SkmRec>(); sink.fill = ctx->skm_fill.as<u64>(); sink.rcap = (u32)rcap; sink.NB = (u32)NB;
+    RecSink sink; sink.slab = ctx->skm_slab.as<SkmRec>(); sink.fill = ctx->skm_fill.as<u64>(); sink.rcap = (u32)rcap; sink.NB = (u32)NBg;
+    sink.b_lo = (u32)(NB * (u64)plan.rank); sink.b_cnt = (u32)NB; sink.read_base = plan.read_base;
     sink.ovf = ctx->skm_ovf.as<SkmRec>(); sink.ovf_cursor = d_ctr + 5; sink.ovf_inst = d_ctr + 6; sink.ovf_cap = ovf_cap;
     const u32 nmax = skm_nmax(k);
     EventPair &pp = next_pair(ctx->pev, ctx->pev_used);
     CK(cudaEventRecord(pp.a, st));
-    if (ctx->nchunks)
+    if (rv.nchunks)
     {
-        const u32 g1 = (u32)std::min<u64>((ctx->nchunks + SK_THREADS - 1) / SK_THREADS, (u64)grid_for(ctx, 4));
-        const u64 iters = (ctx->nchunks + (u64)g1 * SK_THREADS - 1) / ((u64)g1 * SK_THREADS);
+        const u32 g1 = (u32)std::min<u64>((rv.nchunks + SK_THREADS - 1) / SK_THREADS, (u64)grid_for(ctx, 4));
+        const u64 iters = (rv.nchunks + (u64)g1 * SK_THREADS - 1) / ((u64)g1 * SK_THREADS);
         int contig = 1, nr = SK_NR;
         if (const char *e = getenv("ELBA_FE_SKM_ORDER")) contig = std::strcmp(e, "strided") != 0;
         if (const char *e = getenv("ELBA_FE_SKM_NR")) nr = atoi(e);
-        const u64 it1 = contig ? iters : (ctx->nchunks + (u64)g1 * SK_THREADS - 1) / ((u64)g1 * SK_THREADS);
+        const u64 it1 = iters;
         switch (Wm)
         {
             case 8:  k_skm_scatter<8, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig); break;
@@ -547,8 +612,21 @@ int elba_fe_count(elba_fe_ctx *ctx)
     if (direct) P1 = 1;
     // k >= 20, one GPU, every window start: super-k-mers in minimizer buckets (superkmer.cuh); else the two-level hash partition
     int skm_m = 0, skm_W = 0;
-    bool use_skm = !direct && W == 1 && stride == 1 && skm_geometry(k, skm_m, skm_W);
+    // (several GPUs: every GPU parses all reads and counts the buckets it owns, no record crosses NVLink)
+    bool use_skm = !direct && stride == 1 && skm_geometry(k, skm_m, skm_W);
     if (const char *e = getenv("ELBA_FE_COUNT_PATH")) { if (!std::strcmp(e, "hash")) use_skm = false; }
+    SkmPlan plan; plan.rv = rv; plan.Ms = Ms; plan.read_base = 0; plan.nranks = 1; plan.rank = 0;
+    ctx->seeds_global = false;
+    if (use_skm && W > 1)
+    {
+        bool ok = false;
+        CK(cudaEventRecord(ctx->ev_x0, st));
+        int rc0 = gather_reads(ctx, plan, ok);
+        if (rc0) return rc0;
+        CK(cudaEventRecord(ctx->ev_x1, st));
+        if (!ok) use_skm = false;                                        // read blocks not consecutive over the ranks: hash path
+        else ctx->seeds_global = true;
+    }
     if (W > 1) { P1 = (P1 + W - 1) / W * W; if (P1 > MAX_P1) P1 = MAX_P1 / W * W; }      // every rank owns P1 / W partitions
     const u32 Pown = P1 / (u32)W;
     ctx->sz.partitions = P1;
@@ -581,7 +659,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
         else if (use_skm)
         {
             bool again = false;
-            int rc0 = count_superkmers(ctx, skm_m, skm_W, rel_cap, again);
+            int rc0 = count_superkmers(ctx, plan, skm_m, skm_W, rel_cap, again);
             if (rc0) return rc0;
             if (again)
             {
@@ -789,12 +867,13 @@ int elba_fe_count(elba_fe_ctx *ctx)
     if (W > 1)
     {
         std::vector<u64> Rr;
-        int rc0 = allgather_u64(ctx, R, Rr); if (rc0) return rc0;
+        int rc0 = allgather_u64(ctx, R_list, Rr); if (rc0) return rc0;
+        if ((rc0 = allreduce_u64(ctx, &R, 1, ncclSum))) return rc0;       // k-mers (the lists may hold holes)
         u64 Rt = 0; for (u64 v : Rr) Rt += v;
         CK(ctx->rel_all_key.ensure(sizeof(u64) * std::max<u64>(Rt, 1))); CK(ctx->rel_all_cnt.ensure(sizeof(u32) * std::max<u64>(Rt, 1)));
         if ((rc0 = allgatherv(ctx, ctx->rel_key.p, ctx->rel_all_key.p, Rr, sizeof(u64)))) return rc0;
         if ((rc0 = allgatherv(ctx, ctx->rel_cnt.p, ctx->rel_all_cnt.p, Rr, sizeof(u32)))) return rc0;
-        rk = ctx->rel_all_key.as<u64>(); rc_ = ctx->rel_all_cnt.as<u32>(); R = Rt; R_list = Rt;
+        rk = ctx->rel_all_key.as<u64>(); rc_ = ctx->rel_all_cnt.as<u32>(); R_list = Rt;
     }
     if (R >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers on one context");
     ctx->sz.reliable = R;
@@ -829,11 +908,12 @@ int elba_fe_count(elba_fe_ctx *ctx)
 // rows of A of its own reads; one all-gather of those row blocks gives each GPU all of A (read-major, already sorted,
 // since the ranks hold consecutive read ranges), from which it slices R_i as the left CSR and re-sorts C_j as the
 // right CSC.
+static int operands_from_gathered(elba_fe_ctx *ctx, u64 tot);
+
 static int gather_operands(elba_fe_ctx *ctx)
 {
     cudaStream_t st = ctx->stream;
-    const int W = ctx->comm.nranks, me = ctx->comm.rank, pr = ctx->comm.grid_rows, pc = ctx->comm.grid_cols;
-    const u64 nnzA = ctx->sz.nnzA, R = ctx->sz.reliable; const u32 N = ctx->n;
+    const u64 nnzA = ctx->sz.nnzA; const u32 N = ctx->n;
     std::vector<u64> nz;
     int rc = allgather_u64(ctx, nnzA, nz); if (rc) return rc;
     u64 tot = 0; for (u64 v : nz) tot += v;
@@ -843,7 +923,16 @@ static int gather_operands(elba_fe_ctx *ctx)
     if ((rc = allgatherv(ctx, ctx->pack_key.p, ctx->g_key.p, nz, 8))) return rc;
     if ((rc = allgatherv(ctx, ctx->a_pos.p, ctx->g_pos.p, nz, 4))) return rc;
     ctx->panel_bytes = 12 * (tot - nnzA);
+    return operands_from_gathered(ctx, tot);
+}
 
+// g_key (global read << 32 | column, ascending) / g_pos hold ALL of A (tot entries): slice R_i as the left CSR, re-sort C_j as the right CSC
+static int operands_from_gathered(elba_fe_ctx *ctx, u64 tot)
+{
+    cudaStream_t st = ctx->stream;
+    const int me = ctx->comm.rank, pr = ctx->comm.grid_rows, pc = ctx->comm.grid_cols;
+    const u64 R = ctx->sz.reliable;
+    int rc;
     const int bi = me / pc, bj = me % pc;
     int64_t row0, nr, col0, ncb;
     block_extent((int64_t)ctx->N_total, pr, bi, row0, nr);
@@ -871,7 +960,7 @@ static int gather_operands(elba_fe_ctx *ctx)
     k_segment_ptr<<<nblk(R + 1, 256), 256, 0, st>>>(ctx->r_key2.as<u64>(), rn, R, rbits, ctx->r_colptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
     if (rn) { k_split_swap<<<nblk(rn, 256), 256, 0, st>>>(ctx->r_key2.as<u64>(), rn, rbits, cb, ctx->r_row.as<u32>(), nullptr); CKL(); LAUNCHED(ctx); }
     ctx->op.l_rowptr = ctx->l_rowptr.as<int64_t>(); ctx->op.l_col = ctx->l_col.as<u32>(); ctx->op.l_pos = ctx->g_pos.as<u32>() + lb; ctx->op.l_rows = (u32)nr; ctx->op.l_nnz = ln;
-    ctx->op.r_colptr = ctx->r_colptr.as<int64_t>(); ctx->op.r_row = ctx->r_row.as<u32>(); ctx->op.r_pos = ctx->r_pos.as<u32>();
+    ctx->op.r_colptr = ctx->r_colptr.as<int64_t>(); ctx->op.r_row = ctx->r_row.as<u32>(); ctx->op.r_pos = ctx->r_pos.as<u32>(); ctx->op.r_nnz = rn;
     ctx->op.row0 = row0; ctx->op.col0 = col0;
     return 0;
 }
@@ -895,7 +984,8 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     // one GPU: counting already told how many instances belong to reliable k-mers.  Several GPUs: that number is
     // known per OWNER, not per reader, so the triple buffers are sized by the candidate count.
     u64 cap = std::max<u64>(npre, 1);
-    if (W == 1) { CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); }
+    const bool global = ctx->seeds_fused && ctx->seeds_global;        // several GPUs, super-k-mer path: the seeds carry GLOBAL read ids
+    if (W == 1 || ctx->seeds_fused) { CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); }
     // sweep 2: every instance of a reliable k-mer -> (read, column, pos)
     u64 emitted = 0;
     {
@@ -907,7 +997,7 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
             const u64 ncand = ctx->nseeds_fused;
             ctx->sz.candidates = ncand;
             if (ncand) { k_resolve<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->cand.as<Candidate>(), ncand, ctx->lut.as<Slot>(), ctx->lut_slots,
-                             ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, cap, cb); CKL(); LAUNCHED(ctx); }
+                             ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, cap, global ? 32 : cb); CKL(); LAUNCHED(ctx); }
         }
         else if (ctx->nchunks && R)
         {
@@ -948,12 +1038,57 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     }
 
     int rc;
+    u64 nnzA = 0, gathered = 0;
+    if (global)
+    {
+        // The seeds were written by the OWNERS of the k-mers.  SpGEMM needs all of A on every GPU anyway (unsplit inner
+        // dimension), so the triples are all-gathered (12 B each), sorted and deduplicated once, and every GPU slices the
+        // rows of its own reads out of the result: this replaces "send seeds to the read's GPU + build + all-gather A".
+        std::vector<u64> ne;
+        if ((rc = allgather_u64(ctx, npre, ne))) return rc;
+        u64 tpre = 0; for (u64 v : ne) tpre += v;
+        const u64 tp1 = std::max<u64>(tpre, 1);
+        CK(ctx->all_key.ensure(8 * tp1)); CK(ctx->all_pos.ensure(4 * tp1)); CK(ctx->seed_key2.ensure(8 * tp1)); CK(ctx->seed_pos2.ensure(4 * tp1));
+        if ((rc = allgatherv(ctx, ctx->seed_key.p, ctx->all_key.p, ne, 8))) return rc;
+        if ((rc = allgatherv(ctx, ctx->seed_pos.p, ctx->all_pos.p, ne, 4))) return rc;
+        ctx->panel_bytes = 12 * (tpre - npre);
+        const int gb = 32 + bits_for(std::max<u64>((u64)ctx->gr_read0 + ctx->N_total, 2));
+        if ((rc = sort_pairs(ctx, ctx->all_key.as<u64>(), ctx->seed_key2.as<u64>(), ctx->all_pos.as<u32>(), ctx->seed_pos2.as<u32>(), tpre, 0, gb))) return rc;
+        CK(ctx->idx.ensure(8 * (tpre + 1)));
+        k_mark_run_ends<<<nblk(tpre + 1, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), tpre, ctx->idx.as<u64>()); CKL(); LAUNCHED(ctx);
+        if ((rc = exclusive_scan_inplace(ctx, ctx->idx.as<u64>(), tpre + 1))) return rc;
+        CK(cudaMemcpyAsync(&gathered, ctx->idx.as<u64>() + tpre, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(ctx->g_key.ensure(8 * std::max<u64>(gathered, 1))); CK(ctx->g_pos.ensure(4 * std::max<u64>(gathered, 1)));
+        if (tpre) { k_dedupe_write<<<nblk(tpre, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), ctx->seed_pos2.as<u32>(), ctx->idx.as<u64>(), tpre, ctx->g_key.as<u64>(), ctx->g_pos.as<u32>()); CKL(); LAUNCHED(ctx); }
+        // the rows of this GPU's reads
+        CK(ctx->a_rowptr.ensure(8 * ((size_t)N + 2)));
+        k_read_ptr<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), gathered, (u64)ctx->read_id_offset, (u64)N, ctx->a_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
+        int64_t lb = 0, le = 0;
+        CK(cudaMemcpyAsync(&lb, ctx->a_rowptr.as<int64_t>(), 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&le, ctx->a_rowptr.as<int64_t>() + N, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        nnzA = (u64)(le - lb);
+        ctx->sz.nnzA = nnzA;
+        const u64 na = std::max<u64>(nnzA, 1);
+        CK(ctx->a_pos.ensure(4 * na)); CK(ctx->a_col.ensure(4 * na));
+        CK(ctx->at_key.ensure(8 * na)); CK(ctx->at_key2.ensure(8 * na)); CK(ctx->at_pos2.ensure(4 * na)); CK(ctx->at_row.ensure(4 * na)); CK(ctx->at_pos.ensure(4 * na));
+        CK(ctx->at_colptr.ensure(8 * (R + 2)));
+        k_sub_base<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->a_rowptr.as<int64_t>(), (u64)N, lb); CKL(); LAUNCHED(ctx);
+        if (nnzA)
+        {
+            k_slice_left<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), (u64)lb, nnzA, ctx->a_col.as<u32>()); CKL(); LAUNCHED(ctx);
+            CK(cudaMemcpyAsync(ctx->a_pos.p, ctx->g_pos.as<u32>() + lb, 4 * nnzA, cudaMemcpyDeviceToDevice, st));
+            k_slice_right<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), (u64)lb, nnzA, (u64)ctx->read_id_offset, rb, ctx->at_key.as<u64>()); CKL(); LAUNCHED(ctx);
+        }
+    }
+    else
+    {
     // sort by (read, column); merge duplicates keeping the largest position
     if ((rc = sort_pairs(ctx, ctx->seed_key.as<u64>(), ctx->seed_key2.as<u64>(), ctx->seed_pos.as<u32>(), ctx->seed_pos2.as<u32>(), npre, 0, cb + rb))) return rc;
     CK(ctx->idx.ensure(8 * (npre + 1)));
     k_mark_run_ends<<<nblk(npre + 1, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), npre, ctx->idx.as<u64>()); CKL(); LAUNCHED(ctx);
     if ((rc = exclusive_scan_inplace(ctx, ctx->idx.as<u64>(), npre + 1))) return rc;
-    u64 nnzA = 0;
     CK(cudaMemcpyAsync(&nnzA, ctx->idx.as<u64>() + npre, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     ctx->sz.nnzA = nnzA;
@@ -964,6 +1099,7 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     if (npre) { k_dedupe_write<<<nblk(npre, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), ctx->seed_pos2.as<u32>(), ctx->idx.as<u64>(), npre, ctx->a_key.as<u64>(), ctx->a_pos.as<u32>()); CKL(); LAUNCHED(ctx); }
     k_segment_ptr<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, N, cb, ctx->a_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
     if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, cb, rb, ctx->a_col.as<u32>(), ctx->at_key.as<u64>()); CKL(); LAUNCHED(ctx); }
+    }
     // transpose: the same entries sorted by (column, read)
     if ((rc = sort_pairs(ctx, ctx->at_key.as<u64>(), ctx->at_key2.as<u64>(), ctx->a_pos.as<u32>(), ctx->at_pos.as<u32>(), nnzA, 0, cb + rb))) return rc;
     k_segment_ptr<<<nblk(R + 1, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, R, rb, ctx->at_colptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
@@ -971,8 +1107,14 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     // operands of B = A (x) A^T: one GPU multiplies A by its own transpose
     ctx->op.l_rowptr = ctx->a_rowptr.as<int64_t>(); ctx->op.l_col = ctx->a_col.as<u32>(); ctx->op.l_pos = ctx->a_pos.as<u32>(); ctx->op.l_rows = N; ctx->op.l_nnz = nnzA;
     ctx->op.r_colptr = ctx->at_colptr.as<int64_t>(); ctx->op.r_row = ctx->at_row.as<u32>(); ctx->op.r_pos = ctx->at_pos.as<u32>();
+    ctx->op.r_nnz = nnzA;
     ctx->op.row0 = ctx->op.col0 = ctx->read_id_offset;
-    if (W > 1) { rc = gather_operands(ctx); if (rc) return rc; }
+    if (W > 1) { rc = global ? operands_from_gathered(ctx, gathered) : gather_operands(ctx); if (rc) return rc; }
+    if (ctx->op.r_nnz >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "the right SpGEMM operand of one GPU exceeds 2^32 entries");
+    CK(ctx->sp_ptr.ensure(4 * (R + 2))); CK(ctx->sp_ent.ensure(8 * std::max<u64>(ctx->op.r_nnz, 1)));
+    k_spgemm_operand<<<nblk(std::max<u64>(R + 1, ctx->op.r_nnz), 256), 256, 0, st>>>(ctx->op.r_colptr, R, ctx->op.r_row, ctx->op.r_pos, ctx->op.r_nnz,
+        ctx->sp_ptr.as<u32>(), ctx->sp_ent.as<uint2>());
+    CKL(); LAUNCHED(ctx);
     // products per row, F
     CK(ctx->prod.ensure(8 * ((size_t)ctx->op.l_rows + 1)));
     CK(cudaMemsetAsync(d_ctr, 0, 64, st));
@@ -1010,7 +1152,7 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
         u32 *d_bins = ctx->bins.as<u32>(); u64 *d_maxprod = reinterpret_cast<u64*>(d_bins + 4);
         SpgemmArgs A;
         A.a_rowptr = ctx->op.l_rowptr; A.a_col = ctx->op.l_col; A.a_pos = ctx->op.l_pos;
-        A.at_colptr = ctx->op.r_colptr; A.at_row = ctx->op.r_row; A.at_pos = ctx->op.r_pos;
+        A.at_ptr = ctx->sp_ptr.as<u32>(); A.at_ent = ctx->sp_ent.as<uint2>();
         A.nrows = N; A.seed_count = ctx->cfg.seed_count;
         A.t_col = ctx->t_col.as<u32>(); A.t_num = ctx->t_num.as<int32_t>(); A.t_seeds = ctx->t_seeds.as<u32>(); A.cap = cap;
         A.counters = d_ctr; A.row_off = ctx->row_off.as<u64>(); A.row_nnz = ctx->row_nnz.as<u32>();

@@ -68,4 +68,14 @@ __global__ void k_row_products(const int64_t *__restrict__ rowptr, const u32 *__
     if (lane == 0) { prod[warp] = s; if (s) atomicAdd(total, s); }
 }
 
+// the right operand of the SpGEMM as the kernel reads it: 32-bit column pointers (half the footprint: most of it stays in
+// L2) and {row, pos} side by side, so one column is one sector instead of three
+__global__ void k_spgemm_operand(const int64_t *__restrict__ colptr, u64 ncol, const u32 *__restrict__ row, const u32 *__restrict__ pos, u64 nnz,
+                                 u32 *__restrict__ ptr32, uint2 *__restrict__ ent)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= ncol) ptr32[i] = (u32)colptr[i];
+    if (i < nnz) ent[i] = make_uint2(row[i], pos[i]);
+}
+
 } // namespace elba

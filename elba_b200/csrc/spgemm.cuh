@@ -31,7 +31,8 @@ static constexpr int SPG_WARPS_PER_CTA = 8;
 struct SpgemmArgs
 {
     const int64_t *a_rowptr; const u32 *a_col; const u32 *a_pos;       // rows of the left operand (CSR)
-    const int64_t *at_colptr; const u32 *at_row; const u32 *at_pos;    // right operand by column (CSC), rows ascending
+    const u32 *at_ptr; const uint2 *at_ent;                            // right operand by column (CSC), rows ascending: 32-bit column
+                                                                       // pointers and {row, pos} entries side by side (one sector per column)
     u32 nrows;
     int seed_count;
     u32 *t_col; int32_t *t_num; u32 *t_seeds; u64 cap;                 // unordered row storage
@@ -44,8 +45,8 @@ template <bool BLOCK> __device__ __forceinline__ void group_sync() { if (BLOCK) 
 // position of read j inside column c (rows ascending, <= UPPER entries)
 __device__ __forceinline__ u32 pos_in_column(const SpgemmArgs &A, u32 c, u32 j)
 {
-    int64_t b = A.at_colptr[c], e = A.at_colptr[c + 1];
-    for (int64_t q = b; q < e; ++q) if (A.at_row[q] == j) return A.at_pos[q];
+    const u32 b = __ldg(A.at_ptr + c), e = __ldg(A.at_ptr + c + 1);
+    for (u32 q = b; q < e; ++q) { const uint2 v = __ldg(A.at_ent + q); if (v.x == j) return v.y; }
     return 0;   // unreachable: j was found through this column
 }
 
@@ -63,37 +64,54 @@ __device__ bool spgemm_row(const SpgemmArgs &A, u32 row, u32 tid, u32 nth,
 
     const int64_t rs = A.a_rowptr[row];
     const u32 nnz = (u32)(A.a_rowptr[row + 1] - rs);
-    for (u32 t = tid; t < nnz; t += nth)
+    // ncu (profiles/r1_v7_spgemm.md): 9 % issue active, everything waits on three dependent random loads per nonzero
+    // (column id -> column pointers -> entries).  Four nonzeros per thread are in flight at every step of that chain.
+    constexpr int MLP = 4;
+    for (u32 tb = tid; tb < nnz; tb += MLP * nth)
     {
-        u32 c = __ldg(A.a_col + rs + t);
-        int64_t qb = __ldg(A.at_colptr + c), qe = __ldg(A.at_colptr + c + 1);
-        for (int64_t q = qb; q < qe; ++q)
+        u32 c[MLP], qb[MLP], qe[MLP]; uint2 e0[MLP];
+#pragma unroll
+        for (int i = 0; i < MLP; ++i) { const u32 t = tb + i * nth; c[i] = t < nnz ? __ldg(A.a_col + rs + t) : EMPTY32; }
+#pragma unroll
+        for (int i = 0; i < MLP; ++i)
         {
-            u32 j = __ldg(A.at_row + q);
-            u32 h = (j * 0x9E3779B1u) >> shift;
-            bool placed = false;
-            while (ctl[2] == 0)
+            qb[i] = qe[i] = 0;
+            if (c[i] != EMPTY32) { qb[i] = __ldg(A.at_ptr + c[i]); qe[i] = __ldg(A.at_ptr + c[i] + 1); }
+        }
+#pragma unroll
+        for (int i = 0; i < MLP; ++i) { e0[i] = make_uint2(0, 0); if (qb[i] < qe[i]) e0[i] = __ldg(A.at_ent + qb[i]); }
+#pragma unroll
+        for (int i = 0; i < MLP; ++i)
+        {
+            const u32 t = tb + i * nth;
+            for (u32 q = qb[i]; q < qe[i]; ++q)
             {
-                u32 kk = ((volatile u32*)keys)[h];
-                if (kk == j) { placed = true; break; }
-                if (kk == EMPTY32)
+                const u32 j = q == qb[i] ? e0[i].x : __ldg(A.at_ent + q).x;
+                u32 h = (j * 0x9E3779B1u) >> shift;
+                bool placed = false;
+                while (ctl[2] == 0)
                 {
-                    u32 prev = atomicCAS(&keys[h], EMPTY32, j);
-                    if (prev == EMPTY32)
+                    u32 kk = ((volatile u32*)keys)[h];
+                    if (kk == j) { placed = true; break; }
+                    if (kk == EMPTY32)
                     {
-                        u32 d = atomicAdd((u32*)&ctl[0], 1u);
-                        if (d + 1 > limit) ctl[2] = 1;      // too many distinct columns for this table
-                        placed = true; break;
+                        u32 prev = atomicCAS(&keys[h], EMPTY32, j);
+                        if (prev == EMPTY32)
+                        {
+                            u32 d = atomicAdd((u32*)&ctl[0], 1u);
+                            if (d + 1 > limit) ctl[2] = 1;      // too many distinct columns for this table
+                            placed = true; break;
+                        }
+                        if (prev == j) { placed = true; break; }
                     }
-                    if (prev == j) { placed = true; break; }
+                    h = (h + 1) & mask;
                 }
-                h = (h + 1) & mask;
-            }
-            if (placed)
-            {
-                atomicAdd(&cnt[h], 1u);
-                if (t < ((volatile u32*)tmin)[h]) atomicMin(&tmin[h], t);
-                if (t > ((volatile u32*)tmax)[h]) atomicMax(&tmax[h], t);
+                if (placed)
+                {
+                    atomicAdd(&cnt[h], 1u);
+                    if (t < ((volatile u32*)tmin)[h]) atomicMin(&tmin[h], t);
+                    if (t > ((volatile u32*)tmax)[h]) atomicMax(&tmax[h], t);
+                }
             }
         }
     }

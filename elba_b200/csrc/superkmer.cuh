@@ -93,9 +93,12 @@ __device__ __forceinline__ u32 skm_bucket(u32 v, u32 NB)
 // Where records go.  Bucket b (NB of them) owns slab[b * rcap ...]; fill[b] counts every record offered to it (records
 // beyond rcap go to the overflow list, and k_skm_count then sends the rest of that bucket there too, so that all
 // instances of a k-mer are counted in one place).
+// Several GPUs: every GPU parses ALL reads (the 2-bit arena is all-gathered: 0.25 B per base, against 4.6 B per instance
+// for the records) and keeps only the records of the buckets it owns, [b_lo, b_lo + b_cnt) of NB; no record crosses
+// NVLink.  read_base makes the read ids of the records global.
 struct RecSink
 {
-    SkmRec *slab; u64 *fill; u32 rcap; u32 NB;
+    SkmRec *slab; u64 *fill; u32 rcap; u32 NB; u32 b_lo, b_cnt, read_base;
     SkmRec *ovf; u64 *ovf_cursor; u64 *ovf_inst; u64 ovf_cap;
 };
 
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
             prev = x;
         }
         bmask &= (nk >= 32u) ? 0xFFFFFFFFu : ((1u << nk) - 1u);
-        const u64 meta0 = ((u64)read << 32) | p0;
+        const u64 meta0 = ((u64)(read + sink.read_base) << 32) | p0;
         // one record per run of equal minimizers; the bucket reservations of SK_NR records are issued back to back
         while (bmask)
         {
@@ -191,7 +194,8 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
                     bmask &= bmask - 1;
                     n[i] = (bmask ? (u32)__ffs(bmask) - 1u : nk) - s0[i];
                     if (n[i] > nmax) { n[i] = nmax; bmask |= 1u << (s0[i] + n[i]); }
-                    b[i] = skm_bucket(s_mn[s0[i] * SK_THREADS + tid], sink.NB);
+                    b[i] = skm_bucket(s_mn[s0[i] * SK_THREADS + tid], sink.NB) - sink.b_lo;
+                    ok[i] = b[i] < sink.b_cnt;                         // another GPU's bucket: nothing to write
                     const u32 sh = 2 * s0[i];
                     rec[i].x = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
                     rec[i].y = ((w1 << sh) & ~31ull) | (u64)(n[i] - 1);

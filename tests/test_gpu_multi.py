@@ -15,10 +15,10 @@ def _ngpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def _launch(world, args, port):
+def _launch(world, args, port, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_worker.py")] + [str(a) for a in args]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert p.returncode == 0 and "MULTI-GPU PARITY OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
 
 
@@ -34,3 +34,20 @@ def test_multi_gpu_parity_synthetic_hifi(world):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     _launch(world, ["synth:300000,500,12000,0.01", 31, 2, 4, "-", 16], 29631 + world)
+
+
+@pytest.mark.parametrize("world,grid", [(2, "-"), (4, "2x2")])
+def test_multi_gpu_hash_path_forced_k31(world, grid):
+    """k = 31 counts through super-k-mers on several GPUs too (every GPU parses all reads, counts its own buckets);
+    the two-level hash partition with its all-to-all must still give the same bits."""
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _launch(world, ["synth:300000,500,12000,0.01", 31, 2, 4, grid, 16], 29651 + world, env={"ELBA_FE_COUNT_PATH": "hash"})
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_superkmer_other_geometries(world):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _launch(world, ["synth:200000,300,9000,0.02", 25, 2, 6, "-"], 29671 + world)
+    _launch(world, ["reads_fa", 21, 2, 8, "-"], 29681 + world)

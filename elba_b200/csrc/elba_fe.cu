@@ -1156,9 +1156,14 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
         A.nrows = N; A.seed_count = ctx->cfg.seed_count;
         A.t_col = ctx->t_col.as<u32>(); A.t_num = ctx->t_num.as<int32_t>(); A.t_seeds = ctx->t_seeds.as<u32>(); A.cap = cap;
         A.counters = d_ctr; A.row_off = ctx->row_off.as<u64>(); A.row_nnz = ctx->row_nnz.as<u32>();
+        // rows with up to mid_max products would go to the two-warp kernel (k_spgemm_mid).  Measured on C. elegans 40X
+        // (profiles/r1_v8_spgemm.md): 11 two-warp rows per SM are SLOWER than 4 eight-warp rows (8.7 vs 7.3 ms), so the
+        // bin is off unless asked for.
+        u32 mid_max = 0;
+        if (const char *e = getenv("ELBA_FE_SPGEMM_MID")) { long v = atol(e); if (v >= 0 && v <= (long)SPG_MID_MAXPROD) mid_max = (u32)v; }
         if (N)
         {
-            k_spgemm_bin<<<nblk(N, 256), 256, 0, st>>>(ctx->prod.as<u64>(), N, ctx->small_rows.as<u32>(), ctx->mid_rows.as<u32>(), ctx->big_rows.as<u32>(), d_bins, A.row_off, A.row_nnz, d_maxprod);
+            k_spgemm_bin<<<nblk(N, 256), 256, 0, st>>>(ctx->prod.as<u64>(), N, ctx->small_rows.as<u32>(), ctx->mid_rows.as<u32>(), ctx->big_rows.as<u32>(), d_bins, A.row_off, A.row_nnz, d_maxprod, mid_max);
             CKL(); LAUNCHED(ctx);
             EventPair &sp = next_pair(ctx->sev, ctx->sev_used);
             CK(cudaEventRecord(sp.a, st));

@@ -305,3 +305,46 @@ def ref_bloom_fill(entries: int, err: float, kmers: np.ndarray, k: int = 17, low
         return bits, int(L.ref_bloom_hashes(b)), out
     finally:
         L.ref_bloom_free(b)
+
+
+# ---- the consumer of B: X-drop seed-and-extend of every aligned pair ---------------------------
+XDROP_FIELDS = ("begQ", "endQ", "begT", "endT", "score", "rc", "passed", "containedQ", "containedT", "direction", "directionT", "suffix", "suffixT")
+
+
+def alignment_pairs(b_rowptr: np.ndarray, b_col: np.ndarray, b_seeds: np.ndarray):
+    """The nonzeros of B the reference aligns on one rank (src/PairwiseAlignment.cpp:52: strict upper triangle) with the
+    seed it uses (seeds[0], :90): rows, cols, seed position in the row read, seed position in the column read."""
+    rows = np.repeat(np.arange(len(b_rowptr) - 1, dtype=np.int64), np.diff(b_rowptr))
+    cols = np.asarray(b_col, np.int64)
+    keep = rows < cols
+    s = np.asarray(b_seeds).reshape(-1, 4)
+    return rows[keep], cols[keep], np.ascontiguousarray(s[keep, 0], np.uint32), np.ascontiguousarray(s[keep, 1], np.uint32)
+
+
+def _byte_offsets(dna) -> np.ndarray:
+    return np.ascontiguousarray(dna.offsets, np.uint64)
+
+
+def xdrop(dna, k: int, rows, cols, seedq, seedt, mat: int = 1, mis: int = -1, gap: int = -1, dropoff: int = 15) -> np.ndarray:
+    """oracle/xdrop_oracle.cpp: [npairs, 13] int32 in XDROP_FIELDS order (defaults: src/main.cpp:53-56)."""
+    L = lib()
+    n = len(rows)
+    out = np.zeros((n, len(XDROP_FIELDS)), np.int32)
+    assert L.elba_oracle_xdrop_fields() == len(XDROP_FIELDS)
+    L.elba_oracle_xdrop_batch(_p(dna.buf), _p(_byte_offsets(dna)), _p(np.ascontiguousarray(dna.lengths, np.uint64)), _i32(k),
+                              _p(np.ascontiguousarray(rows, np.int64)), _p(np.ascontiguousarray(cols, np.int64)),
+                              _p(np.ascontiguousarray(seedq, np.uint32)), _p(np.ascontiguousarray(seedt, np.uint32)), _u64(n),
+                              _i32(mat), _i32(mis), _i32(gap), _i32(dropoff), _p(out))
+    return out
+
+
+def ref_xdrop(dna, k: int, lower: int, upper: int, rows, cols, seedq, seedt, mat: int = 1, mis: int = -1, gap: int = -1, dropoff: int = 15) -> np.ndarray:
+    """The reference's own XDropAligner.cpp + Overlap.cpp (oracle/_ref) on the same pairs."""
+    L = ref_lib(k, lower, upper)
+    n = len(rows)
+    out = np.zeros((n, len(XDROP_FIELDS)), np.int32)
+    L.ref_xdrop_batch(_p(dna.buf), _p(_byte_offsets(dna)), _p(np.ascontiguousarray(dna.lengths, np.uint64)),
+                      _p(np.ascontiguousarray(rows, np.int64)), _p(np.ascontiguousarray(cols, np.int64)),
+                      _p(np.ascontiguousarray(seedq, np.uint32)), _p(np.ascontiguousarray(seedt, np.uint32)), _u64(n),
+                      _i32(mat), _i32(mis), _i32(gap), _i32(dropoff), _p(out))
+    return out

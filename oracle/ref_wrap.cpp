@@ -39,6 +39,8 @@
 #include "Logger.hpp"
 #include "DnaSeq.hpp"
 #include "DnaBuffer.hpp"
+#include "Overlap.hpp"
+#include "XDropAligner.hpp"
 #include <cstring>
 #include <numeric>
 #include <algorithm>
@@ -278,6 +280,27 @@ void ref_get_B(void *h, int64_t *rowptr, int64_t *col, int32_t *num, uint32_t *s
     RefResult *r = (RefResult*)h;
     std::memcpy(rowptr, r->b_rowptr.data(), r->b_rowptr.size() * 8); std::memcpy(col, r->b_col.data(), r->b_col.size() * 8);
     std::memcpy(num, r->b_num.data(), r->b_num.size() * 4); std::memcpy(seeds, r->b_seeds.data(), r->b_seeds.size() * 4);
+}
+
+/*
+ * The consumer of B: Overlap(len, seed).extend_overlap(seqQ, seqT, ...) exactly as
+ * src/PairwiseAlignment.cpp:82-91 drives it — xdrop_aligner + classify_alignment (src/XDropAligner.cpp) and the
+ * direction / suffix fields (src/Overlap.cpp:20-73).  13 ints per pair, the order of oracle/xdrop_oracle.cpp.
+ */
+void ref_xdrop_batch(const uint8_t *packed, const uint64_t *off, const uint64_t *lens, const int64_t *rows, const int64_t *cols,
+                     const uint32_t *seedq, const uint32_t *seedt, uint64_t npairs, int mat, int mis, int gap, int drop, int32_t *out)
+{
+    for (uint64_t p = 0; p < npairs; ++p)
+    {
+        const size_t lq = lens[rows[p]], lt = lens[cols[p]];
+        DnaSeq seqQ(lq, const_cast<uint8_t*>(packed + off[rows[p]])), seqT(lt, const_cast<uint8_t*>(packed + off[cols[p]]));
+        Overlap o(std::make_tuple((PosInRead)lq, (PosInRead)lt), std::make_tuple((PosInRead)seedq[p], (PosInRead)seedt[p]));
+        o.extend_overlap(seqQ, seqT, mat, mis, gap, drop);
+        int32_t *r = out + 13 * p;
+        r[0] = (int32_t)std::get<0>(o.beg); r[1] = (int32_t)std::get<0>(o.end); r[2] = (int32_t)std::get<1>(o.beg); r[3] = (int32_t)std::get<1>(o.end);
+        r[4] = o.score; r[5] = o.rc; r[6] = o.passed; r[7] = o.containedQ; r[8] = o.containedT;
+        r[9] = o.direction; r[10] = o.directionT; r[11] = o.suffix; r[12] = o.suffixT;
+    }
 }
 
 } // extern "C"

@@ -7,6 +7,7 @@
 #include "matrix_build.cuh"
 #include "spgemm.cuh"
 #include "superkmer.cuh"
+#include "xdrop.cuh"
 #include "comm.cuh"
 #include <cub/cub.cuh>
 #include <string>
@@ -75,6 +76,8 @@ struct elba_fe_ctx
     int col_bits = 1, read_bits = 1;
     // B
     DevBuf sp_ptr, sp_ent;               // the right operand as the SpGEMM reads it (k_spgemm_operand)
+    DevBuf xd_flag, xd_rowof, xd_prow, xd_pcol, xd_sq, xd_st, xd_nz, xd_out, xd_scratch, xd_max;      // elba_fe_align
+    u64 xd_pairs = 0; bool xd_done = false; cudaEvent_t xd_e0 = nullptr, xd_e1 = nullptr;
     DevBuf t_col, t_num, t_seeds, row_off, row_nnz, bins, small_rows, mid_rows, big_rows, ovf_rows, gscratch, b_rowptr, b_col, b_num, b_seeds;
     u64 b_cap_hint = 0;
     DevBuf cubtmp, hll_regs, bloom;
@@ -223,7 +226,7 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
-    cudaEventCreate(&ctx->ev_x0); cudaEventCreate(&ctx->ev_x1);
+    cudaEventCreate(&ctx->ev_x0); cudaEventCreate(&ctx->ev_x1); cudaEventCreate(&ctx->xd_e0); cudaEventCreate(&ctx->xd_e1);
     if (const char *e = getenv("ELBA_FE_SCRATCH_MB")) { long v = atol(e); if (v >= 8 && v <= 65536) ctx->scratch_mb = (u64)v; }
     // opt in to large dynamic shared memory
     cudaFuncSetAttribute(k_scatter1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S1_TILE + 2 * sizeof(u32) * MAX_P1));
@@ -248,7 +251,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut, &ctx->filter,
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
-        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->gr_packed, &ctx->gr_off, &ctx->gr_len64, &ctx->gr_len32, &ctx->gr_chunk, &ctx->gr_kmer, &ctx->gr_nks, &ctx->all_key, &ctx->all_pos, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
+        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->gr_packed, &ctx->gr_off, &ctx->gr_len64, &ctx->gr_len32, &ctx->gr_chunk, &ctx->gr_kmer, &ctx->gr_nks, &ctx->all_key, &ctx->all_pos, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
@@ -263,6 +266,8 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_x0) cudaEventDestroy(ctx->ev_x0);
     if (ctx->ev_x1) cudaEventDestroy(ctx->ev_x1);
+    if (ctx->xd_e0) cudaEventDestroy(ctx->xd_e0);
+    if (ctx->xd_e1) cudaEventDestroy(ctx->xd_e1);
     delete ctx;
     return 0;
 }
@@ -1407,6 +1412,78 @@ int elba_fe_device_A(elba_fe_ctx *ctx, const int64_t **rowptr, const uint32_t **
     if (!ctx) return ELBA_FE_ERR_INVALID;
     if (ctx->phase < 3) return fail(ctx, ELBA_FE_ERR_STATE, "A not built");
     if (rowptr) *rowptr = ctx->a_rowptr.as<int64_t>(); if (col) *col = ctx->a_col.as<u32>(); if (pos) *pos = ctx->a_pos.as<u32>();
+    return 0;
+}
+
+// ---- the consumer of B: X-drop alignment of its nonzeros (xdrop.cuh) ----------------------------------------
+int elba_fe_align(elba_fe_ctx *ctx, int mat, int mis, int gap, int dropoff, uint64_t *npairs)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 4) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_align: call elba_fe_spgemm first");
+    if (ctx->comm.nranks > 1) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_align: one GPU only in this version");
+    if (mat <= 0 || mis > 0 || gap >= 0 || dropoff < 0) return fail(ctx, ELBA_FE_ERR_INVALID, "elba_fe_align: need mat > 0, mis <= 0, gap < 0, dropoff >= 0");
+    CK(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->stream;
+    const u64 nnz = ctx->sz.nnzB; const u32 N = ctx->b_rows;
+    ctx->xd_done = false;
+    CK(cudaEventRecord(ctx->xd_e0, st));
+    CK(ctx->xd_flag.ensure(8 * (nnz + 2))); CK(ctx->xd_rowof.ensure(4 * (nnz + 1))); CK(ctx->xd_max.ensure(64));
+    k_xdrop_select<<<nblk(nnz + 1, 256), 256, 0, st>>>(ctx->b_rowptr.as<int64_t>(), ctx->b_col.as<u32>(), N, nnz, ctx->op.row0, ctx->op.col0,
+        ctx->xd_flag.as<u64>(), ctx->xd_rowof.as<u32>());
+    CKL(); LAUNCHED(ctx);
+    int rc = exclusive_scan_inplace(ctx, ctx->xd_flag.as<u64>(), nnz + 1);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->xd_max.p, 0, 64, st));
+    if (ctx->n) { k_max_u32<<<grid_for(ctx, 2), 256, 0, st>>>(ctx->len32.as<u32>(), ctx->n, ctx->xd_max.as<u32>()); CKL(); LAUNCHED(ctx); }
+    u64 np = 0; u32 maxlen = 0;
+    CK(cudaMemcpyAsync(&np, ctx->xd_flag.as<u64>() + nnz, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&maxlen, ctx->xd_max.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const u64 n1 = std::max<u64>(np, 1);
+    CK(ctx->xd_prow.ensure(4 * n1)); CK(ctx->xd_pcol.ensure(4 * n1)); CK(ctx->xd_sq.ensure(4 * n1)); CK(ctx->xd_st.ensure(4 * n1)); CK(ctx->xd_nz.ensure(8 * n1));
+    CK(ctx->xd_out.ensure(4 * XD_FIELDS * n1));
+    if (nnz) { k_xdrop_pairs<<<nblk(nnz, 256), 256, 0, st>>>(ctx->xd_flag.as<u64>(), ctx->xd_rowof.as<u32>(), ctx->b_col.as<u32>(), ctx->b_seeds.as<u32>(), nnz,
+                   ctx->xd_prow.as<u32>(), ctx->xd_pcol.as<u32>(), ctx->xd_sq.as<u32>(), ctx->xd_st.as<u32>(), ctx->xd_nz.as<u64>()); CKL(); LAUNCHED(ctx); }
+    if (np)
+    {
+        const u32 warps_per_cta = 4;
+        const u32 grid = (u32)std::min<u64>((np + warps_per_cta - 1) / warps_per_cta, (u64)grid_for(ctx, 8));
+        XdropArgs A;
+        A.buf = ctx->packed.as<uint8_t>(); A.off = ctx->off.as<u64>(); A.len = ctx->len32.as<u32>();
+        A.k = ctx->cfg.k; A.mat = mat; A.mis = mis; A.gap = gap; A.drop = dropoff;
+        A.prow = ctx->xd_prow.as<u32>(); A.pcol = ctx->xd_pcol.as<u32>(); A.sq = ctx->xd_sq.as<u32>(); A.st = ctx->xd_st.as<u32>(); A.npairs = np;
+        A.stride = (u64)maxlen + 4;
+        CK(ctx->xd_scratch.ensure(sizeof(int) * 3 * A.stride * (u64)grid * warps_per_cta));
+        A.scratch = ctx->xd_scratch.as<int>(); A.out = ctx->xd_out.as<int32_t>();
+        k_xdrop<<<grid, 32 * warps_per_cta, 0, st>>>(A); CKL(); LAUNCHED(ctx);
+    }
+    CK(cudaEventRecord(ctx->xd_e1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; if (cudaEventElapsedTime(&ms, ctx->xd_e0, ctx->xd_e1) == cudaSuccess) ctx->tm.align_ms = ms;
+    ctx->xd_pairs = np; ctx->xd_done = true;
+    if (npairs) *npairs = np;
+    return 0;
+}
+
+static __global__ void k_xdrop_ids(const u32 *__restrict__ prow, const u32 *__restrict__ pcol, u64 n, int64_t row0, int64_t col0, int64_t *__restrict__ row, int64_t *__restrict__ col)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { row[i] = row0 + prow[i]; col[i] = col0 + pcol[i]; }
+}
+
+int elba_fe_get_alignments(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t *fields)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (!ctx->xd_done || ctx->phase < 4) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_get_alignments: call elba_fe_align first");
+    const u64 np = ctx->xd_pairs;
+    if (!np) return 0;
+    DevBuf tmp;
+    CK(tmp.ensure(16 * np));
+    k_xdrop_ids<<<nblk(np, 256), 256, 0, ctx->stream>>>(ctx->xd_prow.as<u32>(), ctx->xd_pcol.as<u32>(), np, ctx->op.row0, ctx->op.col0, tmp.as<int64_t>(), tmp.as<int64_t>() + np);
+    LAUNCHED(ctx);
+    D2H(row, tmp.p, 8 * np); D2H(col, tmp.as<int64_t>() + np, 8 * np); D2H(fields, ctx->xd_out.p, 4 * (size_t)XD_FIELDS * np);
+    CK(cudaStreamSynchronize(ctx->stream));
+    tmp.release();
     return 0;
 }
 

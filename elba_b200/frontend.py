@@ -49,7 +49,7 @@ class Timings(C.Structure):
     _fields_ = [("upload_ms", C.c_float), ("count_ms", C.c_float), ("build_ms", C.c_float), ("spgemm_ms", C.c_float),
                 ("download_ms", C.c_float), ("count_kernel_ms", C.c_float), ("spgemm_kernel_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("partition_ms", C.c_float), ("lookup_ms", C.c_float), ("exchange_ms", C.c_float),
-                ("exchange_mbytes", C.c_float), ("panel_mbytes", C.c_float), ("reserved", C.c_float * 3)]
+                ("exchange_mbytes", C.c_float), ("panel_mbytes", C.c_float), ("align_ms", C.c_float), ("reserved", C.c_float * 2)]
 
     def as_dict(self):
         return {n: (int(getattr(self, n)) if n == "kernel_launches" else float(getattr(self, n))) for n, _ in self._fields_ if n != "reserved"}
@@ -61,7 +61,7 @@ ABI_SYMBOLS = (
     "elba_fe_upload_reads", "elba_fe_set_reads_device", "elba_fe_count", "elba_fe_build_A", "elba_fe_spgemm", "elba_fe_run",
     "elba_fe_synchronize", "elba_fe_sizes", "elba_fe_get_kmers", "elba_fe_get_A", "elba_fe_get_AT", "elba_fe_get_B",
     "elba_fe_get_B_triples", "elba_fe_device_B", "elba_fe_device_A", "elba_fe_hll", "elba_fe_bloom", "elba_fe_get_kmer_stream",
-    "elba_fe_timings", "elba_fe_reset_timings",
+    "elba_fe_timings", "elba_fe_reset_timings", "elba_fe_align", "elba_fe_get_alignments",
     "elba_fe_comm_get_id", "elba_fe_comm_init", "elba_fe_comm_set_grid", "elba_fe_comm_info", "elba_fe_block_extent", "elba_fe_sizes_global",
 )
 
@@ -240,6 +240,18 @@ class Context:
         num, seeds = np.zeros(s["nnzB"], np.int32), np.zeros((s["nnzB"], 4), np.uint32)
         self._ck(self.L.elba_fe_get_B_triples(self.h, _p(row), _p(col), _p(num), _p(seeds)))
         return row, col, num, seeds
+
+    ALIGN_FIELDS = ("begQ", "endQ", "begT", "endT", "score", "rc", "passed", "containedQ", "containedT", "direction", "directionT", "suffix", "suffixT")
+
+    def align(self, mat: int = 1, mis: int = -1, gap: int = -1, dropoff: int = 15):
+        """X-drop seed-and-extend of B's nonzeros (PairwiseAlignment, src/PairwiseAlignment.cpp:5-106; defaults src/main.cpp:53-56):
+        (rows, cols, fields[npairs, 13]) with global read ids, pairs in B's row-major order."""
+        n = C.c_uint64()
+        self._ck(self.L.elba_fe_align(self.h, C.c_int(mat), C.c_int(mis), C.c_int(gap), C.c_int(dropoff), C.byref(n)))
+        rows, cols = np.zeros(n.value, np.int64), np.zeros(n.value, np.int64)
+        out = np.zeros((n.value, len(self.ALIGN_FIELDS)), np.int32)
+        self._ck(self.L.elba_fe_get_alignments(self.h, _p(rows), _p(cols), _p(out)))
+        return rows, cols, out
 
     def hll(self):
         regs, est = np.zeros(4096, np.uint8), C.c_double()

@@ -163,6 +163,17 @@ int elba_fe_get_B_triples(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t 
 int elba_fe_device_B(elba_fe_ctx *ctx, const int64_t **rowptr, const uint32_t **col, const int32_t **numshared, const uint32_t **seeds);
 int elba_fe_device_A(elba_fe_ctx *ctx, const int64_t **rowptr, const uint32_t **col, const uint32_t **pos);
 
+/* ---- the consumer of B (next row of the hot path; first version, one GPU) ------------------------------------------ */
+/* X-drop seed-and-extend of B's nonzeros: PairwiseAlignment (src/PairwiseAlignment.cpp:5-106) keeps the strict upper
+ * triangle of the local block (:52) and runs Overlap(len, seeds[0]).extend_overlap on each (:90-91; src/Overlap.cpp:20-73;
+ * xdrop_aligner + classify_alignment, src/XDropAligner.cpp:7-282).  mat / mis / gap / dropoff: src/main.cpp:53-56
+ * (1, -1, -1, 15).  *npairs = number of aligned pairs. */
+#define ELBA_FE_ALIGN_FIELDS 13   /* begQ endQ begT endT score rc passed containedQ containedT direction directionT suffix suffixT */
+int elba_fe_align(elba_fe_ctx *ctx, int mat, int mis, int gap, int dropoff, uint64_t *npairs);
+/* the aligned pairs in B's row-major order: global row / column read ids and ELBA_FE_ALIGN_FIELDS ints each = the fields of
+ * the reference's Overlap (include/Overlap.hpp:25-31) that extend_overlap sets */
+int elba_fe_get_alignments(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t *fields);
+
 /* ---- the reference's sizing sketches, bit-exact (not needed for the result when lower >= 2) ----------- */
 /* HyperLogLog over the canonical k-mers of the uploaded reads exactly as KmerEstimateHandler drives it
  * (include/KmerOps.hpp:58-69, src/HyperLogLog.cpp:40-76): registers[4096] and estimate(). */
@@ -188,7 +199,8 @@ typedef struct {
     float exchange_ms;      /* several GPUs: the all-to-all of the k-mer partitions */
     float exchange_mbytes;  /* MB this rank sent in it */
     float panel_mbytes;     /* MB this rank received in the all-gather of A's row blocks */
-    float reserved[3];
+    float align_ms;         /* elba_fe_align: pair selection + the X-drop kernel */
+    float reserved[2];
 } elba_fe_timings_t;
 int elba_fe_timings(elba_fe_ctx *ctx, elba_fe_timings_t *out);
 int elba_fe_reset_timings(elba_fe_ctx *ctx);

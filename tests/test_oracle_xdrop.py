@@ -1,7 +1,7 @@
 """The oracle of the NEXT hot-path row (X-drop seed-and-extend of B's nonzeros, the stage that consumes
 the overlap matrix) against the reference: golden digests made by the reference's own XDropAligner.cpp + Overlap.cpp
 (tests/golden/make_golden_xdrop.py), and the two run side by side where oracle/_ref is present.  CPU only: the CUDA kernel
-for this row is round-2 work; this pins what it will be compared with."""
+for this row (elba_b200/csrc/xdrop.cuh) is checked against exactly this in tests/test_gpu_xdrop.py."""
 import json
 import os
 

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="celegans40x_hifi")
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--passes", type=int, default=3)
+ap.add_argument("--align", action="store_true", help="also run the X-drop alignment of B's nonzeros once per variant and print its time")
 ap.add_argument("variants", nargs="*", default=[""])
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -49,6 +50,13 @@ for v in a.variants:
             first = sig
         print(f"[tune] {v or 'default':40s} wall {best['wall_ms']:8.2f} ms  " + "  ".join(f"{n[:-3]} {best.get(n, 0):7.2f}" for n in keys)
               + f"  launches {best.get('kernel_launches')}  sizes {sig} {'==' if sig == first else '!= FIRST VARIANT'}", flush=True)
+        if a.align:
+            t1 = time.perf_counter()
+            rows, cols, out = ctx.align()
+            wall = (time.perf_counter() - t1) * 1e3
+            tm = ctx.timings()
+            print(f"[tune] {v or 'default':40s} align: {len(rows)} pairs, device {tm['align_ms']:.1f} ms (wall incl. D2H {wall:.1f} ms), "
+                  f"{len(rows) / max(tm['align_ms'], 1e-9) * 1e3:.0f} pairs/s, passed {int(out[:, 6].sum())}, mean score {out[:, 4].mean() if len(rows) else 0:.1f}", flush=True)
         ctx.close()
     except Exception as ex:  # keep going: the other variants still tell something
         print(f"[tune] {v or 'default':40s} FAILED: {ex}", flush=True)

@@ -15,7 +15,8 @@
 //                    32-bit integer arithmetic, pruned cells included, so scores and end points are bit-exact; the one
 //                    floating-point comparison of classify_alignment is evaluated with the same expression.
 //
-// This is the first correct version of this row (parity against oracle/xdrop_oracle.cpp and the reference's digests); it is
+// This is the first correct version of this row (parity against the CPU oracle and the reference's own digests,
+// tests/test_gpu_xdrop.py); it is
 // not tuned: one warp per pair regardless of its length, both directions one after the other.
 #pragma once
 #include "common.cuh"

@@ -24,6 +24,9 @@
  */
 #include "KmerOps.hpp"
 #include "SharedSeeds.hpp"
+#ifdef ELBA_FE_SHIM_ALIGN
+#include "PairwiseAlignment.hpp"      /* also replaces src/PairwiseAlignment.cpp (first version, one rank) */
+#endif
 #include "elba_fe.h"
 
 #include <cstdio>
@@ -214,7 +217,9 @@ create_seed_matrix(CT<PosInRead>::PSpParMat& A, CT<PosInRead>::PSpParMat& AT)
 
     std::vector<int64_t> rows(sz.nnzB), cols(sz.nnzB); std::vector<int32_t> num(sz.nnzB); std::vector<uint32_t> seeds(4 * sz.nnzB);
     fe_check(elba_fe_get_B_triples(st.ctx, rows.data(), cols.data(), num.data(), seeds.data()), st.ctx, "elba_fe_get_B_triples", comm);
+#ifndef ELBA_FE_SHIM_ALIGN
     elba_fe_destroy(st.ctx);
+#endif
 
     /* field-wise: std::tuple's memory order is not its template order */
     std::vector<SharedSeeds> vals; vals.reserve(sz.nnzB);
@@ -233,11 +238,57 @@ create_seed_matrix(CT<PosInRead>::PSpParMat& A, CT<PosInRead>::PSpParMat& AT)
     for (uint64_t e = 0; e < sz.nnzB; ++e) tuples[e] = std::make_tuple(rows[e] - roff, cols[e] - coff, vals[e]);
     combblas::SpTuples<int64_t, SharedSeeds> spt((int64_t)sz.nnzB, nloc_r, nloc_c, tuples, false);
     auto *dcsc = new CT<SharedSeeds>::PSpDCCols(spt, false);
-    return std::make_unique<CT<SharedSeeds>::PSpParMat>(dcsc, st.grid);
+    auto B = std::make_unique<CT<SharedSeeds>::PSpParMat>(dcsc, st.grid);
 #else
     CT<int64_t>::PDistVec drows(rows, st.grid);
     CT<int64_t>::PDistVec dcols(cols, st.grid);
     CT<SharedSeeds>::PDistVec dvals(vals, st.grid);
-    return std::make_unique<CT<SharedSeeds>::PSpParMat>(st.totreads, st.totreads, drows, dcols, dvals, false);
+    auto B = std::make_unique<CT<SharedSeeds>::PSpParMat>(st.totreads, st.totreads, drows, dcols, dvals, false);
 #endif
+#ifdef ELBA_FE_SHIM_ALIGN
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_states[B.get()] = st;                 /* B is still on the device: PairwiseAlignment below aligns it there */
+    }
+#endif
+    return B;
 }
+
+#ifdef ELBA_FE_SHIM_ALIGN
+/*
+ * PairwiseAlignment (include/PairwiseAlignment.hpp:9-10, src/PairwiseAlignment.cpp:5-106) on the device: the nonzeros of
+ * the upper triangle of B, each extended from seeds[0] by the X-drop aligner (elba_fe_align).  The reads and B never left
+ * the GPU, so dfd's row / column buffers are not touched.  The result goes through the same triple constructor as in
+ * the reference (:97-103); the Overlap values are filled field-wise from the 13 ints per pair.  One rank in this version.
+ */
+std::unique_ptr<CT<Overlap>::PSpParMat>
+PairwiseAlignment(DistributedFastaData& dfd, CT<SharedSeeds>::PSpParMat& Bmat, int mat, int mis, int gap, int dropoff)
+{
+    FeState st = take_state(&Bmat);
+    MPI_Comm comm = st.grid->GetWorld();
+    uint64_t np = 0;
+    fe_check(elba_fe_align(st.ctx, mat, mis, gap, dropoff, &np), st.ctx, "elba_fe_align", comm);
+    std::vector<int64_t> rows(np), cols(np); std::vector<int32_t> f((size_t)ELBA_FE_ALIGN_FIELDS * np);
+    fe_check(elba_fe_get_alignments(st.ctx, rows.data(), cols.data(), f.data()), st.ctx, "elba_fe_get_alignments", comm);
+    /* read lengths of the aligned pairs: from the library's copy of the reads (dfd keeps the same lengths in its index) */
+    elba_fe_destroy(st.ctx);
+
+    auto& index = dfd.getindex();
+    const auto& records = index.getmyrecords();     /* one rank: every read is local */
+    std::vector<Overlap> overlaps; overlaps.reserve(np);
+    for (uint64_t p = 0; p < np; ++p)
+    {
+        const int32_t *r = &f[(size_t)ELBA_FE_ALIGN_FIELDS * p];
+        std::tuple<PosInRead, PosInRead> len((PosInRead)records[rows[p]].len, (PosInRead)records[cols[p]].len);
+        Overlap o(len, std::make_tuple((PosInRead)0, (PosInRead)0));
+        std::get<0>(o.beg) = (PosInRead)r[0]; std::get<0>(o.end) = (PosInRead)r[1]; std::get<1>(o.beg) = (PosInRead)r[2]; std::get<1>(o.end) = (PosInRead)r[3];
+        o.score = r[4]; o.rc = r[5] != 0; o.passed = r[6] != 0; o.containedQ = r[7] != 0; o.containedT = r[8] != 0;
+        o.direction = (int8_t)r[9]; o.directionT = (int8_t)r[10]; o.suffix = r[11]; o.suffixT = r[12];
+        overlaps.push_back(o);
+    }
+    CT<int64_t>::PDistVec drows(rows, st.grid);
+    CT<int64_t>::PDistVec dcols(cols, st.grid);
+    CT<Overlap>::PDistVec dvals(overlaps, st.grid);
+    return std::make_unique<CT<Overlap>::PSpParMat>(st.totreads, st.totreads, drows, dcols, dvals, false);
+}
+#endif

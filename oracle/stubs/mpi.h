@@ -31,6 +31,7 @@ typedef long long MPI_Count;
 typedef long MPI_Aint;
 typedef int MPI_Datatype;
 typedef int MPI_Op;
+typedef int MPI_Request;     /* DistributedFastaData.hpp:54 only declares vectors of them */
 
 #define MPI_COMM_WORLD 0
 #define MPI_SUCCESS 0

@@ -69,8 +69,8 @@ def test_cpp_shim_compiles_against_the_reference_headers():
     ref = "/root/reference"
     if not os.path.exists(os.path.join(ref, "include", "KmerOps.hpp")):
         pytest.skip("reference tree not present")
-    for k, lo, up in ((31, 15, 35), (17, 2, 8)):
-        cmd = ["g++", "-fsyntax-only", "-std=c++17", f"-DKMER_SIZE={k}", f"-DLOWER_KMER_FREQ={lo}", f"-DUPPER_KMER_FREQ={up}", "-DLOG_LEVEL=0",
+    for k, lo, up, extra in ((31, 15, 35, []), (17, 2, 8, []), (17, 2, 8, ["-DELBA_FE_SHIM_ALIGN"])):      # the last one also replaces PairwiseAlignment
+        cmd = ["g++", "-fsyntax-only", "-std=c++17", "-Wno-deprecated-declarations", f"-DKMER_SIZE={k}", f"-DLOWER_KMER_FREQ={lo}", f"-DUPPER_KMER_FREQ={up}", "-DLOG_LEVEL=0", *extra,
                "-I", os.path.join(ROOT, "oracle", "stubs"), "-I", os.path.join(ref, "include"), "-I", os.path.join(ref, "src"),
                "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "elba_b200", "host", "elba_fe_shim.cpp")]
         p = subprocess.run(cmd, capture_output=True, text=True)

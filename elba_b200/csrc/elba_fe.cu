@@ -397,9 +397,6 @@ static __global__ void k_add_u64(u64 *__restrict__ v, u64 n, u64 add)
     if (i < n) v[i] += add;
 }
 
-static int allgather_u64(elba_fe_ctx *ctx, u64 mine, std::vector<u64> &all);
-static int allgatherv(elba_fe_ctx *ctx, const void *send, void *recv, const std::vector<u64> &count, size_t esize);
-
 // Several GPUs: all-gather the 2-bit arenas (0.25 B per base) and the read tables; the ranks hold consecutive blocks of reads,
 // so the gathered index of a read is its global id minus the first rank's offset.  ok = false: the blocks are not consecutive.
 static int gather_reads(elba_fe_ctx *ctx, SkmPlan &plan, bool &ok)

@@ -325,6 +325,16 @@ def main():
                     "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_e2e},
             "gpu_launches": int(tm["kernel_launches"]), "clocks": clocks,
         }
+        if world > 1:
+            # NVLink side of the roofline: what this rank received in the counting exchange over its device time
+            try:
+                xb, xs = float(tm.get("exchange_mbytes", 0.0)) * 1e6, float(tm.get("exchange_ms", 0.0)) / 1e3
+                line["roofline_nvlink"] = {"bound": "nvlink", "exchange": ("all-gather of the 2-bit reads and read tables" if skm else "all-to-all of the level-1 k-mer partitions"),
+                                           "bytes_per_gpu": xb, "seconds": xs, "achieved": (xb / xs / 1e9) if xs > 0 else 0.0, "peak": 900.0, "unit": "GB/s",
+                                           "frac": (xb / xs / 1e9 / 900.0) if xs > 0 else 0.0, "peak_source": "NVLink 5, 900 GB/s per direction per GPU (nominal)",
+                                           "panel_bytes_per_gpu": float(tm.get("panel_mbytes", 0.0)) * 1e6}
+            except Exception as ex:          # never lose the bench line over a reporting extra
+                line["roofline_nvlink"] = {"error": str(ex)}
         if world == 1 and not args.no_cpu_baseline:
             dna, ck, cl, cu, sample = cpu_reference_sample(args.workload)
             ranks, cores = square_ranks()

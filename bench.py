@@ -104,19 +104,30 @@ def load_workload(name: str, rank: int, world: int, device, scale: float = 1.0):
     s = synth.SHAPES[w["shape"]]
     genome, reads = int(s["genome"] * scale), int(s["reads"] * scale)
     r0, r1 = reads * rank // world, reads * (rank + 1) // world
-    # every rank draws from the SAME genome (seed) and its own block of reads
-    g = synth.random_genome(genome, 313, device)
-    bufs, offs, lens_all, base = [], [], [], 0
-    batch = 16384
-    for b0 in range(r0, r1, batch):
-        nb = min(batch, r1 - b0)
-        codes, lens = synth.sample_reads(g, nb, s["mean"], s["sd"], s["err"], 313 * 1000003 + b0 + 1)
-        buf, off, lens = synth.pack_reads(codes, lens)
-        del codes
-        bufs.append(buf); offs.append(off + base); lens_all.append(lens)
-        base += buf.numel()
-    del g
-    return torch.cat(bufs), torch.cat(offs), torch.cat(lens_all), s["k"], s["lower"], s["upper"], reads, r0
+    buf, off, lens = synth.make_reads_block(genome, reads, s["mean"], s["sd"], s["err"], 313, device, r0, r1)
+    return buf, off, lens, s["k"], s["lower"], s["upper"], reads, r0
+
+
+def check_digests(workload: str, scale: float, input_digest: str, digests: dict, digests_e2e: dict) -> str:
+    """The timed result against tests/golden/bench_digests.json (pinned by tests/test_gpu_fullscale.py: the CPU oracle where it
+    can run the workload, N = 1 == N = 8 everywhere).  A mismatch makes the number invalid: say so loudly."""
+    if digests != digests_e2e:
+        print("bench.py: INVALID RUN: the resident and the end-to-end passes disagree: " + json.dumps([digests, digests_e2e]), file=sys.stderr, flush=True)
+        return "MISMATCH between the resident and the end-to-end pass"
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_digests.json")) as f:
+            gold = json.load(f).get(f"{workload}@{scale:g}")
+    except Exception:
+        gold = None
+    if not gold:
+        return "no golden for this workload/scale"
+    if gold.get("input_digest") != input_digest:
+        print(f"bench.py: INVALID RUN: input digest {input_digest} != golden {gold.get('input_digest')}", file=sys.stderr, flush=True)
+        return "MISMATCH: the generated input differs from the golden input"
+    if {a: gold.get(a) for a in digests} != digests:
+        print("bench.py: INVALID RUN: result digests differ from tests/golden/bench_digests.json: " + json.dumps(digests), file=sys.stderr, flush=True)
+        return "MISMATCH: results differ from the golden digests"
+    return "match (" + gold.get("pinned_by", "golden") + ")"
 
 
 def cpu_reference_sample(name: str):
@@ -207,6 +218,16 @@ def main():
     buf, off, lens, k, lo, up, total_reads, r0 = load_workload(args.workload, rank, world, dev, args.scale)
     nreads = lens.numel()
     M = int((lens - k + 1).clamp(min=0).sum().item())
+    # what is being timed: a digest of the input that does not depend on how the reads are split over the GPUs
+    from elba_b200 import synth as _synth
+    nbytes_all = torch.tensor([buf.numel() if r == rank else 0 for r in range(world)], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(nbytes_all)
+    din = _synth.input_digest_parts(buf, lens, int(nbytes_all[:rank].sum().item()), r0)
+    din_t = torch.tensor([x - (1 << 64) if x >= (1 << 63) else x for x in din], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(din_t)            # int64 sums wrap mod 2^64
+    input_digest = "".join(f"{int(x) & 0xFFFFFFFFFFFFFFFF:016x}" for x in din_t.tolist())
     # host (pinned) copies for the end-to-end leg
     hbuf, hoff, hlen = (t.cpu().pin_memory() for t in (buf, off, lens))
     torch.cuda.synchronize()
@@ -270,8 +291,10 @@ def main():
     clocks = sampler.stop()
     sizes_local = ctx.sizes()
     sizes = ctx.sizes_global()              # whole-job totals (collective)
+    digests = ctx.digests()                 # whole-job result digests of the last timed pass (collective)
     ms_e2e, tm_e2e = timed(step_e2e, max(2, args.steps // 2), 1)
     sizes_e2e = ctx.sizes()
+    digests_e2e = ctx.digests()
     info = ctx.comm_info()
 
     # per-phase device times: the slowest rank
@@ -319,6 +342,7 @@ def main():
                        "reads": int(tot_reads), "kmer_instances": int(tot_M), "reliable_kmers": int(tot_R), "nnzA": int(tot_nnzA), "products": int(tot_F),
                        "nnzB": int(tot_nnzB), "partitions": sizes["partitions"], "grid": f"{info['grid_rows']}x{info['grid_cols']}", "l2_policy": "inputs larger than L2 / every step rewrites count tables and partition buffers",
                        "timing": "CUDA events on the launching stream around K steps, max over ranks; per-phase numbers from the library's own CUDA events on the same stream"},
+            "input_digest": input_digest, "digests": digests, "digest_check": check_digests(args.workload, args.scale, input_digest, digests, digests_e2e),
             "phases_ms": {a: round(b, 4) for a, b in tm.items() if a.endswith("_ms")},
             "roofline": roofline,
             "roofline_spgemm": {"bound": "hbm", "kernel": "k_spgemm_warp + k_spgemm_block", "achieved": ach_sp, "peak": peak, "unit": "GB/s", "frac": ach_sp / peak,

@@ -8,6 +8,7 @@
 #include "spgemm.cuh"
 #include "superkmer.cuh"
 #include "xdrop.cuh"
+#include "digest.cuh"
 #include "comm.cuh"
 #include <cub/cub.cuh>
 #include <string>
@@ -182,6 +183,13 @@ int prepare_reads(elba_fe_ctx *ctx)
 extern "C" {
 
 int elba_fe_version(void) { return ELBA_FE_VERSION; }
+
+int elba_fe_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 void elba_fe_default_config(elba_fe_config *cfg)
 {
@@ -1334,6 +1342,31 @@ int elba_fe_sizes_global(elba_fe_ctx *ctx, elba_fe_sizes_t *out)
     if (rc) return rc;
     out->nreads = v[0]; out->num_kmers = v[1]; out->distinct = v[2]; out->nnzA_pre = v[3]; out->nnzA = v[4]; out->products = v[5];
     out->nnzB_pre = v[6]; out->nnzB = v[7]; out->candidates = v[8]; out->overflow_instances = v[9];
+    return 0;
+}
+
+// ---- result digests (digest.cuh): global values, identical for any number of GPUs -------------------------------
+int elba_fe_digests(elba_fe_ctx *ctx, uint64_t out[4])
+{
+    if (!ctx || !out) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 2) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_digests: call elba_fe_count first");
+    CK(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->tmp64.ensure(8 * 64));
+    u64 *d = ctx->tmp64.as<u64>() + 8;              // [8..11]: the four sums ([0..7] is the scratch of allreduce_u64)
+    CK(cudaMemsetAsync(d, 0, 32, st));
+    const u64 R = ctx->sz.reliable;
+    // the reliable list is replicated on every GPU: one rank contributes it
+    if (R && ctx->comm.rank == 0) { k_digest_kmers<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), R, d); CKL(); LAUNCHED(ctx); }
+    if (ctx->phase >= 3 && ctx->n) { k_digest_A<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->a_rowptr.as<int64_t>(), ctx->a_col.as<u32>(), ctx->a_pos.as<u32>(), ctx->n, (u64)ctx->read_id_offset, d + 1); CKL(); LAUNCHED(ctx); }
+    if (ctx->phase >= 4 && ctx->b_rows) { k_digest_B<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->b_rowptr.as<int64_t>(), ctx->b_col.as<u32>(), ctx->b_num.as<int32_t>(), ctx->b_seeds.as<u32>(), ctx->b_rows,
+                                                (u64)ctx->op.row0, (u64)ctx->op.col0, d + 2, d + 3); CKL(); LAUNCHED(ctx); }
+    u64 h[4];
+    CK(cudaMemcpyAsync(h, d, 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int rc = allreduce_u64(ctx, h, 4, ncclSum);
+    if (rc) return rc;
+    for (int i = 0; i < 4; ++i) out[i] = h[i];
     return 0;
 }
 

@@ -63,6 +63,7 @@ ABI_SYMBOLS = (
     "elba_fe_get_B_triples", "elba_fe_device_B", "elba_fe_device_A", "elba_fe_hll", "elba_fe_bloom", "elba_fe_get_kmer_stream",
     "elba_fe_timings", "elba_fe_reset_timings", "elba_fe_align", "elba_fe_get_alignments",
     "elba_fe_comm_get_id", "elba_fe_comm_init", "elba_fe_comm_set_grid", "elba_fe_comm_info", "elba_fe_block_extent", "elba_fe_sizes_global",
+    "elba_fe_digests", "elba_fe_device_count",
 )
 
 _lib = None
@@ -176,6 +177,12 @@ class Context:
         s = Sizes()
         self._ck(self.L.elba_fe_sizes_global(self.h, C.byref(s)))
         return s.as_dict()
+
+    def digests(self) -> dict:
+        """Whole-job multiset hashes of the results (elba_fe_digests; collective on several GPUs): hex strings."""
+        d = (C.c_uint64 * 4)()
+        self._ck(self.L.elba_fe_digests(self.h, d))
+        return {n: f"{int(d[i]):016x}" for i, n in enumerate(("kmers", "A", "B", "seeds"))}
 
     # -- several GPUs (one Context per process / GPU) ---------------------------------------------
     @staticmethod

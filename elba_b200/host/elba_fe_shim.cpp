@@ -103,8 +103,16 @@ get_kmer_count_map_keys(const DnaBuffer& myreads, std::shared_ptr<CommGrid> comm
     elba_fe_default_config(&cfg);
     cfg.k = KMER_SIZE; cfg.lower = LOWER_KMER_FREQ; cfg.upper = UPPER_KMER_FREQ; cfg.stride = 1; cfg.seed_count = 2;
     if (const char *d = std::getenv("ELBA_FE_DEVICE")) cfg.device = std::atoi(d);
-    else if (const char *l = std::getenv("OMPI_COMM_WORLD_LOCAL_RANK")) cfg.device = std::atoi(l);
-    else if (const char *l2 = std::getenv("SLURM_LOCALID")) cfg.device = std::atoi(l2);
+    else
+    {
+        /* one rank drives one GPU: rank inside its node, modulo the devices the node shows (any launcher) */
+        MPI_Comm node; int local = 0;
+        MPI_Comm_split_type(comm, MPI_COMM_TYPE_SHARED, myrank, MPI_INFO_NULL, &node);
+        MPI_Comm_rank(node, &local);
+        MPI_Comm_free(&node);
+        int ndev = elba_fe_device_count();
+        cfg.device = ndev > 0 ? local % ndev : 0;
+    }
 
     FeState st; st.grid = commgrid;
     fe_check(elba_fe_create(&cfg, &st.ctx), nullptr, "elba_fe_create", comm);

@@ -109,6 +109,51 @@ def make_reads(genome_len: int, n_reads: int, mean_len: float, sd_len: float, er
     return torch.cat(bufs), torch.cat(offs), torch.cat(lens_all)
 
 
+GLOBAL_BATCH = 16384       # reads per generation batch: batch b holds the global reads [b * GLOBAL_BATCH, (b + 1) * GLOBAL_BATCH)
+
+
+def make_reads_block(genome_len: int, n_reads: int, mean_len: float, sd_len: float, err: float, seed: int, device, r0: int, r1: int):
+    """The global reads [r0, r1) of the set make_reads(genome_len, n_reads, ..., batch_reads=GLOBAL_BATCH) would produce:
+    batches are seeded by their GLOBAL first read and always generated whole, then sliced, so every read is bit-identical
+    no matter how the set is split over GPUs.  Returns (buf, byte offsets relative to the block, lens)."""
+    genome = random_genome(genome_len, seed, device)
+    bufs, offs, lens_all, base = [], [], [], 0
+    for b0 in range((r0 // GLOBAL_BATCH) * GLOBAL_BATCH, r1, GLOBAL_BATCH):
+        nb = min(GLOBAL_BATCH, n_reads - b0)
+        codes, lens = sample_reads(genome, nb, mean_len, sd_len, err, seed * 1000003 + b0 + 1)
+        buf, off, lens = pack_reads(codes, lens)
+        del codes
+        lo, hi = max(r0, b0) - b0, min(r1, b0 + nb) - b0
+        if lo > 0 or hi < nb:
+            byte_lo = int(off[lo].item())
+            byte_hi = int(off[hi].item()) if hi < nb else buf.numel()
+            buf, off, lens = buf[byte_lo:byte_hi].clone(), off[lo:hi] - byte_lo, lens[lo:hi]
+        bufs.append(buf); offs.append(off + base); lens_all.append(lens)
+        base += buf.numel()
+    del genome
+    if not bufs:
+        z = torch.zeros(0, dtype=torch.int64, device=device)
+        return torch.zeros(0, dtype=torch.uint8, device=device), z, z.clone()
+    return torch.cat(bufs), torch.cat(offs), torch.cat(lens_all)
+
+
+def input_digest_parts(buf: torch.Tensor, lens: torch.Tensor, byte_base: int, read_base: int):
+    """Two wrap-around int64 sums that identify the input independently of how it is split: every arena byte weighted by
+    a mix of its GLOBAL byte offset, every read length weighted by a mix of its GLOBAL read id.  Summed over the ranks
+    (mod 2^64) they give the same value for any number of GPUs."""
+    dev = buf.device
+    total = torch.zeros((), dtype=torch.int64, device=dev)
+    step = 1 << 25
+    for c0 in range(0, buf.numel(), step):
+        b = buf[c0:c0 + step].to(torch.int64)
+        idx = torch.arange(c0, c0 + b.numel(), device=dev, dtype=torch.int64) + byte_base
+        w = (idx * -7046029254386353131) ^ (idx >> 11)          # 0x9E3779B97F4A7C15 as int64
+        total += ((b + 1) * w).sum()
+    ids = torch.arange(lens.numel(), device=dev, dtype=torch.int64) + read_base
+    lsum = ((ids * -4417276706812531889) ^ (ids >> 7)) * (lens.to(torch.int64) + 1)
+    return int(total.item()) & 0xFFFFFFFFFFFFFFFF, int(lsum.sum().item()) & 0xFFFFFFFFFFFFFFFF
+
+
 def to_dnabuffer(buf: torch.Tensor, off: torch.Tensor, lens: torch.Tensor) -> DnaBuffer:
     return DnaBuffer(buf.cpu().numpy(), off.cpu().numpy().astype(np.uint64), lens.cpu().numpy().astype(np.uint64))
 

@@ -8,7 +8,7 @@
  *
  * The reference has no FFI layer; its interface for this path is five C++ free
  * functions (include/KmerOps.hpp:24-31, include/SharedSeeds.hpp:98-99).  The
- * C++ shim include/elba_fe_shim.hpp keeps those five signatures and implements
+ * C++ shim elba_b200/host/elba_fe_shim.cpp keeps those five signatures and implements
  * them on top of the symbols below, so src/main.cpp compiles unchanged (see
  * INTEGRATION.md).  Everything here is plain C: pointers and sizes, no C++/torch
  * types.  Every function returns 0 on success or a negative elba_fe_status;
@@ -76,6 +76,7 @@ int         elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out);
 int         elba_fe_destroy(elba_fe_ctx *ctx);
 const char *elba_fe_last_error(const elba_fe_ctx *ctx);      /* ctx may be NULL: error of the last failed create */
 int         elba_fe_version(void);
+int         elba_fe_device_count(void);                      /* usable (sm_100) CUDA devices this process sees; 0 if none */
 /* Use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own. */
 int         elba_fe_set_stream(elba_fe_ctx *ctx, void *cuda_stream);
 
@@ -145,6 +146,15 @@ typedef struct {
 int elba_fe_sizes(elba_fe_ctx *ctx, elba_fe_sizes_t *out);
 /* the same summed over the GPUs (collective); equals elba_fe_sizes on one GPU */
 int elba_fe_sizes_global(elba_fe_ctx *ctx, elba_fe_sizes_t *out);
+
+/* ---- result digests: what a run produced, without moving it to the host -------------------------------------------
+ * Order-independent 64-bit multiset hashes (sum mod 2^64 of one mix per entry, GLOBAL ids; elba_b200/csrc/digest.cuh,
+ * restated in numpy in tests/common.py): out[0] reliable k-mers + counts (the KmerCountMap of src/KmerOps.cpp:18-350),
+ * out[1] A = (read, column id, position) (src/KmerOps.cpp:361-401), out[2] B = (row, column, numshared) after Prune
+ * (src/SharedSeeds.cpp:4-10), out[3] B's retained seed positions (include/SharedSeeds.hpp:94-95).  Entries of phases
+ * not run yet are 0.  Collective over the GPUs: every rank gets the whole-job values, which do not depend on the
+ * number of GPUs or on the grid. */
+int elba_fe_digests(elba_fe_ctx *ctx, uint64_t out[4]);
 
 /* ---- results to host (caller allocates from elba_fe_sizes) ------------------------------------------- */
 /* reliable k-mers ascending by 64-bit value (== column id order) and their counts */

@@ -188,6 +188,12 @@ struct Result
 };
 
 int g_threads = 1;
+int g_stride = 1;      /* -s of the legacy command line (README.md:85): only window starts p with p % stride == 0 are visited; the reference hard-wires 1 */
+template <class F> void foreach_kmer_s(const uint8_t *mem, uint64_t len, int k, F f)
+{
+    if (g_stride <= 1) { foreach_kmer(mem, len, k, f); return; }
+    foreach_kmer(mem, len, k, [&](uint64_t x, uint64_t p) { if (p % (uint64_t)g_stride == 0) f(x, p); });
+}
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 /*
@@ -198,20 +204,31 @@ double now() { return std::chrono::duration<double>(std::chrono::steady_clock::n
  */
 void count_kmers(const Reads &rd, int k, int lower, int upper, Result &res)
 {
-    std::vector<uint64_t> all;
+    const uint64_t st = g_stride < 1 ? 1 : (uint64_t)g_stride;
     uint64_t M = 0;
-    for (uint64_t r = 0; r < rd.n; ++r) if (rd.len[r] >= (uint64_t)k) M += rd.len[r] - k + 1;
-    all.reserve(M);
-    for (uint64_t r = 0; r < rd.n; ++r)
-        foreach_kmer(rd.buf + rd.off[r], rd.len[r], k, [&](uint64_t x, uint64_t) { all.push_back(x); });
-    std::sort(all.begin(), all.end());
+    for (uint64_t r = 0; r < rd.n; ++r) if (rd.len[r] >= (uint64_t)k) M += (rd.len[r] - k + 1 + st - 1) / st;
     res.M = M; res.D = 0;
-    for (size_t i = 0; i < all.size(); )
+    /* value ranges by the top byte: sorted range after sorted range is the ascending order; ranges sort in parallel */
+    const int NRANGE = 256;
+    std::vector<std::vector<uint64_t>> part(NRANGE);
+    for (auto &v : part) v.reserve(M / NRANGE + M / (4 * NRANGE) + 16);
+    for (uint64_t r = 0; r < rd.n; ++r)
+        foreach_kmer_s(rd.buf + rd.off[r], rd.len[r], k, [&](uint64_t x, uint64_t) { part[x >> 56].push_back(x); });
+    int nt = g_threads < 1 ? 1 : g_threads;
+    auto body = [&](int t) { for (int q = t; q < NRANGE; q += nt) std::sort(part[q].begin(), part[q].end()); };
+    if (nt == 1) body(0);
+    else { std::vector<std::thread> th; for (int t = 0; t < nt; ++t) th.emplace_back(body, t); for (auto &x : th) x.join(); }
+    for (int q = 0; q < NRANGE; ++q)
     {
-        size_t j = i + 1; while (j < all.size() && all[j] == all[i]) ++j;
-        res.D++;
-        if (j - i >= (size_t)lower && j - i <= (size_t)upper) { res.rel_kmer.push_back(all[i]); res.rel_count.push_back((uint32_t)(j - i)); }
-        i = j;
+        const std::vector<uint64_t> &all = part[q];
+        for (size_t i = 0; i < all.size(); )
+        {
+            size_t j = i + 1; while (j < all.size() && all[j] == all[i]) ++j;
+            res.D++;
+            if (j - i >= (size_t)lower && j - i <= (size_t)upper) { res.rel_kmer.push_back(all[i]); res.rel_count.push_back((uint32_t)(j - i)); }
+            i = j;
+        }
+        std::vector<uint64_t>().swap(part[q]);
     }
     res.R = res.rel_kmer.size();
 }
@@ -226,17 +243,33 @@ void build_A(const Reads &rd, int k, Result &res)
     std::unordered_map<uint64_t, uint32_t> id; id.reserve(res.R * 2);
     for (uint32_t c = 0; c < res.R; ++c) id.emplace(res.rel_kmer[c], c);
     res.a_rowptr.assign(rd.n + 1, 0);
-    std::vector<std::pair<uint32_t, uint32_t>> row;
-    for (uint64_t r = 0; r < rd.n; ++r)
+    int nt = g_threads < 1 ? 1 : g_threads;
+    struct Part { std::vector<uint32_t> col, pos; uint64_t pre = 0; };
+    std::vector<Part> parts(nt);
+    std::vector<int64_t> rownnz(rd.n, 0);
+    auto body = [&](int t)
     {
-        row.clear();
-        foreach_kmer(rd.buf + rd.off[r], rd.len[r], k, [&](uint64_t x, uint64_t p) {
-            auto it = id.find(x); if (it != id.end()) row.emplace_back(it->second, (uint32_t)p); });
-        res.nnzA_pre += row.size();
-        std::sort(row.begin(), row.end());
-        for (size_t i = 0; i < row.size(); ++i)
-            if (i + 1 == row.size() || row[i + 1].first != row[i].first) { res.a_col.push_back(row[i].first); res.a_pos.push_back(row[i].second); }
-        res.a_rowptr[r + 1] = (int64_t)res.a_col.size();
+        Part &pt = parts[t];
+        std::vector<std::pair<uint32_t, uint32_t>> row;
+        for (uint64_t r = rd.n * t / nt; r < rd.n * (t + 1) / nt; ++r)
+        {
+            row.clear();
+            foreach_kmer_s(rd.buf + rd.off[r], rd.len[r], k, [&](uint64_t x, uint64_t p) {
+                auto it = id.find(x); if (it != id.end()) row.emplace_back(it->second, (uint32_t)p); });
+            pt.pre += row.size();
+            std::sort(row.begin(), row.end());
+            for (size_t i = 0; i < row.size(); ++i)
+                if (i + 1 == row.size() || row[i + 1].first != row[i].first) { pt.col.push_back(row[i].first); pt.pos.push_back(row[i].second); rownnz[r]++; }
+        }
+    };
+    if (nt == 1) body(0);
+    else { std::vector<std::thread> th; for (int t = 0; t < nt; ++t) th.emplace_back(body, t); for (auto &x : th) x.join(); }
+    for (uint64_t r = 0; r < rd.n; ++r) res.a_rowptr[r + 1] = res.a_rowptr[r] + rownnz[r];
+    for (auto &pt : parts)
+    {
+        res.nnzA_pre += pt.pre;
+        res.a_col.insert(res.a_col.end(), pt.col.begin(), pt.col.end());
+        res.a_pos.insert(res.a_pos.end(), pt.pos.begin(), pt.pos.end());
     }
     /* transpose (src/main.cpp:272-273): same entries grouped by column, rows ascending */
     res.at_colptr.assign(res.R + 1, 0);
@@ -403,6 +436,7 @@ void *eo_run(const uint8_t *buf, const uint64_t *off, const uint64_t *len, uint6
 }
 void eo_free(void *h) { delete (Result*)h; }
 void eo_set_threads(int t) { g_threads = t; }
+void eo_set_stride(int s) { g_stride = s < 1 ? 1 : s; }
 void eo_sizes(void *h, uint64_t *o /*[10]*/)
 {
     Result *r = (Result*)h;

@@ -148,10 +148,12 @@ def pass1_keys(dna, k: int, entries: int) -> int:
     return int(lib().eo_pass1_keys(_p(dna.buf), _p(dna.offsets), _p(dna.lengths), _u64(dna.size()), k, _i64(entries)))
 
 
-def run(dna, k: int, lower: int, upper: int, stop_after: int = 0, threads: int = 1) -> OracleResult:
-    """The whole hot path on the CPU.  stop_after: 0 = through B, 1 = counting only, 2 = through A."""
+def run(dna, k: int, lower: int, upper: int, stop_after: int = 0, threads: int = 1, stride: int = 1) -> OracleResult:
+    """The whole hot path on the CPU.  stop_after: 0 = through B, 1 = counting only, 2 = through A.
+    stride: the legacy -s flag (README.md:85); the reference itself hard-wires 1."""
     L = lib()
     L.eo_set_threads(int(threads))
+    L.eo_set_stride(int(stride))
     h = _vp(L.eo_run(_p(dna.buf), _p(dna.offsets), _p(dna.lengths), _u64(dna.size()), k, lower, upper, stop_after))
     try:
         sz = np.zeros(10, np.uint64)
@@ -269,6 +271,30 @@ def ref_run(dna, k: int, lower: int, upper: int, nranks: int = 1, fetch: bool = 
         return r
     finally:
         L.ref_free(h)
+
+
+def shim_path(k: int, lower: int, upper: int) -> str:
+    return os.path.join(HERE, "_ref", f"libelba_shim_k{k}_l{lower}_u{upper}.so")
+
+
+def shim_run(dna, k: int, lower: int, upper: int) -> RefResult:
+    """The reference's driver sequence (src/main.cpp:191-282, restated in ref_wrap.cpp::ref_run) over the PRODUCT's drop-in
+    shim (elba_b200/host/elba_fe_shim.cpp) and libelba_fe.so, with the reference's own headers: executes the boundary.
+    Needs a B200; the library is built where /root/reference exists (oracle/Makefile target `shim`) and travels prebuilt."""
+    key = ("shim", k, lower, upper)
+    if key not in _ref_libs:
+        L = _c.CDLL(shim_path(k, lower, upper))
+        L.ref_run.restype = _vp
+        _ref_libs[key] = L
+    saved = _ref_libs.get((k, lower, upper))
+    _ref_libs[(k, lower, upper)] = _ref_libs[key]
+    try:
+        return ref_run(dna, k, lower, upper, nranks=1)
+    finally:
+        if saved is None:
+            del _ref_libs[(k, lower, upper)]
+        else:
+            _ref_libs[(k, lower, upper)] = saved
 
 
 def ref_kmer_info(s: str, lower: int = 2, upper: int = 8):

@@ -55,9 +55,16 @@
  * per-thread; every header the file includes is already included above
  * (guards), so the macro below touches that single declaration only.
  */
+#ifdef REF_IS_SHIM
+/* the "shim" flavour (oracle/Makefile target `shim`): the same driver sequence, but the five functions come from
+ * elba_b200/host/elba_fe_shim.cpp + libelba_fe.so instead of the reference's KmerOps.cpp / SharedSeeds.cpp: this is
+ * how the drop-in boundary is EXECUTED (tests/test_gpu_shim.py), with the reference's headers and the same stubs. */
+#include REF_KMEROPS_CPP   /* = "<repo>/elba_b200/host/elba_fe_shim.cpp" */
+#else
 #define static static thread_local
 #include REF_KMEROPS_CPP   /* = "<reference>/src/KmerOps.cpp", set by oracle/Makefile */
 #undef static
+#endif
 
 namespace {
 

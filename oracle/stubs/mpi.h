@@ -109,6 +109,11 @@ inline void fold_ranks(std::vector<uint8_t>& tmp, int upto, int n, MPI_Datatype 
 static inline int MPI_Comm_rank(MPI_Comm, int *r) { *r = fake_mpi::t_rank; return 0; }
 static inline int MPI_Comm_size(MPI_Comm, int *s) { *s = fake_mpi::nranks(); return 0; }
 static inline int MPI_Barrier(MPI_Comm) { fake_mpi::barrier(); return 0; }
+#define MPI_COMM_TYPE_SHARED 1
+#define MPI_INFO_NULL 0
+/* every thread-rank lives on the one node: the node communicator is the world */
+static inline int MPI_Comm_split_type(MPI_Comm c, int, int, int, MPI_Comm *out) { *out = c; return 0; }
+static inline int MPI_Comm_free(MPI_Comm *) { return 0; }
 static inline int MPI_Abort(MPI_Comm, int code) { std::fprintf(stderr, "MPI_Abort(%d)\n", code); std::abort(); return 0; }
 /* root's buffer to every rank-thread */
 static inline int MPI_Bcast(void *buf, int n, MPI_Datatype t, int root, MPI_Comm)

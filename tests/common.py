@@ -46,3 +46,38 @@ def check_seeds_valid(dna, k, b_rowptr, b_col, b_seeds, max_checks=20000, seed=0
             if len(a) != k or len(b) != k or not (np.array_equal(a, b) or np.array_equal(a, revcomp_codes(b))):
                 bad += 1
     return bad
+
+
+# ---- the device-side result digests (elba_b200/csrc/digest.cuh) restated in numpy: sums mod 2^64 of one mix per entry ----
+_U = np.uint64
+_C1, _C2, _C3 = _U(0x9E3779B97F4A7C15), _U(0xC2B2AE3D27D4EB4F), _U(0x165667B19E3779F9)
+
+
+def _mix64(x):
+    x = x.astype(np.uint64, copy=True)
+    with np.errstate(over="ignore"):
+        x ^= x >> _U(32); x *= _U(0x9E3779B97F4A7C15); x ^= x >> _U(29); x *= _U(0xBF58476D1CE4E5B9); x ^= x >> _U(32)
+    return x
+
+
+def _hex(v):
+    return f"{int(v):016x}"
+
+
+def result_digests(kmers, counts, a_rowptr, a_col, a_pos, b_rowptr, b_col, b_num, b_seeds, row0=0, col0=0):
+    """What elba_fe_digests returns for these results (global ids: row0 / col0 are added to local ones)."""
+    with np.errstate(over="ignore"):
+        dk = _mix64(kmers.astype(np.uint64) ^ _mix64(counts.astype(np.uint64) + _C1)).sum(dtype=np.uint64)
+        rows = np.repeat(np.arange(len(a_rowptr) - 1, dtype=np.uint64), np.diff(a_rowptr)) + _U(row0)
+        da = _mix64(_mix64((rows << _U(32)) | a_col.astype(np.uint64)) ^ (a_pos.astype(np.uint64) + _C2)).sum(dtype=np.uint64)
+        rows = np.repeat(np.arange(len(b_rowptr) - 1, dtype=np.uint64), np.diff(b_rowptr)) + _U(row0)
+        cols = b_col.astype(np.uint64) + _U(col0)
+        rc = _mix64((rows << _U(32)) | cols)
+        db = _mix64(rc + b_num.astype(np.uint32).astype(np.uint64) * _C3).sum(dtype=np.uint64)
+        s = np.asarray(b_seeds).reshape(-1, 4).astype(np.uint64)
+        ds = _mix64(_mix64(rc ^ ((s[:, 0] << _U(32)) | s[:, 1])) ^ (((s[:, 2] << _U(32)) | s[:, 3]) + _C1)).sum(dtype=np.uint64)
+    return dict(kmers=_hex(dk), A=_hex(da), B=_hex(db), seeds=_hex(ds))
+
+
+def oracle_result_digests(r):
+    return result_digests(r.kmers, r.counts, r.a_rowptr, r.a_col, r.a_pos, r.b_rowptr, r.b_col, r.b_num, r.b_seeds)

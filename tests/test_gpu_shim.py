@@ -1,0 +1,54 @@
+"""The drop-in boundary EXECUTED: the reference's driver sequence (src/main.cpp:191-282: get_kmer_count_map_keys ->
+get_kmer_count_map_values -> create_kmer_matrix -> copy + Transpose -> create_seed_matrix) over the product's shim
+(elba_b200/host/elba_fe_shim.cpp) + libelba_fe.so, compiled against the reference's own headers and the runnable MPI /
+CombBLAS stand-ins of oracle/stubs (oracle/Makefile target `shim`; built where /root/reference exists, travels prebuilt).
+What comes out of the reference-side objects (KmerCountMap, SpParMat A, SpParMat B) must equal what the reference's own
+KmerOps.cpp / SharedSeeds.cpp put there (the committed digests of tests/golden/golden.json) and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from common import digest
+
+pytestmark = pytest.mark.gpu
+
+
+def _tier1(r):
+    order = np.argsort(r.kmers, kind="stable")
+    rank = np.empty(r.R, np.int64)
+    rank[order] = np.arange(r.R)
+    rows = np.repeat(np.arange(r.N), np.diff(r.a_rowptr))
+    acol = rank[r.a_col] if r.R else r.a_col
+    ka = np.lexsort((acol, rows))
+    return r.kmers[order], r.counts[order].astype(np.uint32), acol[ka].astype(np.uint32), r.a_val[ka].astype(np.uint32)
+
+
+@pytest.mark.parametrize("key", ["reads_fa_k17_l2_u8", "example_medium_k17_l2_u8", "reads_fa_k31_l2_u4", "example_medium_k31_l2_u4"])
+def test_driver_sequence_through_the_shim(fixtures, golden, key):
+    from oracle import oracle as O
+    g = golden["configs"][key]
+    if not os.path.exists(O.shim_path(g["k"], g["lower"], g["upper"])):
+        pytest.skip("oracle/_ref/libelba_shim_* not built (needs the reference headers)")
+    dna = fixtures(g["fixture"])
+    r = O.shim_run(dna, g["k"], g["lower"], g["upper"])
+    ref = O.run(dna, g["k"], g["lower"], g["upper"])
+    kmers, counts, acol, aval = _tier1(r)
+    # the KmerCountMap the driver holds (main.cpp:449-485 logs it; create_kmer_matrix receives it)
+    assert np.array_equal(kmers, ref.kmers) and np.array_equal(counts, ref.counts)
+    assert digest(kmers, counts) == g["digests"]["kmers"]
+    # READIDS / POSITIONS of every entry: the (read, position) set of the k-mer (after the max-position merge)
+    for i in range(0, r.R, 53):
+        c = int(np.searchsorted(ref.kmers, r.kmers[i]))
+        b, e = ref.at_colptr[c], ref.at_colptr[c + 1]
+        n = min(int(e - b), g["upper"])
+        assert set(zip(r.reads[i, :n].tolist(), r.pos[i, :n].tolist())) <= set(zip(ref.at_row[b:e].tolist(), ref.at_pos[b:e].tolist()))
+        assert int(r.counts[i]) == int(ref.counts[c])
+    # A as the SpParMat the reference constructor built from the shim's triples
+    assert np.array_equal(r.a_rowptr, ref.a_rowptr) and np.array_equal(acol, ref.a_col) and np.array_equal(aval, ref.a_pos)
+    assert digest(r.a_rowptr.astype(np.int64), acol, aval) == g["digests"]["A"]
+    # B as the SpParMat<SharedSeeds> handed to PairwiseAlignment
+    assert r.nnzB == g["nnzB"] and r.nnzB_pre == g["nnzB_pre"]
+    assert np.array_equal(r.b_rowptr, ref.b_rowptr) and np.array_equal(r.b_col, ref.b_col) and np.array_equal(r.b_num, ref.b_num)
+    assert digest(r.b_rowptr.astype(np.int64), r.b_col.astype(np.uint32), r.b_num.astype(np.int32)) == g["digests"]["B"]
+    assert np.array_equal(r.b_seeds, ref.b_seeds)

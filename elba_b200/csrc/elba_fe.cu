@@ -7,6 +7,7 @@
 #include "matrix_build.cuh"
 #include "spgemm.cuh"
 #include "superkmer.cuh"
+#include "skm_count.cuh"
 #include "xdrop.cuh"
 #include "digest.cuh"
 #include "comm.cuh"
@@ -45,6 +46,9 @@ struct DevBuf
 
 struct EventPair { cudaEvent_t a = nullptr, b = nullptr; };
 
+// geometry of the bucket count kernel (skm_count.cuh): 4 CTAs x 256 threads per SM, 2048-slot tables, 960-record staging buffers
+constexpr int SK4_THREADS = 256, SK4_SLOTS = 2048, SK4_RMAX = 752, SK4_POOL = 2048, SK4_MINB = 4;
+
 } // namespace
 
 struct elba_fe_ctx
@@ -63,7 +67,9 @@ struct elba_fe_ctx
     u64 ovf_cap = 0;
     DevBuf skm_slab, skm_fill, skm_ovf;      // super-k-mer path: record slabs, per-bucket fill, overflow records
     u64 skm_ovf_cap = 0;
-    bool seeds_fused = false; u64 nseeds_fused = 0;      // counting already wrote the seed list (ctx->cand) of this pass
+    bool seeds_fused = false; u64 nseeds_fused = 0;      // counting already wrote the seed list (ctx->seeds) of this pass
+    DevBuf seeds, perm, rel_idx, rel_idx_s;              // super-k-mer path: {list index, pos, read} seeds; list index -> column id; sort payload
+    u64 seed_cap = 0, seed_id_base = 0; double hist_dm = 0.0;              // seed-list capacity; distinct / instances of the last pass (sizes the buckets)
     u64 skm_reliable = 0;                                // super-k-mer path: reliable k-mers among the (holey) list entries handed out
     // several GPUs, super-k-mer path: every GPU holds all reads (all-gathered arena) and counts the buckets it owns
     DevBuf gr_packed, gr_off, gr_len64, gr_len32, gr_chunk, gr_kmer, gr_nks, all_key, all_pos;
@@ -242,10 +248,8 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaFuncSetAttribute(k_scatter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_scatter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_count_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS));
-    cudaFuncSetAttribute(k_skm_count<512, 8192, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_count_smem(8192, 512));
-    cudaFuncSetAttribute(k_skm_count<512, 8192, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_count_smem(8192, 512));
-    cudaFuncSetAttribute(k_skm_count<256, 4096, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_count_smem(4096, 256));
-    cudaFuncSetAttribute(k_skm_count<256, 4096, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skm_count_smem(4096, 256));
+    if (cudaFuncSetAttribute(k_skm_count4<SK4_THREADS, SK4_SLOTS, SK4_RMAX, SK4_POOL, SK4_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk4_smem(SK4_SLOTS, SK4_RMAX, SK4_POOL)) != cudaSuccess)
+    { elba_fe_destroy(ctx); return fail(nullptr, ELBA_FE_ERR_CUDA, "cudaFuncSetAttribute(k_skm_count4) failed"); }
     *out = ctx;
     return 0;
 }
@@ -261,7 +265,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
         &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->gr_packed, &ctx->gr_off, &ctx->gr_len64, &ctx->gr_len32, &ctx->gr_chunk, &ctx->gr_kmer, &ctx->gr_nks, &ctx->all_key, &ctx->all_pos, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
-        &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf,
+        &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf, &ctx->seeds, &ctx->perm, &ctx->rel_idx, &ctx->rel_idx_s,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
         &ctx->r_key, &ctx->r_key2, &ctx->r_pos, &ctx->r_colptr, &ctx->r_row, &ctx->r_ptr };
     for (DevBuf *b : all) b->release();
@@ -459,37 +463,37 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     const u64 Ms_own = Ms / (u64)plan.nranks + 1;           // what this GPU expects to count: decides the list capacities
     u64 *d_ctr = ctx->ctr.as<u64>(); u32 *d_err = reinterpret_cast<u32*>(d_ctr + 3);
     retry = false;
-    bool fuse = true, small = false;
-    if (const char *e = getenv("ELBA_FE_FUSE")) fuse = atoi(e) != 0;
-    if (const char *e = getenv("ELBA_FE_SKM_GEOM")) small = !std::strcmp(e, "small");      // 4 CTAs x 256 threads x 4096 slots per SM instead of 2 x 512 x 8192
-    const u32 slots = small ? 4096u : 8192u, bcap = skm_bucket_cap(slots);
-    // buckets: mean fill capacity / 2.5 (a bucket is a handful of genomic super-k-mers times the coverage: CV ~ 0.4)
-    u64 mean_inst = bcap * 2 / 5;
+    const u32 slots = SK4_SLOTS, bcap = sk4_cap(SK4_THREADS);
+    const double avg_run = 32.0 / (64.0 / (double)(Wm + 1) + 1.0);    // a chunk of 32 window starts holds 32 * 2 / (W + 1) minimizer runs plus the one its start cuts
+    // mean bucket: a third of the table in DISTINCT k-mers (distinct / instances of the last pass, else a guess), records well inside the staging
+    // buffer, instances within 2 / 5 of the capacity (a bucket is a handful of genomic super-k-mers times the coverage: CV ~ 0.4)
+    const double dm = ctx->hist_dm > 0.0 ? std::min(1.0, std::max(0.05, ctx->hist_dm)) : 0.3;
+    u64 mean_inst = (u64)std::min({ (double)bcap * 0.4, 0.36 * (double)slots / dm, (double)SK4_RMAX / 2.2 * avg_run });
+    mean_inst = std::max<u64>(mean_inst, 64);
     if (const char *e = getenv("ELBA_FE_SKM_MEAN")) { long v = atol(e); if (v >= 64 && v <= (long)bcap) mean_inst = (u64)v; }
     u64 NBg = std::max<u64>(1, (Ms + mean_inst - 1) / mean_inst);
     if (ctx->cfg.num_partitions > 1) NBg = std::max<u64>(NBg, (u64)ctx->cfg.num_partitions);
     const u64 NB = (NBg + plan.nranks - 1) / plan.nranks;   // buckets of this GPU: [rank * NB, (rank + 1) * NB) of NBg
     NBg = NB * (u64)plan.nranks;
     if (NBg >= (1ull << 31)) return fail(ctx, ELBA_FE_ERR_INVALID, "too many minimizer buckets for one context");
-    // records per bucket: a chunk of 32 window starts holds 32 * 2 / (W + 1) minimizer runs plus the one its start cuts
-    const double avg_run = 32.0 / (64.0 / (double)(Wm + 1) + 1.0);
     double slack = 2.5;
     if (const char *e = getenv("ELBA_FE_SKM_SLACK")) { double v = atof(e); if (v >= 1.0 && v <= 16.0) slack = v; }
     u64 rcap = (u64)((double)Ms / (double)NBg / avg_run * slack) + 32;
-    rcap = std::min<u64>(rcap, SC_MAXREC);
+    rcap = std::min<u64>(rcap, SK4_RMAX);
     ctx->sz.partitions = NBg; ctx->sz.table_slots = slots;
     const u64 ovf_cap = std::max<u64>(ctx->skm_ovf_cap, std::max<u64>(Ms_own / 64, 1u << 16));
     CK(ctx->skm_slab.ensure(sizeof(SkmRec) * NB * rcap)); CK(ctx->skm_fill.ensure(sizeof(u64) * NB));
     CK(ctx->skm_ovf.ensure(sizeof(SkmRec) * ovf_cap));
     ctx->skm_ovf_cap = ovf_cap;
-    // seed list: {k-mer, pos, read} of every instance of a reliable k-mer; the size of the last pass, else a guess
-    const u64 gc_max = (u64)grid_for(ctx, 4);                         // CTAs of k_skm_count: each may leave one chunk partly used
-    u64 seed_guess = Ms_own / 16 + (1u << 20) + gc_max * SEED_CHUNK;
+    // seed list: {list index, pos, read} of every instance of a reliable k-mer; the size of the last pass, else a guess
+    const u64 gc_max = (u64)grid_for(ctx, SK4_MINB);                  // CTAs of the count kernel: each may leave one chunk partly used
+    u64 seed_guess = Ms_own / 16 + (1u << 20) + gc_max * SK4_CHUNK;
     if (const char *e = getenv("ELBA_FE_SEED_CAP")) { long long v = atoll(e); if (v >= 1) seed_guess = (u64)v; }      // tests: force the resize
-    const u64 seed_cap = fuse ? std::max<u64>(ctx->cand_cap, seed_guess) : std::max<u64>(ctx->cand_cap, 1);
-    CK(ctx->cand.ensure(sizeof(Candidate) * seed_cap));
-    ctx->cand_cap = seed_cap;
-    SeedSink seeds; seeds.out = ctx->cand.as<Candidate>(); seeds.cursor = d_ctr + 7; seeds.cap = seed_cap;
+    const u64 seed_cap = std::max<u64>(ctx->seed_cap, seed_guess);
+    CK(ctx->seeds.ensure(sizeof(Seed) * seed_cap));
+    ctx->seed_cap = seed_cap;
+    if (rel_cap >= 0xFFFFFFF0ull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 entries in the reliable list of one context");
+    SeedSink2 seeds; seeds.out = ctx->seeds.as<Seed>(); seeds.cursor = d_ctr + 7; seeds.cap = seed_cap;
     CK(cudaMemsetAsync(ctx->skm_fill.p, 0, sizeof(u64) * NB, st));
     RecSink sink; sink.slab = ctx->skm_slab.as<SkmRec>(); sink.fill = ctx->skm_fill.as<u64>(); sink.rcap = (u32)rcap; sink.NB = (u32)NBg;
     sink.b_lo = (u32)(NB * (u64)plan.rank); sink.b_cnt = (u32)NB; sink.read_base = plan.read_base;
@@ -523,62 +527,46 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
     CK(cudaEventRecord(ep.a, st));
     {
-        u64 *oh = ctx->rel_key.as<u64>(); u32 *oc = ctx->rel_cnt.as<u32>();
-        if (small)
-        {
-            const u32 gc = (u32)std::min<u64>(NB, (u64)grid_for(ctx, 4));
-            const size_t sm = skm_count_smem(4096, 256);
-            if (fuse) k_skm_count<256, 4096, 4, true><<<gc, 256, sm, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
-            else      k_skm_count<256, 4096, 4, false><<<gc, 256, sm, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
-        }
-        else
-        {
-            const u32 gc = (u32)std::min<u64>(NB, (u64)grid_for(ctx, 2));
-            const size_t sm = skm_count_smem(8192, 512);
-            if (fuse) k_skm_count<512, 8192, 2, true><<<gc, 512, sm, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
-            else      k_skm_count<512, 8192, 2, false><<<gc, 512, sm, st>>>(in, (u32)NB, k, ovf, lower, upper, oh, oc, d_ctr, rel_cap, seeds);
-        }
+        const u32 gc = (u32)std::min<u64>(NB, gc_max);
+        k_skm_count4<SK4_THREADS, SK4_SLOTS, SK4_RMAX, SK4_POOL, SK4_MINB><<<gc, SK4_THREADS, sk4_smem(SK4_SLOTS, SK4_RMAX, SK4_POOL), st>>>(in, (u32)NB, k, ovf, lower, upper,
+            ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap, seeds);
     }
     CKL(); LAUNCHED(ctx);
     CK(cudaEventRecord(ep.b, st));
-    u64 o[2] = {0, 0}, slots_before = 0;
+    u64 o[2] = {0, 0};
     CK(cudaMemcpyAsync(o, d_ctr + 5, 16, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&slots_before, d_ctr, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const u64 novf = o[0], ninst = o[1];
     if (novf > ovf_cap) { ctx->skm_ovf_cap = novf + (novf >> 3); retry = true; return 0; }
     ctx->sz.slow_partitions = 0; ctx->sz.overflow_instances = ninst;
     if (novf)
     {
-        const u64 slots = std::max<u64>(2 * ninst + 64, 1024);
-        if (slots >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "the overflow of the minimizer buckets needs a count table of more than 2^32 slots");
-        CK(ctx->table.ensure(sizeof(Slot) * slots));
-        k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), slots, EMPTY_H); CKL(); LAUNCHED(ctx);
-        TableRef T{ctx->table.as<Slot>(), (u32)slots};
-        k_skm_count_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->skm_ovf.as<SkmRec>(), novf, k, T, d_err, d_ctr + 2); CKL(); LAUNCHED(ctx);
-        if (fuse) { k_skm_emit_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->skm_ovf.as<SkmRec>(), novf, k, T, lower, upper, seeds); CKL(); LAUNCHED(ctx); }
-        k_table_collect<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap);
-        CKL(); LAUNCHED(ctx);
+        // buckets that overflowed their record capacity, 6144 instances or 3/4 of the table: exact count in one global table
+        const u64 gslots = std::max<u64>(2 * ninst + 64, 1024);
+        if (gslots >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "the overflow of the minimizer buckets needs a count table of more than 2^32 slots");
+        CK(ctx->table.ensure(sizeof(Slot) * gslots));
+        k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), gslots, EMPTY_KEY); CKL(); LAUNCHED(ctx);
+        TableRef T{ctx->table.as<Slot>(), (u32)gslots};
+        k_skm4_count_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->skm_ovf.as<SkmRec>(), d_ctr + 5, ovf_cap, k, T, d_err, d_ctr + 2); CKL(); LAUNCHED(ctx);
+        k_skm4_collect_global<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap); CKL(); LAUNCHED(ctx);
+        k_skm4_emit_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->skm_ovf.as<SkmRec>(), d_ctr + 5, ovf_cap, k, T, lower, upper, seeds); CKL(); LAUNCHED(ctx);
     }
     ctx->seeds_fused = false;
     {
-        // [0] list entries handed out (chunks with holes + what the fallback appended), [1] sum of reliable counts,
-        // [2] seed entries handed out, [3] reliable k-mers the bucket kernel found
-        u64 h[4] = {0, 0, 0, 0};
-        CK(cudaMemcpyAsync(&h[0], d_ctr, 16, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&h[2], d_ctr + 7, 16, cudaMemcpyDeviceToHost, st));
+        // [0] list entries handed out (chunks with holes + what the fallback appended), [1] sum of reliable counts, [2] distinct,
+        // [7] seed entries handed out, [8] reliable k-mers
+        u64 h[9];
+        CK(cudaMemcpyAsync(h, d_ctr, sizeof h, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        ctx->skm_reliable = h[3] + (h[0] - slots_before);
-        if (fuse)
+        ctx->skm_reliable = h[8];
+        if (h[7] > seed_cap) { ctx->seed_cap = h[7] + (h[7] >> 4) + 1024; retry = true; return 0; }
+        if (h[0] <= rel_cap && h[7] < h[1])
         {
-            if (h[2] > seed_cap) { ctx->cand_cap = h[2] + (h[2] >> 4) + 1024; retry = true; return 0; }
-            if (h[2] < h[1])
-            {
-                char b[160]; snprintf(b, sizeof b, "fused seed emission handed out %llu entries, the counts promise %llu", (unsigned long long)h[2], (unsigned long long)h[1]);
-                return fail(ctx, ELBA_FE_ERR_CUDA, b);
-            }
-            ctx->seeds_fused = true; ctx->nseeds_fused = h[2];
+            char b[160]; snprintf(b, sizeof b, "fused seed emission handed out %llu entries, the counts promise %llu", (unsigned long long)h[7], (unsigned long long)h[1]);
+            return fail(ctx, ELBA_FE_ERR_CUDA, b);
         }
+        ctx->seeds_fused = true; ctx->nseeds_fused = h[7];
+        if (Ms) ctx->hist_dm = (double)h[2] / (double)Ms_own;
     }
     return 0;
 }
@@ -866,7 +854,6 @@ int elba_fe_count(elba_fe_ctx *ctx)
         if (attempt == 3) return fail(ctx, ELBA_FE_ERR_CUDA, "reliable list overflow after resize");
         rel_cap = std::max(rel_cap, R);       // exact; redo the count
     }
-    (void)me;
     ctx->sz.distinct = D; ctx->sz.nnzA_pre = sumcnt;
     // super-k-mer path: the list has holes (h = EMPTY_H -> k-mer = all ones, sorted behind every k-mer); R_list entries, R k-mers
     u64 R_list = R;
@@ -884,14 +871,31 @@ int elba_fe_count(elba_fe_ctx *ctx)
         if ((rc0 = allgatherv(ctx, ctx->rel_key.p, ctx->rel_all_key.p, Rr, sizeof(u64)))) return rc0;
         if ((rc0 = allgatherv(ctx, ctx->rel_cnt.p, ctx->rel_all_cnt.p, Rr, sizeof(u32)))) return rc0;
         rk = ctx->rel_all_key.as<u64>(); rc_ = ctx->rel_all_cnt.as<u32>(); R_list = Rt;
+        ctx->seed_id_base = 0; for (int r = 0; r < me; ++r) ctx->seed_id_base += Rr[r];      // my list inside the concatenation
     }
+    else ctx->seed_id_base = 0;
     if (R >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers on one context");
     ctx->sz.reliable = R;
 
+    CK(ctx->rel_key_s.ensure(sizeof(u64) * std::max<u64>(R_list, 1))); CK(ctx->rel_cnt_s.ensure(sizeof(u32) * std::max<u64>(R_list, 1)));
+    int rc;
+    if (ctx->seeds_fused)
+    {
+        // super-k-mer path: the list holds the k-mers themselves (holes = all ones, sorted behind every k-mer) and the seeds name
+        // their k-mer by its list index: column id = rank by value = where the sort puts the entry; perm[list index] = column id.
+        // No k-mer -> column hash table is built (round 1: 34 M random CAS into an 826 MB table per pass).
+        if (R_list >= 0xFFFFFFF0ull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 entries in the reliable lists");
+        CK(ctx->rel_idx.ensure(4 * std::max<u64>(R_list, 1))); CK(ctx->rel_idx_s.ensure(4 * std::max<u64>(R_list, 1))); CK(ctx->perm.ensure(4 * std::max<u64>(R_list, 1)));
+        if (R_list) { k_iota_u32<<<nblk(R_list, 256), 256, 0, st>>>(ctx->rel_idx.as<u32>(), R_list); CKL(); LAUNCHED(ctx); }
+        rc = sort_pairs(ctx, rk, ctx->rel_key_s.as<u64>(), ctx->rel_idx.as<u32>(), ctx->rel_idx_s.as<u32>(), R_list, 64 - 2 * k, 64);
+        if (rc) return rc;
+        if (R) { k_rank_finish<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_idx_s.as<u32>(), rc_, R, ctx->perm.as<u32>(), ctx->rel_cnt_s.as<u32>()); CKL(); LAUNCHED(ctx); }
+    }
+    else
+    {
     // the lists hold h = mix64(k-mer): back to k-mers, then column ids = rank by k-mer value: sort (key, count) by key
     if (R_list) { k_unmix<<<nblk(R_list, 256), 256, 0, st>>>(rk, R_list); CKL(); LAUNCHED(ctx); }
-    CK(ctx->rel_key_s.ensure(sizeof(u64) * std::max<u64>(R_list, 1))); CK(ctx->rel_cnt_s.ensure(sizeof(u32) * std::max<u64>(R_list, 1)));
-    int rc = sort_pairs(ctx, rk, ctx->rel_key_s.as<u64>(), rc_, ctx->rel_cnt_s.as<u32>(), R_list, 64 - 2 * k, 64);    // the first R of R_list are k-mers
+    rc = sort_pairs(ctx, rk, ctx->rel_key_s.as<u64>(), rc_, ctx->rel_cnt_s.as<u32>(), R_list, 64 - 2 * k, 64);    // the first R of R_list are k-mers
     if (rc) return rc;
     // k-mer -> column id table in HBM, fronted by a blocked Bloom filter sized to stay L2-resident
     u64 lslots = std::max<u64>(R + R / 2 + 64, 1024);
@@ -902,11 +906,11 @@ int elba_fe_count(elba_fe_ctx *ctx)
     u64 fwords = std::max<u64>((R * bits_per_key + 63) / 64, 1024);
     CK(ctx->filter.ensure(8 * fwords));
     ctx->filter_words = (u32)fwords;
-    const bool need_filter = !ctx->seeds_fused;          // the filter fronts sweep 2, which the fused seed list replaces
-    if (need_filter) CK(cudaMemsetAsync(ctx->filter.p, 0, 8 * fwords, st));
+    CK(cudaMemsetAsync(ctx->filter.p, 0, 8 * fwords, st));
     k_table_clear<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->lut.as<Slot>(), lslots, EMPTY_KEY); CKL(); LAUNCHED(ctx);
     if (R) { k_lookup_build<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), (u32)R, ctx->lut.as<Slot>(), ctx->lut_slots,
-                                                       need_filter ? ctx->filter.as<u64>() : nullptr, ctx->filter_words); CKL(); LAUNCHED(ctx); }
+                                                       ctx->filter.as<u64>(), ctx->filter_words); CKL(); LAUNCHED(ctx); }
+    }
     CK(cudaEventRecord(ctx->ev[3], st));
     ctx->phase = 2;
     return 0;
@@ -994,20 +998,27 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     // one GPU: counting already told how many instances belong to reliable k-mers.  Several GPUs: that number is
     // known per OWNER, not per reader, so the triple buffers are sized by the candidate count.
     u64 cap = std::max<u64>(npre, 1);
-    const bool global = ctx->seeds_fused && ctx->seeds_global;        // several GPUs, super-k-mer path: the seeds carry GLOBAL read ids
-    if (W == 1 || ctx->seeds_fused) { CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); }
+    const bool fused = ctx->seeds_fused;
+    const bool global = fused && ctx->seeds_global;        // several GPUs, super-k-mer path: the seeds carry GLOBAL read ids
+    const int gb = 32 + bits_for(std::max<u64>((u64)ctx->gr_read0 + ctx->N_total, 2));      // key bits of (global read << 32 | column)
+    u64 nsort = 0;                                         // entries handed to the (read, column) sort; fused: the seed list with its holes
+    if (fused) cap = std::max<u64>(ctx->nseeds_fused, 1);
+    if (W == 1 || fused) { CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); }
     // sweep 2: every instance of a reliable k-mer -> (read, column, pos)
     u64 emitted = 0;
     {
         EventPair &lp = next_pair(ctx->lev, ctx->lev_used);
         CK(cudaEventRecord(lp.a, st));
-        if (ctx->seeds_fused)
+        if (fused)
         {
-            // counting already listed every instance of a reliable k-mer (superkmer.cuh): only the column ids are missing
+            // counting already listed every instance of a reliable k-mer as {list index, pos, read} (skm_count.cuh): the column id
+            // is perm[list index]; holes keep a key that sorts behind every entry
             const u64 ncand = ctx->nseeds_fused;
             ctx->sz.candidates = ncand;
-            if (ncand) { k_resolve<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->cand.as<Candidate>(), ncand, ctx->lut.as<Slot>(), ctx->lut_slots,
-                             ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr, cap, global ? 32 : cb); CKL(); LAUNCHED(ctx); }
+            nsort = ncand;
+            const u64 hole_key = 1ull << (global ? gb : cb + rb);
+            if (ncand) { k_seed_keys<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->seeds.as<Seed>(), ncand, ctx->perm.as<u32>(), (u32)ctx->seed_id_base, global ? 32 : cb, hole_key,
+                             ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr); CKL(); LAUNCHED(ctx); }
         }
         else if (ctx->nchunks && R)
         {
@@ -1043,8 +1054,10 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
         if (W > 1) { int rc0 = allreduce_u64(ctx, chk, 2, ncclSum); if (rc0) return rc0; }
         if (chk[0] != chk[1]) { char b[160]; snprintf(b, sizeof b, "seed emission produced %llu triples, counting promised %llu", (unsigned long long)chk[0], (unsigned long long)chk[1]); return fail(ctx, ELBA_FE_ERR_CUDA, b); }
         npre = emitted;
-        CK(ctx->seed_key.ensure(8 * std::max<u64>(npre, 1))); CK(ctx->seed_pos.ensure(4 * std::max<u64>(npre, 1)));
-        CK(ctx->seed_key2.ensure(8 * std::max<u64>(npre, 1))); CK(ctx->seed_pos2.ensure(4 * std::max<u64>(npre, 1)));
+        if (!fused) nsort = npre;
+        const u64 ns1 = std::max<u64>(nsort, 1);
+        CK(ctx->seed_key.ensure(8 * ns1)); CK(ctx->seed_pos.ensure(4 * ns1));
+        CK(ctx->seed_key2.ensure(8 * ns1)); CK(ctx->seed_pos2.ensure(4 * ns1));
     }
 
     int rc;
@@ -1055,15 +1068,15 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
         // dimension), so the triples are all-gathered (12 B each), sorted and deduplicated once, and every GPU slices the
         // rows of its own reads out of the result: this replaces "send seeds to the read's GPU + build + all-gather A".
         std::vector<u64> ne;
-        if ((rc = allgather_u64(ctx, npre, ne))) return rc;
-        u64 tpre = 0; for (u64 v : ne) tpre += v;
-        const u64 tp1 = std::max<u64>(tpre, 1);
+        if ((rc = allgather_u64(ctx, nsort, ne))) return rc;
+        u64 tsort = 0; for (u64 v : ne) tsort += v;
+        u64 tpre = npre; if ((rc = allreduce_u64(ctx, &tpre, 1, ncclSum))) return rc;        // valid triples; the holes sort behind them
+        const u64 tp1 = std::max<u64>(tsort, 1);
         CK(ctx->all_key.ensure(8 * tp1)); CK(ctx->all_pos.ensure(4 * tp1)); CK(ctx->seed_key2.ensure(8 * tp1)); CK(ctx->seed_pos2.ensure(4 * tp1));
         if ((rc = allgatherv(ctx, ctx->seed_key.p, ctx->all_key.p, ne, 8))) return rc;
         if ((rc = allgatherv(ctx, ctx->seed_pos.p, ctx->all_pos.p, ne, 4))) return rc;
-        ctx->panel_bytes = 12 * (tpre - npre);
-        const int gb = 32 + bits_for(std::max<u64>((u64)ctx->gr_read0 + ctx->N_total, 2));
-        if ((rc = sort_pairs(ctx, ctx->all_key.as<u64>(), ctx->seed_key2.as<u64>(), ctx->all_pos.as<u32>(), ctx->seed_pos2.as<u32>(), tpre, 0, gb))) return rc;
+        ctx->panel_bytes = 12 * (tsort - nsort);
+        if ((rc = sort_pairs(ctx, ctx->all_key.as<u64>(), ctx->seed_key2.as<u64>(), ctx->all_pos.as<u32>(), ctx->seed_pos2.as<u32>(), tsort, 0, gb + 1))) return rc;
         CK(ctx->idx.ensure(8 * (tpre + 1)));
         k_mark_run_ends<<<nblk(tpre + 1, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), tpre, ctx->idx.as<u64>()); CKL(); LAUNCHED(ctx);
         if ((rc = exclusive_scan_inplace(ctx, ctx->idx.as<u64>(), tpre + 1))) return rc;
@@ -1095,7 +1108,7 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     else
     {
     // sort by (read, column); merge duplicates keeping the largest position
-    if ((rc = sort_pairs(ctx, ctx->seed_key.as<u64>(), ctx->seed_key2.as<u64>(), ctx->seed_pos.as<u32>(), ctx->seed_pos2.as<u32>(), npre, 0, cb + rb))) return rc;
+    if ((rc = sort_pairs(ctx, ctx->seed_key.as<u64>(), ctx->seed_key2.as<u64>(), ctx->seed_pos.as<u32>(), ctx->seed_pos2.as<u32>(), nsort, 0, cb + rb + (fused ? 1 : 0)))) return rc;      // the first npre are triples, holes behind
     CK(ctx->idx.ensure(8 * (npre + 1)));
     k_mark_run_ends<<<nblk(npre + 1, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), npre, ctx->idx.as<u64>()); CKL(); LAUNCHED(ctx);
     if ((rc = exclusive_scan_inplace(ctx, ctx->idx.as<u64>(), npre + 1))) return rc;

@@ -41,7 +41,7 @@ def test_every_minimizer_geometry(hifi, k):
     ref = O.run(hifi, k, 2, 6)
     out = _run_cuda(hifi, k, 2, 6)
     _compare(out, ref, f"skm k={k}")
-    assert out["sizes"]["table_slots"] == 8192 and out["sizes"]["partitions"] > 100      # the bucket path ran
+    assert out["sizes"]["table_slots"] == 2048 and out["sizes"]["partitions"] > 100      # the bucket path ran
 
 
 def test_hash_path_forced_gives_the_same_bits(hifi):
@@ -106,27 +106,31 @@ def test_ragged_reads_k31():
         _compare(out, ref, f"ragged k={k}")
 
 
-def test_fused_seed_list_variants(hifi):
-    """Pass 2 fused into counting (the default), the separate second sweep (ELBA_FE_FUSE=0) and the small bucket geometry
-    (4096-slot tables, 256 threads) must give the same bits; with the fused list build_A sees exactly nnzA_pre candidates (no filter false positives)."""
+def test_fused_seed_list(hifi):
+    """Pass 2 is fused into counting: build_A sees exactly nnzA_pre seeds plus the holes of the chunked list (no filter, no false positives)."""
     from oracle import oracle as O
     ref = O.run(hifi, 31, 2, 4)
     out = _run_cuda(hifi, 31, 2, 4)
     _compare(out, ref, "fused")
-    assert ref.nnzA_pre <= out["sizes"]["candidates"] <= ref.nnzA_pre + 296 * 16384      # chunked list: holes, no false positives
-    with _env(ELBA_FE_FUSE="0"):
-        out = _run_cuda(hifi, 31, 2, 4)
-    _compare(out, ref, "second sweep")
-    assert out["sizes"]["candidates"] >= ref.nnzA_pre
-    for fuse in ("1", "0"):
-        with _env(ELBA_FE_SKM_GEOM="small", ELBA_FE_FUSE=fuse):
-            out = _run_cuda(hifi, 27, 2, 6)
-        _compare(out, O.run(hifi, 27, 2, 6), f"4096-slot tables, 256 threads, fuse={fuse}")
-        assert out["sizes"]["table_slots"] == 4096
-    with _env(ELBA_FE_SKM_GEOM="small", ELBA_FE_SKM_MEAN="3072", ELBA_FE_SKM_SLACK="4.0"):
-        out = _run_cuda(hifi, 31, 2, 4)
-    _compare(out, ref, "4096-slot tables, instance overflow")
-    assert out["sizes"]["overflow_instances"] > 100_000
+    assert ref.nnzA_pre <= out["sizes"]["candidates"] <= ref.nnzA_pre + 592 * 16384
+
+
+def test_table_too_full_spills_the_bucket():
+    """Noisy reads (15 % errors): nearly every k-mer instance is distinct, so buckets sized for HiFi data hold more distinct
+    k-mers than 3/4 of the 2048-slot table: the kernel notices while inserting and hands those buckets, whole, to the exact
+    global-table fallback.  Nothing may change."""
+    from elba_b200.synth import make_dnabuffer
+    from oracle import oracle as O
+    dna = make_dnabuffer(genome_len=150_000, n_reads=250, mean_len=9000, sd_len=1000, err=0.15, seed=23)
+    for k, mean in ((31, 3500), (25, 2400), (21, 6000)):
+        ref = O.run(dna, k, 2, 8)
+        assert ref.D > 0.8 * ref.M
+        with _env(ELBA_FE_SKM_MEAN=mean, ELBA_FE_SKM_SLACK="4.0"):
+            out = _run_cuda(dna, k, 2, 8)
+        _compare(out, ref, f"full tables k={k}")
+        assert out["sizes"]["overflow_instances"] > 200_000
+    # with the default geometry (sized for a distinct ratio of 0.3 on the first pass) the result is the same
+    _compare(_run_cuda(dna, 31, 2, 8), O.run(dna, 31, 2, 8), "noisy reads, default geometry")
 
 
 def test_fused_seed_list_resize_and_overflow_buckets(hifi):

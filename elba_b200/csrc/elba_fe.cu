@@ -46,6 +46,10 @@ struct DevBuf
 
 struct EventPair { cudaEvent_t a = nullptr, b = nullptr; };
 
+// A device buffer other GPUs of the job write into: peer[r] is rank r's buffer mapped into this process (CUDA IPC),
+// peer[me] the local one.  With one rank it is a plain buffer.
+struct Window { DevBuf buf; void *peer[elba::SK_MAXW] = {}; bool mapped = false; };
+
 // geometry of the bucket count kernel (skm_count.cuh): 4 CTAs x 256 threads per SM, 2048-slot tables, 960-record staging buffers
 constexpr int SK4_THREADS = 256, SK4_SLOTS = 2048, SK4_RMAX = 752, SK4_POOL = 2048, SK4_MINB = 4;
 
@@ -71,9 +75,13 @@ struct elba_fe_ctx
     DevBuf seeds, perm, rel_idx, rel_idx_s;              // super-k-mer path: {list index, pos, read} seeds; list index -> column id; sort payload
     u64 seed_cap = 0, seed_id_base = 0; double hist_dm = 0.0;              // seed-list capacity; distinct / instances of the last pass (sizes the buckets)
     u64 skm_reliable = 0;                                // super-k-mer path: reliable k-mers among the (holey) list entries handed out
-    // several GPUs, super-k-mer path: every GPU holds all reads (all-gathered arena) and counts the buckets it owns
-    DevBuf gr_packed, gr_off, gr_len64, gr_len32, gr_chunk, gr_kmer, gr_nks, all_key, all_pos;
-    u64 gr_n = 0, gr_nchunks = 0, gr_M = 0; int64_t gr_read0 = 0; bool seeds_global = false;
+    // several GPUs, super-k-mer path: every GPU parses its own reads and writes the records into the owners' slabs (peer memory)
+    Window w_slab, w_ovf, w_octr, w_rkey, w_rpos, w_rcnt;     // record slabs, overflow list + its counters, routed seed triples + their counts
+    DevBuf skm_fillin, skm_plan, d_roff, route_cur, rel_gid, glob_key, glob_cnt, glob_gid, glob_cnt_in;
+    std::vector<u64> roff;                                   // [W + 1] first global read id of every rank's block
+    int64_t read_base0 = 0;                                  // global id of the first read of rank 0
+    bool p2p = false, kmers_distributed = false; u64 R_local = 0; std::vector<u64> rel_counts;
+    u64 Ms_total = 0, route_cap = 0;
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_x0 = nullptr, ev_x1 = nullptr;
     u64 exchange_bytes = 0, panel_bytes = 0;
     u64 scratch_mb = 64;
@@ -103,6 +111,8 @@ struct elba_fe_ctx
     std::vector<EventPair> pev; size_t pev_used = 0;      // partition kernels
     std::vector<EventPair> lev; size_t lev_used = 0;      // lookup kernel
 };
+
+extern "C" { static void window_release(elba_fe_ctx *ctx, Window &w); }
 
 namespace {
 
@@ -241,6 +251,7 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreate(&ctx->ev_x0); cudaEventCreate(&ctx->ev_x1); cudaEventCreate(&ctx->xd_e0); cudaEventCreate(&ctx->xd_e1);
+    if (ctx->tmp64.ensure(8192) != cudaSuccess || ctx->ctr.ensure(128) != cudaSuccess) { elba_fe_destroy(ctx); return fail(nullptr, ELBA_FE_ERR_OOM, "cudaMalloc failed"); }
     if (const char *e = getenv("ELBA_FE_SCRATCH_MB")) { long v = atol(e); if (v >= 8 && v <= 65536) ctx->scratch_mb = (u64)v; }
     // opt in to large dynamic shared memory
     cudaFuncSetAttribute(k_scatter1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S1_TILE + 2 * sizeof(u32) * MAX_P1));
@@ -263,11 +274,12 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut, &ctx->filter,
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
-        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->gr_packed, &ctx->gr_off, &ctx->gr_len64, &ctx->gr_len32, &ctx->gr_chunk, &ctx->gr_kmer, &ctx->gr_nks, &ctx->all_key, &ctx->all_pos, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
+        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->skm_fillin, &ctx->skm_plan, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf, &ctx->seeds, &ctx->perm, &ctx->rel_idx, &ctx->rel_idx_s,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
         &ctx->r_key, &ctx->r_key2, &ctx->r_pos, &ctx->r_colptr, &ctx->r_row, &ctx->r_ptr };
+    for (Window *w : { &ctx->w_slab, &ctx->w_ovf, &ctx->w_octr, &ctx->w_rkey, &ctx->w_rpos, &ctx->w_rcnt }) window_release(ctx, *w);
     for (DevBuf *b : all) b->release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     for (auto *v : { &ctx->kev, &ctx->sev, &ctx->pev, &ctx->lev }) for (auto &p : *v) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -403,55 +415,106 @@ static int count_with_global_table(elba_fe_ctx *ctx, const std::vector<std::pair
 // What the super-k-mer path counts: one GPU: its own reads, all buckets.  Several GPUs: ALL reads, the buckets of this rank.
 struct SkmPlan { ReadsView rv; u64 Ms; u32 read_base; int nranks, rank; };
 
-static __global__ void k_add_u64(u64 *__restrict__ v, u64 n, u64 add)
+// ---- peer-memory windows -----------------------------------------------------------------------------------
+static void window_unmap(elba_fe_ctx *ctx, Window &w)
 {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] += add;
+    if (!w.mapped) return;
+    for (int r = 0; r < ctx->comm.nranks && r < SK_MAXW; ++r) if (r != ctx->comm.rank && w.peer[r]) cudaIpcCloseMemHandle(w.peer[r]);
+    for (auto &p : w.peer) p = nullptr;
+    w.mapped = false;
 }
+static void window_release(elba_fe_ctx *ctx, Window &w) { window_unmap(ctx, w); w.buf.release(); }
 
-// Several GPUs: all-gather the 2-bit arenas (0.25 B per base) and the read tables; the ranks hold consecutive blocks of reads,
-// so the gathered index of a read is its global id minus the first rank's offset.  ok = false: the blocks are not consecutive.
-static int gather_reads(elba_fe_ctx *ctx, SkmPlan &plan, bool &ok)
+// COLLECTIVE over the ranks when there are several (every rank calls it with the same `bytes`): (re)allocates the buffer if
+// it is too small and maps every rank's buffer into every process.  The handles travel over NCCL.
+static int window_ensure(elba_fe_ctx *ctx, Window &w, size_t bytes)
 {
-    cudaStream_t st = ctx->stream;
-    const int W = ctx->comm.nranks;
-    std::vector<u64> nr, nb, ro;
-    int rc;
-    if ((rc = allgather_u64(ctx, ctx->n, nr))) return rc;
-    if ((rc = allgather_u64(ctx, ctx->packed_bytes, nb))) return rc;
-    if ((rc = allgather_u64(ctx, (u64)ctx->read_id_offset, ro))) return rc;
-    u64 Nt = 0, Bt = 0; ok = true;
-    for (int r = 0; r < W; ++r) { if (ro[r] != ro[0] + Nt) ok = false; Nt += nr[r]; Bt += nb[r]; }
-    if (ro[0] + Nt >= 0xFFFFFFF0ull) ok = false;             // global read ids travel as 32 bits in the records
-    if (!ok) return 0;
-    CK(ctx->gr_packed.ensure(Bt + 64)); CK(ctx->gr_off.ensure(8 * (Nt + 1))); CK(ctx->gr_len64.ensure(8 * (Nt + 1)));
-    CK(ctx->gr_len32.ensure(4 * (Nt + 1))); CK(ctx->gr_chunk.ensure(8 * (Nt + 1))); CK(ctx->gr_kmer.ensure(8 * (Nt + 1))); CK(ctx->gr_nks.ensure(8 * (Nt + 1)));
-    CK(cudaMemsetAsync(ctx->gr_packed.as<uint8_t>() + Bt, 0, 64, st));
-    if ((rc = allgatherv(ctx, ctx->packed.p, ctx->gr_packed.p, nb, 1))) return rc;
-    if ((rc = allgatherv(ctx, ctx->off.p, ctx->gr_off.p, nr, 8))) return rc;
-    if ((rc = allgatherv(ctx, ctx->len64.p, ctx->gr_len64.p, nr, 8))) return rc;
-    u64 rbase = 0, bbase = 0;
+    const int W = ctx->comm.nranks, me = ctx->comm.rank;
+    bytes = std::max<size_t>(bytes, 256);
+    if (W == 1) { CK(w.buf.ensure(bytes)); w.peer[0] = w.buf.p; return 0; }
+    if (w.mapped && bytes <= w.buf.cap) return 0;
+    // nobody may still be writing into (or have mapped) the old buffer: two barriers around the unmap
+    u64 one = 1; int rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((rc = allreduce_u64(ctx, &one, 1, ncclSum))) return rc;
+    window_unmap(ctx, w);
+    one = 1; if ((rc = allreduce_u64(ctx, &one, 1, ncclSum))) return rc;
+    CK(w.buf.ensure(bytes));
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, w.buf.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(ctx->tmp64.ensure(64 * (size_t)(W + 1) + 512));
+    char *d = ctx->tmp64.as<char>() + 512;                      // [0, 512) is the scratch of the scalar collectives
+    CK(cudaMemcpyAsync(d + 64 * (size_t)W, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx->comm.api->AllGather(d + 64 * (size_t)W, d, 64, ncclUint8, ctx->comm.comm, ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all(W);
+    CK(cudaMemcpyAsync(all.data(), d, 64 * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < W; ++r)
     {
-        if (r && nr[r]) { k_add_u64<<<nblk(nr[r], 256), 256, 0, st>>>(ctx->gr_off.as<u64>() + rbase, nr[r], bbase); CKL(); LAUNCHED(ctx); }
-        rbase += nr[r]; bbase += nb[r];
+        if (r == me) { w.peer[r] = w.buf.p; continue; }
+        cudaError_t e = cudaIpcOpenMemHandle(&w.peer[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { w.peer[r] = nullptr; w.mapped = true; window_unmap(ctx, w); return fail(ctx, ELBA_FE_ERR_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
     }
-    const u32 n = (u32)Nt;
-    k_prep_reads<<<nblk((u64)n + 1, 256), 256, 0, st>>>(ctx->gr_len64.as<u64>(), n, ctx->cfg.k, ctx->cfg.stride,
-        ctx->gr_len32.as<u32>(), ctx->gr_chunk.as<u64>(), ctx->gr_kmer.as<u64>(), ctx->gr_nks.as<u64>());
-    CKL(); LAUNCHED(ctx);
-    if ((rc = exclusive_scan_inplace(ctx, ctx->gr_chunk.as<u64>(), (u64)n + 1))) return rc;
-    if ((rc = exclusive_scan_inplace(ctx, ctx->gr_kmer.as<u64>(), (u64)n + 1))) return rc;
-    u64 tot[2];
-    CK(cudaMemcpyAsync(&tot[0], ctx->gr_chunk.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&tot[1], ctx->gr_kmer.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    ctx->gr_n = Nt; ctx->gr_nchunks = tot[0]; ctx->gr_M = tot[1]; ctx->gr_read0 = (int64_t)ro[0];
-    plan.rv.buf = ctx->gr_packed.as<uint8_t>(); plan.rv.off = ctx->gr_off.as<u64>(); plan.rv.len = ctx->gr_len32.as<u32>();
-    plan.rv.chunk_start = ctx->gr_chunk.as<u64>(); plan.rv.kmer_start = ctx->gr_kmer.as<u64>(); plan.rv.n = n; plan.rv.nchunks = tot[0];
-    plan.Ms = tot[1]; plan.read_base = (u32)ro[0]; plan.nranks = W; plan.rank = ctx->comm.rank;
-    ctx->exchange_bytes = Bt - ctx->packed_bytes + 16 * (Nt - ctx->n);
+    w.mapped = true;
     return 0;
+}
+
+// all ranks reach this point of their streams before any of them goes on (device-side: no host synchronisation)
+static int stream_barrier(elba_fe_ctx *ctx)
+{
+    if (ctx->comm.nranks == 1) return 0;
+    CK(ctx->tmp64.ensure(1024));
+    NC(ctx->comm.api->AllReduce(ctx->tmp64.as<u64>() + 48, ctx->tmp64.as<u64>() + 48, 1, ncclUint64, ncclSum, ctx->comm.comm, ctx->stream));
+    return 0;
+}
+
+// Several GPUs: what every rank must know before the super-k-mer path can run across them: the blocks of reads are
+// consecutive in rank order (global read ids travel as 32 bits in the records), the total number of instances (bucket
+// geometry) and that every GPU can address every other one.  ok = false: use the hash path with its NCCL all-to-all.
+static int multi_setup(elba_fe_ctx *ctx, bool &ok)
+{
+    const int W = ctx->comm.nranks;
+    std::vector<u64> nr, ro, ms;
+    int rc;
+    if ((rc = allgather_u64(ctx, ctx->n, nr))) return rc;
+    if ((rc = allgather_u64(ctx, (u64)ctx->read_id_offset, ro))) return rc;
+    if ((rc = allgather_u64(ctx, ctx->Ms, ms))) return rc;
+    u64 Nt = 0, Mt = 0; ok = W <= SK_MAXW;
+    for (int r = 0; r < W; ++r) { if (ro[r] != ro[0] + Nt) ok = false; Nt += nr[r]; Mt += ms[r]; }
+    if (ro[0] + Nt >= 0xFFFFFFF0ull) ok = false;
+    ctx->N_total = Nt; ctx->Ms_total = Mt; ctx->read_base0 = (int64_t)ro[0];
+    ctx->roff.assign(W + 1, ro[0] + Nt);
+    for (int r = 0; r < W; ++r) ctx->roff[r] = ro[r];
+    if (ok)
+    {
+        CK(ctx->d_roff.ensure(8 * (size_t)(W + 1)));
+        CK(cudaMemcpyAsync(ctx->d_roff.p, ctx->roff.data(), 8 * (size_t)(W + 1), cudaMemcpyHostToDevice, ctx->stream));
+        // peer access from this GPU to every other GPU of the job
+        std::vector<u64> dev;
+        if ((rc = allgather_u64(ctx, (u64)ctx->cfg.device, dev))) return rc;
+        u64 can = 1;
+        for (int r = 0; r < W; ++r)
+            if (r != ctx->comm.rank)
+            {
+                int a = 0;
+                if ((int)dev[r] == ctx->cfg.device || cudaDeviceCanAccessPeer(&a, ctx->cfg.device, (int)dev[r]) != cudaSuccess || !a) can = 0;
+            }
+        if (const char *e = getenv("ELBA_FE_P2P")) { if (atoi(e) == 0) can = 0; }
+        if ((rc = allreduce_u64(ctx, &can, 1, ncclMin))) return rc;
+        if (!can) ok = false;
+    }
+    ctx->p2p = ok;
+    return 0;
+}
+
+static __global__ void k_remote_records(const u64 *__restrict__ fill, u64 nbg, u32 nb_own, u32 me, u64 *__restrict__ out)
+{
+    u64 acc = 0;
+    for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nbg; b += (u64)gridDim.x * blockDim.x)
+        if (b / nb_own != me) acc += (u32)fill[b];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
 static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm, u64 rel_cap, bool &retry)
@@ -459,9 +522,11 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     cudaStream_t st = ctx->stream;
     const ReadsView rv = plan.rv;
     const int k = ctx->cfg.k; const u32 lower = ctx->cfg.lower, upper = ctx->cfg.upper;
-    const u64 Ms = plan.Ms;                                 // instances of ALL the reads in rv: decides the bucket geometry
+    const u64 Ms = plan.Ms;                                 // instances of the reads of ALL GPUs: decides the bucket geometry
     const u64 Ms_own = Ms / (u64)plan.nranks + 1;           // what this GPU expects to count: decides the list capacities
+    const int W = plan.nranks, me = plan.rank;
     u64 *d_ctr = ctx->ctr.as<u64>(); u32 *d_err = reinterpret_cast<u32*>(d_ctr + 3);
+    int rc;
     retry = false;
     const u32 slots = SK4_SLOTS, bcap = sk4_cap(SK4_THREADS);
     const double avg_run = 32.0 / (64.0 / (double)(Wm + 1) + 1.0);    // a chunk of 32 window starts holds 32 * 2 / (W + 1) minimizer runs plus the one its start cuts
@@ -476,15 +541,23 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     const u64 NB = (NBg + plan.nranks - 1) / plan.nranks;   // buckets of this GPU: [rank * NB, (rank + 1) * NB) of NBg
     NBg = NB * (u64)plan.nranks;
     if (NBg >= (1ull << 31)) return fail(ctx, ELBA_FE_ERR_INVALID, "too many minimizer buckets for one context");
+    // records per (bucket, source GPU): the bucket sizes vary by ~40 % whatever the number of sources, the share of one
+    // source adds its own (Poisson-like) spread
     double slack = 2.5;
     if (const char *e = getenv("ELBA_FE_SKM_SLACK")) { double v = atof(e); if (v >= 1.0 && v <= 16.0) slack = v; }
-    u64 rcap = (u64)((double)Ms / (double)NBg / avg_run * slack) + 32;
+    const double mean_rec = (double)Ms / (double)NBg / avg_run / (double)W;
+    u64 rcap = (u64)(mean_rec * slack + (W > 1 ? 4.0 * std::sqrt(1.5 * mean_rec) : 0.0)) + (W > 1 ? 16 : 32);
     rcap = std::min<u64>(rcap, SK4_RMAX);
     ctx->sz.partitions = NBg; ctx->sz.table_slots = slots;
+    // every rank computes the same capacities from the same global numbers: the windows are (re)allocated collectively
     const u64 ovf_cap = std::max<u64>(ctx->skm_ovf_cap, std::max<u64>(Ms_own / 64, 1u << 16));
-    CK(ctx->skm_slab.ensure(sizeof(SkmRec) * NB * rcap)); CK(ctx->skm_fill.ensure(sizeof(u64) * NB));
-    CK(ctx->skm_ovf.ensure(sizeof(SkmRec) * ovf_cap));
+    if ((rc = window_ensure(ctx, ctx->w_slab, sizeof(SkmRec) * NB * (u64)W * rcap))) return rc;
+    if ((rc = window_ensure(ctx, ctx->w_ovf, sizeof(SkmRec) * ovf_cap))) return rc;
+    if ((rc = window_ensure(ctx, ctx->w_octr, 64))) return rc;
+    CK(ctx->skm_fill.ensure(sizeof(u64) * NBg));
+    if (W > 1) { CK(ctx->skm_fillin.ensure(sizeof(u64) * NBg)); CK(ctx->skm_plan.ensure(sizeof(u64) * NB)); }
     ctx->skm_ovf_cap = ovf_cap;
+    u64 *d_octr = ctx->w_octr.buf.as<u64>();                              // [0] records, [1] instances in my overflow list
     // seed list: {list index, pos, read} of every instance of a reliable k-mer; the size of the last pass, else a guess
     const u64 gc_max = (u64)grid_for(ctx, SK4_MINB);                  // CTAs of the count kernel: each may leave one chunk partly used
     u64 seed_guess = Ms_own / 16 + (1u << 20) + gc_max * SK4_CHUNK;
@@ -494,10 +567,15 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     ctx->seed_cap = seed_cap;
     if (rel_cap >= 0xFFFFFFF0ull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 entries in the reliable list of one context");
     SeedSink2 seeds; seeds.out = ctx->seeds.as<Seed>(); seeds.cursor = d_ctr + 7; seeds.cap = seed_cap;
-    CK(cudaMemsetAsync(ctx->skm_fill.p, 0, sizeof(u64) * NB, st));
-    RecSink sink; sink.slab = ctx->skm_slab.as<SkmRec>(); sink.fill = ctx->skm_fill.as<u64>(); sink.rcap = (u32)rcap; sink.NB = (u32)NBg;
-    sink.b_lo = (u32)(NB * (u64)plan.rank); sink.b_cnt = (u32)NB; sink.read_base = plan.read_base;
-    sink.ovf = ctx->skm_ovf.as<SkmRec>(); sink.ovf_cursor = d_ctr + 5; sink.ovf_inst = d_ctr + 6; sink.ovf_cap = ovf_cap;
+    CK(cudaMemsetAsync(ctx->skm_fill.p, 0, sizeof(u64) * NBg, st));
+    CK(cudaMemsetAsync(d_octr, 0, 64, st));
+    // several GPUs: nobody writes into a slab (or bumps an overflow counter) that its owner still reads from the previous pass
+    if ((rc = stream_barrier(ctx))) return rc;
+    RecSink sink; std::memset(&sink, 0, sizeof sink);
+    for (int r = 0; r < W; ++r) { sink.slab[r] = (SkmRec*)ctx->w_slab.peer[r]; sink.ovf[r] = (SkmRec*)ctx->w_ovf.peer[r]; sink.ovf_ctr[r] = (u64*)ctx->w_octr.peer[r]; }
+    sink.fill = ctx->skm_fill.as<u64>(); sink.rcap = (u32)rcap; sink.nb_own = (u32)NB; sink.nsrc = (u32)W; sink.me = (u32)me;
+    sink.read_base = plan.read_base; sink.ovf_cap = ovf_cap;
+    if (W > 1) CK(cudaEventRecord(ctx->ev_x0, st));
     const u32 nmax = skm_nmax(k);
     EventPair &pp = next_pair(ctx->pev, ctx->pev_used);
     CK(cudaEventRecord(pp.a, st));
@@ -522,8 +600,24 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
         CKL(); LAUNCHED(ctx);
     }
     CK(cudaEventRecord(pp.b, st));
-    RecSlabs in; in.slab = ctx->skm_slab.as<SkmRec>(); in.fill = ctx->skm_fill.as<u64>(); in.rcap = (u32)rcap;
-    RecOverflow ovf; ovf.list = ctx->skm_ovf.as<SkmRec>(); ovf.cursor = d_ctr + 5; ovf.inst = d_ctr + 6; ovf.cap = ovf_cap;
+    RecSlabs in; in.slab = ctx->w_slab.buf.as<SkmRec>(); in.fill = ctx->skm_fill.as<u64>(); in.plan = in.fill; in.rcap = (u32)rcap; in.nsrc = (u32)W; in.nb = (u32)NB;
+    if (W > 1)
+    {
+        // the reservation words follow the records: rank d gets, from every source, the fill words of its own buckets.  Stream
+        // order makes this exchange the barrier behind the peer-memory stores of the scatter.
+        NC(ctx->comm.api->GroupStart());
+        for (int r = 0; r < W; ++r)
+        {
+            NC(ctx->comm.api->Send(ctx->skm_fill.as<u64>() + NB * (u64)r, NB, ncclUint64, r, ctx->comm.comm, st));
+            NC(ctx->comm.api->Recv(ctx->skm_fillin.as<u64>() + NB * (u64)r, NB, ncclUint64, r, ctx->comm.comm, st));
+        }
+        NC(ctx->comm.api->GroupEnd());
+        CK(cudaEventRecord(ctx->ev_x1, st));
+        k_skm_plan<<<nblk(NB, 256), 256, 0, st>>>(ctx->skm_fillin.as<u64>(), (u32)NB, (u32)W, (u32)rcap, ctx->skm_plan.as<u64>()); CKL(); LAUNCHED(ctx);
+        k_remote_records<<<grid_for(ctx, 2), 256, 0, st>>>(ctx->skm_fill.as<u64>(), NBg, (u32)NB, (u32)me, d_ctr + 9); CKL(); LAUNCHED(ctx);
+        in.fill = ctx->skm_fillin.as<u64>(); in.plan = ctx->skm_plan.as<u64>();
+    }
+    RecOverflow ovf; ovf.list = ctx->w_ovf.buf.as<SkmRec>(); ovf.cursor = d_octr; ovf.inst = d_octr + 1; ovf.cap = ovf_cap;
     EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
     CK(cudaEventRecord(ep.a, st));
     {
@@ -534,10 +628,15 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     CKL(); LAUNCHED(ctx);
     CK(cudaEventRecord(ep.b, st));
     u64 o[2] = {0, 0};
-    CK(cudaMemcpyAsync(o, d_ctr + 5, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o, d_octr, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const u64 novf = o[0], ninst = o[1];
-    if (novf > ovf_cap) { ctx->skm_ovf_cap = novf + (novf >> 3); retry = true; return 0; }
+    {
+        // an overflow list that was too small anywhere: every rank redoes the pass with the largest need (the windows are collective)
+        u64 need = novf > ovf_cap ? novf + (novf >> 3) : 0;
+        if (W > 1 && (rc = allreduce_u64(ctx, &need, 1, ncclMax))) return rc;
+        if (need) { ctx->skm_ovf_cap = std::max(ctx->skm_ovf_cap, need); retry = true; return 0; }
+    }
     ctx->sz.slow_partitions = 0; ctx->sz.overflow_instances = ninst;
     if (novf)
     {
@@ -547,19 +646,25 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
         CK(ctx->table.ensure(sizeof(Slot) * gslots));
         k_table_clear<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->table.as<Slot>(), gslots, EMPTY_KEY); CKL(); LAUNCHED(ctx);
         TableRef T{ctx->table.as<Slot>(), (u32)gslots};
-        k_skm4_count_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->skm_ovf.as<SkmRec>(), d_ctr + 5, ovf_cap, k, T, d_err, d_ctr + 2); CKL(); LAUNCHED(ctx);
+        k_skm4_count_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->w_ovf.buf.as<SkmRec>(), d_octr, ovf_cap, k, T, d_err, d_ctr + 2); CKL(); LAUNCHED(ctx);
         k_skm4_collect_global<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap); CKL(); LAUNCHED(ctx);
-        k_skm4_emit_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->skm_ovf.as<SkmRec>(), d_ctr + 5, ovf_cap, k, T, lower, upper, seeds); CKL(); LAUNCHED(ctx);
+        k_skm4_emit_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->w_ovf.buf.as<SkmRec>(), d_octr, ovf_cap, k, T, lower, upper, seeds); CKL(); LAUNCHED(ctx);
     }
     ctx->seeds_fused = false;
     {
         // [0] list entries handed out (chunks with holes + what the fallback appended), [1] sum of reliable counts, [2] distinct,
         // [7] seed entries handed out, [8] reliable k-mers
-        u64 h[9];
+        u64 h[10];
         CK(cudaMemcpyAsync(h, d_ctr, sizeof h, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         ctx->skm_reliable = h[8];
-        if (h[7] > seed_cap) { ctx->seed_cap = h[7] + (h[7] >> 4) + 1024; retry = true; return 0; }
+        ctx->exchange_bytes = 32 * h[9];                      // records this GPU wrote into other GPUs' slabs
+        {
+            u64 again = h[7] > seed_cap;
+            if (again) ctx->seed_cap = h[7] + (h[7] >> 4) + 1024;
+            if (W > 1 && (rc = allreduce_u64(ctx, &again, 1, ncclMax))) return rc;
+            if (again) { retry = true; return 0; }
+        }
         if (h[0] <= rel_cap && h[7] < h[1])
         {
             char b[160]; snprintf(b, sizeof b, "fused seed emission handed out %llu entries, the counts promise %llu", (unsigned long long)h[7], (unsigned long long)h[1]);
@@ -614,16 +719,15 @@ int elba_fe_count(elba_fe_ctx *ctx)
     bool use_skm = !direct && stride == 1 && skm_geometry(k, skm_m, skm_W);
     if (const char *e = getenv("ELBA_FE_COUNT_PATH")) { if (!std::strcmp(e, "hash")) use_skm = false; }
     SkmPlan plan; plan.rv = rv; plan.Ms = Ms; plan.read_base = 0; plan.nranks = 1; plan.rank = 0;
-    ctx->seeds_global = false;
-    if (use_skm && W > 1)
+    ctx->p2p = false; ctx->kmers_distributed = false; ctx->read_base0 = ctx->read_id_offset;
+    if (W > 1)
     {
+        // every GPU parses ITS OWN reads; the records go straight into the owners' slabs through peer memory (superkmer.cuh)
         bool ok = false;
-        CK(cudaEventRecord(ctx->ev_x0, st));
-        int rc0 = gather_reads(ctx, plan, ok);
+        int rc0 = multi_setup(ctx, ok);
         if (rc0) return rc0;
-        CK(cudaEventRecord(ctx->ev_x1, st));
-        if (!ok) use_skm = false;                                        // read blocks not consecutive over the ranks: hash path
-        else ctx->seeds_global = true;
+        if (use_skm && !ok) use_skm = false;                             // read blocks not consecutive over the ranks / no peer access: hash path
+        if (use_skm) { plan.Ms = ctx->Ms_total; plan.read_base = (u32)ctx->read_id_offset; plan.nranks = W; plan.rank = me; }
     }
     if (W > 1) { P1 = (P1 + W - 1) / W * W; if (P1 > MAX_P1) P1 = MAX_P1 / W * W; }      // every rank owns P1 / W partitions
     const u32 Pown = P1 / (u32)W;
@@ -631,7 +735,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
 
     u64 rel_cap = Ms_max / lower + 1;
     if (rel_cap * 12 > (1ull << 30)) rel_cap = std::max<u64>(ctx->rel_cap, std::max<u64>(Ms_max / 8, (1ull << 30) / 12));
-    if (use_skm) rel_cap += (u64)grid_for(ctx, 4) * REL_CHUNK;           // the bucket kernel hands the list out in chunks
+    if (use_skm) rel_cap += (u64)grid_for(ctx, SK4_MINB) * SK4_CHUNK;           // the bucket kernel hands the list out in chunks
     u64 R = 0, sumcnt = 0, D = 0;
     for (int attempt = 0; attempt < 4; ++attempt)
     {
@@ -859,8 +963,37 @@ int elba_fe_count(elba_fe_ctx *ctx)
     u64 R_list = R;
     if (use_skm) R = ctx->skm_reliable;
 
-    // ---- several GPUs: every rank needs the whole reliable list (column ids are ranks among ALL reliable k-mers)
     u64 *rk = ctx->rel_key.as<u64>(); u32 *rc_ = ctx->rel_cnt.as<u32>();
+    if (W > 1 && ctx->seeds_fused)
+    {
+        // ---- several GPUs, super-k-mer path: NOTHING is replicated.  Every GPU sorts the reliable k-mers it owns; the sorted
+        // runs are all-gathered (8 B per k-mer) and the column id of a k-mer = its rank in the own run + the number of smaller
+        // k-mers in every other run (binary searches, k_rank_global).  (reference: the Allreduce / Exscan of src/KmerOps.cpp:371-374)
+        const u64 Rl = ctx->skm_reliable;
+        if (R_list >= 0xFFFFFFF0ull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 entries in the reliable list of one context");
+        CK(ctx->rel_key_s.ensure(8 * std::max<u64>(R_list, 1))); CK(ctx->rel_cnt_s.ensure(4 * std::max<u64>(R_list, 1)));
+        CK(ctx->rel_idx.ensure(4 * std::max<u64>(R_list, 1))); CK(ctx->rel_idx_s.ensure(4 * std::max<u64>(R_list, 1))); CK(ctx->perm.ensure(4 * std::max<u64>(R_list, 1)));
+        CK(ctx->rel_gid.ensure(4 * std::max<u64>(Rl, 1)));
+        if (R_list) { k_iota_u32<<<nblk(R_list, 256), 256, 0, st>>>(ctx->rel_idx.as<u32>(), R_list); CKL(); LAUNCHED(ctx); }
+        int rc1 = sort_pairs(ctx, rk, ctx->rel_key_s.as<u64>(), ctx->rel_idx.as<u32>(), ctx->rel_idx_s.as<u32>(), R_list, 64 - 2 * k, 64);
+        if (rc1) return rc1;
+        if ((rc1 = allgather_u64(ctx, Rl, ctx->rel_counts))) return rc1;
+        u64 Rt = 0; for (u64 v : ctx->rel_counts) Rt += v;
+        if (Rt >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers");
+        CK(ctx->rel_all_key.ensure(8 * std::max<u64>(Rt, 1)));
+        if ((rc1 = allgatherv(ctx, ctx->rel_key_s.p, ctx->rel_all_key.p, ctx->rel_counts, 8))) return rc1;
+        RankRuns runs; std::memset(&runs, 0, sizeof runs);
+        { u64 o = 0; for (int r = 0; r < W; ++r) { runs.off[r] = o; runs.n[r] = ctx->rel_counts[r]; o += ctx->rel_counts[r]; } }
+        runs.nruns = (u32)W; runs.me = (u32)me;
+        if (Rl) { k_rank_global<<<nblk(Rl, 256), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_idx_s.as<u32>(), rc_, Rl, ctx->rel_all_key.as<u64>(), runs,
+                      ctx->perm.as<u32>(), ctx->rel_cnt_s.as<u32>(), ctx->rel_gid.as<u32>()); CKL(); LAUNCHED(ctx); }
+        ctx->R_local = Rl; ctx->kmers_distributed = true; ctx->seed_id_base = 0;
+        ctx->sz.reliable = Rt;
+        CK(cudaEventRecord(ctx->ev[3], st));
+        ctx->phase = 2;
+        return 0;
+    }
+    // ---- several GPUs, hash path: every rank needs the whole reliable list (column ids are ranks among ALL reliable k-mers)
     if (W > 1)
     {
         std::vector<u64> Rr;
@@ -871,9 +1004,8 @@ int elba_fe_count(elba_fe_ctx *ctx)
         if ((rc0 = allgatherv(ctx, ctx->rel_key.p, ctx->rel_all_key.p, Rr, sizeof(u64)))) return rc0;
         if ((rc0 = allgatherv(ctx, ctx->rel_cnt.p, ctx->rel_all_cnt.p, Rr, sizeof(u32)))) return rc0;
         rk = ctx->rel_all_key.as<u64>(); rc_ = ctx->rel_all_cnt.as<u32>(); R_list = Rt;
-        ctx->seed_id_base = 0; for (int r = 0; r < me; ++r) ctx->seed_id_base += Rr[r];      // my list inside the concatenation
     }
-    else ctx->seed_id_base = 0;
+    ctx->seed_id_base = 0;
     if (R >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers on one context");
     ctx->sz.reliable = R;
 
@@ -951,6 +1083,7 @@ static int operands_from_gathered(elba_fe_ctx *ctx, u64 tot)
     int64_t row0, nr, col0, ncb;
     block_extent((int64_t)ctx->N_total, pr, bi, row0, nr);
     block_extent((int64_t)ctx->N_total, pc, bj, col0, ncb);
+    row0 += ctx->read_base0; col0 += ctx->read_base0;                    // the gathered keys carry GLOBAL read ids, which start at rank 0's offset
     // left: rows R_i are one contiguous slice
     CK(ctx->l_rowptr.ensure(8 * ((size_t)nr + 2))); CK(ctx->r_ptr.ensure(8 * ((size_t)ncb + 2)));
     k_read_ptr<<<nblk((u64)nr + 1, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), tot, (u64)row0, (u64)nr, ctx->l_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
@@ -996,28 +1129,72 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     u64 *d_ctr = ctx->ctr.as<u64>();
     CK(cudaMemsetAsync(d_ctr, 0, 64, st));
     // one GPU: counting already told how many instances belong to reliable k-mers.  Several GPUs: that number is
-    // known per OWNER, not per reader, so the triple buffers are sized by the candidate count.
+    // known per OWNER, not per reader, so the triple buffers are sized by what arrives.
     u64 cap = std::max<u64>(npre, 1);
     const bool fused = ctx->seeds_fused;
-    const bool global = fused && ctx->seeds_global;        // several GPUs, super-k-mer path: the seeds carry GLOBAL read ids
-    const int gb = 32 + bits_for(std::max<u64>((u64)ctx->gr_read0 + ctx->N_total, 2));      // key bits of (global read << 32 | column)
-    u64 nsort = 0;                                         // entries handed to the (read, column) sort; fused: the seed list with its holes
-    if (fused) cap = std::max<u64>(ctx->nseeds_fused, 1);
-    if (W == 1 || fused) { CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); }
+    const bool routed = fused && W > 1;                    // several GPUs, super-k-mer path: the k-mer owners send the triples to the read owners
+    u64 nsort = 0;                                         // entries handed to the (read, column) sort
+    bool holes = false;                                    // ... some of which are holes of the chunked seed list (sorted behind the triples)
+    if (fused && !routed) cap = std::max<u64>(ctx->nseeds_fused, 1);
+    if ((W == 1 || fused) && !routed) { CK(ctx->seed_key.ensure(8 * cap)); CK(ctx->seed_pos.ensure(4 * cap)); }
     // sweep 2: every instance of a reliable k-mer -> (read, column, pos)
     u64 emitted = 0;
     {
         EventPair &lp = next_pair(ctx->lev, ctx->lev_used);
         CK(cudaEventRecord(lp.a, st));
-        if (fused)
+        if (routed)
+        {
+            // The seeds lie with the OWNERS of the k-mers; the rows of A belong to the owners of the reads.  Every GPU turns its
+            // seeds into (global read, column, pos) and stores each straight into the read owner's receive window through peer
+            // memory (region [source][route_cap] of that window; the slot comes from a local cursor per destination): the
+            // reference's second exchange (src/KmerOps.cpp:274) without packing, 12 B per instance of a reliable k-mer.
+            const u64 ncand = ctx->nseeds_fused;
+            ctx->sz.candidates = ncand;
+            u64 most = ncand; int rc0;
+            if ((rc0 = allreduce_u64(ctx, &most, 1, ncclMax))) return rc0;
+            const u64 rcap_t = std::max<u64>(ctx->route_cap, most / (u64)W + most / (u64)(2 * W) + (1u << 16));      // same on every rank
+            ctx->route_cap = rcap_t;
+            if ((rc0 = window_ensure(ctx, ctx->w_rkey, 8 * rcap_t * (u64)W))) return rc0;
+            if ((rc0 = window_ensure(ctx, ctx->w_rpos, 4 * rcap_t * (u64)W))) return rc0;
+            if ((rc0 = window_ensure(ctx, ctx->w_rcnt, 8 * (size_t)SK_MAXW))) return rc0;
+            CK(ctx->route_cur.ensure(8 * (size_t)SK_MAXW));
+            CK(cudaMemsetAsync(ctx->route_cur.p, 0, 8 * (size_t)SK_MAXW, st));
+            if ((rc0 = stream_barrier(ctx))) return rc0;          // the windows of the previous pass have been read
+            RouteSink rs; std::memset(&rs, 0, sizeof rs);
+            for (int r = 0; r < W; ++r) { rs.key[r] = (u64*)ctx->w_rkey.peer[r]; rs.pos[r] = (u32*)ctx->w_rpos.peer[r]; rs.cnt[r] = (u64*)ctx->w_rcnt.peer[r]; rs.first[r] = ctx->roff[r]; }
+            rs.first[W] = ctx->roff[W]; rs.nranks = (u32)W; rs.me = (u32)ctx->comm.rank; rs.cap = rcap_t; rs.cursor = ctx->route_cur.as<u64>();
+            if (ncand) { k_seed_route<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->seeds.as<Seed>(), ncand, ctx->perm.as<u32>(), rs); CKL(); LAUNCHED(ctx); }
+            k_route_publish<<<1, 32, 0, st>>>(rs); CKL(); LAUNCHED(ctx);
+            if ((rc0 = stream_barrier(ctx))) return rc0;          // every source has stored its triples and its counts
+            u64 got[SK_MAXW];
+            CK(cudaMemcpyAsync(got, ctx->w_rcnt.buf.p, 8 * (size_t)W, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            u64 tot = 0, over = 0;
+            for (int r = 0; r < W; ++r) { if (got[r] > rcap_t) over = std::max(over, got[r]); tot += std::min(got[r], rcap_t); }
+            if ((rc0 = allreduce_u64(ctx, &over, 1, ncclMax))) return rc0;
+            if (over) { ctx->route_cap = over + over / 8; return fail(ctx, ELBA_FE_ERR_CUDA, "seed routing window too small (the reads are very unevenly distributed over the GPUs): call elba_fe_build_A again"); }
+            const u64 t1 = std::max<u64>(tot, 1);
+            CK(ctx->seed_key.ensure(8 * t1)); CK(ctx->seed_pos.ensure(4 * t1));
+            u64 o = 0;
+            for (int r = 0; r < W; ++r)
+            {
+                if (got[r]) { k_route_unpack<<<nblk(got[r], 256), 256, 0, st>>>(ctx->w_rkey.buf.as<u64>() + rcap_t * (u64)r, ctx->w_rpos.buf.as<u32>() + rcap_t * (u64)r, got[r],
+                                  (u64)ctx->read_id_offset, cb, ctx->seed_key.as<u64>() + o, ctx->seed_pos.as<u32>() + o); CKL(); LAUNCHED(ctx); }
+                o += got[r];
+            }
+            ctx->panel_bytes = 12 * (tot - got[ctx->comm.rank]);
+            CK(cudaMemsetAsync(d_ctr, 0, 8, st));
+            emitted = tot; nsort = tot;
+        }
+        else if (fused)
         {
             // counting already listed every instance of a reliable k-mer as {list index, pos, read} (skm_count.cuh): the column id
             // is perm[list index]; holes keep a key that sorts behind every entry
             const u64 ncand = ctx->nseeds_fused;
             ctx->sz.candidates = ncand;
-            nsort = ncand;
-            const u64 hole_key = 1ull << (global ? gb : cb + rb);
-            if (ncand) { k_seed_keys<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->seeds.as<Seed>(), ncand, ctx->perm.as<u32>(), (u32)ctx->seed_id_base, global ? 32 : cb, hole_key,
+            nsort = ncand; holes = true;
+            const u64 hole_key = 1ull << (cb + rb);
+            if (ncand) { k_seed_keys<<<grid_for(ctx, 8), 256, 0, st>>>(ctx->seeds.as<Seed>(), ncand, ctx->perm.as<u32>(), 0u, cb, hole_key,
                              ctx->seed_key.as<u64>(), ctx->seed_pos.as<u32>(), d_ctr); CKL(); LAUNCHED(ctx); }
         }
         else if (ctx->nchunks && R)
@@ -1045,8 +1222,11 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
             }
         }
         CK(cudaEventRecord(lp.b, st));
-        CK(cudaMemcpyAsync(&emitted, d_ctr, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        if (!routed)
+        {
+            CK(cudaMemcpyAsync(&emitted, d_ctr, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
     }
     {
         // every instance of a reliable k-mer must have been found again: emitted == what counting promised (summed over the GPUs)
@@ -1061,54 +1241,9 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     }
 
     int rc;
-    u64 nnzA = 0, gathered = 0;
-    if (global)
-    {
-        // The seeds were written by the OWNERS of the k-mers.  SpGEMM needs all of A on every GPU anyway (unsplit inner
-        // dimension), so the triples are all-gathered (12 B each), sorted and deduplicated once, and every GPU slices the
-        // rows of its own reads out of the result: this replaces "send seeds to the read's GPU + build + all-gather A".
-        std::vector<u64> ne;
-        if ((rc = allgather_u64(ctx, nsort, ne))) return rc;
-        u64 tsort = 0; for (u64 v : ne) tsort += v;
-        u64 tpre = npre; if ((rc = allreduce_u64(ctx, &tpre, 1, ncclSum))) return rc;        // valid triples; the holes sort behind them
-        const u64 tp1 = std::max<u64>(tsort, 1);
-        CK(ctx->all_key.ensure(8 * tp1)); CK(ctx->all_pos.ensure(4 * tp1)); CK(ctx->seed_key2.ensure(8 * tp1)); CK(ctx->seed_pos2.ensure(4 * tp1));
-        if ((rc = allgatherv(ctx, ctx->seed_key.p, ctx->all_key.p, ne, 8))) return rc;
-        if ((rc = allgatherv(ctx, ctx->seed_pos.p, ctx->all_pos.p, ne, 4))) return rc;
-        ctx->panel_bytes = 12 * (tsort - nsort);
-        if ((rc = sort_pairs(ctx, ctx->all_key.as<u64>(), ctx->seed_key2.as<u64>(), ctx->all_pos.as<u32>(), ctx->seed_pos2.as<u32>(), tsort, 0, gb + 1))) return rc;
-        CK(ctx->idx.ensure(8 * (tpre + 1)));
-        k_mark_run_ends<<<nblk(tpre + 1, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), tpre, ctx->idx.as<u64>()); CKL(); LAUNCHED(ctx);
-        if ((rc = exclusive_scan_inplace(ctx, ctx->idx.as<u64>(), tpre + 1))) return rc;
-        CK(cudaMemcpyAsync(&gathered, ctx->idx.as<u64>() + tpre, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(ctx->g_key.ensure(8 * std::max<u64>(gathered, 1))); CK(ctx->g_pos.ensure(4 * std::max<u64>(gathered, 1)));
-        if (tpre) { k_dedupe_write<<<nblk(tpre, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), ctx->seed_pos2.as<u32>(), ctx->idx.as<u64>(), tpre, ctx->g_key.as<u64>(), ctx->g_pos.as<u32>()); CKL(); LAUNCHED(ctx); }
-        // the rows of this GPU's reads
-        CK(ctx->a_rowptr.ensure(8 * ((size_t)N + 2)));
-        k_read_ptr<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), gathered, (u64)ctx->read_id_offset, (u64)N, ctx->a_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
-        int64_t lb = 0, le = 0;
-        CK(cudaMemcpyAsync(&lb, ctx->a_rowptr.as<int64_t>(), 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&le, ctx->a_rowptr.as<int64_t>() + N, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        nnzA = (u64)(le - lb);
-        ctx->sz.nnzA = nnzA;
-        const u64 na = std::max<u64>(nnzA, 1);
-        CK(ctx->a_pos.ensure(4 * na)); CK(ctx->a_col.ensure(4 * na));
-        CK(ctx->at_key.ensure(8 * na)); CK(ctx->at_key2.ensure(8 * na)); CK(ctx->at_pos2.ensure(4 * na)); CK(ctx->at_row.ensure(4 * na)); CK(ctx->at_pos.ensure(4 * na));
-        CK(ctx->at_colptr.ensure(8 * (R + 2)));
-        k_sub_base<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->a_rowptr.as<int64_t>(), (u64)N, lb); CKL(); LAUNCHED(ctx);
-        if (nnzA)
-        {
-            k_slice_left<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), (u64)lb, nnzA, ctx->a_col.as<u32>()); CKL(); LAUNCHED(ctx);
-            CK(cudaMemcpyAsync(ctx->a_pos.p, ctx->g_pos.as<u32>() + lb, 4 * nnzA, cudaMemcpyDeviceToDevice, st));
-            k_slice_right<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), (u64)lb, nnzA, (u64)ctx->read_id_offset, rb, ctx->at_key.as<u64>()); CKL(); LAUNCHED(ctx);
-        }
-    }
-    else
-    {
+    u64 nnzA = 0;
     // sort by (read, column); merge duplicates keeping the largest position
-    if ((rc = sort_pairs(ctx, ctx->seed_key.as<u64>(), ctx->seed_key2.as<u64>(), ctx->seed_pos.as<u32>(), ctx->seed_pos2.as<u32>(), nsort, 0, cb + rb + (fused ? 1 : 0)))) return rc;      // the first npre are triples, holes behind
+    if ((rc = sort_pairs(ctx, ctx->seed_key.as<u64>(), ctx->seed_key2.as<u64>(), ctx->seed_pos.as<u32>(), ctx->seed_pos2.as<u32>(), nsort, 0, cb + rb + (holes ? 1 : 0)))) return rc;      // the first npre are triples, holes behind
     CK(ctx->idx.ensure(8 * (npre + 1)));
     k_mark_run_ends<<<nblk(npre + 1, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), npre, ctx->idx.as<u64>()); CKL(); LAUNCHED(ctx);
     if ((rc = exclusive_scan_inplace(ctx, ctx->idx.as<u64>(), npre + 1))) return rc;
@@ -1122,7 +1257,6 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     if (npre) { k_dedupe_write<<<nblk(npre, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), ctx->seed_pos2.as<u32>(), ctx->idx.as<u64>(), npre, ctx->a_key.as<u64>(), ctx->a_pos.as<u32>()); CKL(); LAUNCHED(ctx); }
     k_segment_ptr<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, N, cb, ctx->a_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
     if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, cb, rb, ctx->a_col.as<u32>(), ctx->at_key.as<u64>()); CKL(); LAUNCHED(ctx); }
-    }
     // transpose: the same entries sorted by (column, read)
     if ((rc = sort_pairs(ctx, ctx->at_key.as<u64>(), ctx->at_key2.as<u64>(), ctx->a_pos.as<u32>(), ctx->at_pos.as<u32>(), nnzA, 0, cb + rb))) return rc;
     k_segment_ptr<<<nblk(R + 1, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, R, rb, ctx->at_colptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
@@ -1132,7 +1266,7 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     ctx->op.r_colptr = ctx->at_colptr.as<int64_t>(); ctx->op.r_row = ctx->at_row.as<u32>(); ctx->op.r_pos = ctx->at_pos.as<u32>();
     ctx->op.r_nnz = nnzA;
     ctx->op.row0 = ctx->op.col0 = ctx->read_id_offset;
-    if (W > 1) { rc = global ? operands_from_gathered(ctx, gathered) : gather_operands(ctx); if (rc) return rc; }
+    if (W > 1) { rc = gather_operands(ctx); if (rc) return rc; }
     if (ctx->op.r_nnz >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "the right SpGEMM operand of one GPU exceeds 2^32 entries");
     CK(ctx->sp_ptr.ensure(4 * (R + 2))); CK(ctx->sp_ent.ensure(8 * std::max<u64>(ctx->op.r_nnz, 1)));
     k_spgemm_operand<<<nblk(std::max<u64>(R + 1, ctx->op.r_nnz), 256), 256, 0, st>>>(ctx->op.r_colptr, R, ctx->op.r_row, ctx->op.r_pos, ctx->op.r_nnz,
@@ -1328,9 +1462,9 @@ int elba_fe_comm_info(elba_fe_ctx *ctx, int *rank, int *nranks, int *grid_rows, 
     if (grid_rows) *grid_rows = ctx->comm.grid_rows; if (grid_cols) *grid_cols = ctx->comm.grid_cols;
     int64_t o, l;
     const int64_t Nt = ctx->comm.nranks > 1 ? (int64_t)ctx->N_total : (int64_t)ctx->n;
-    if (ctx->comm.nranks > 1) block_extent(Nt, ctx->comm.grid_rows, ctx->comm.rank / ctx->comm.grid_cols, o, l); else { o = ctx->read_id_offset; l = ctx->n; }
+    if (ctx->comm.nranks > 1) { block_extent(Nt, ctx->comm.grid_rows, ctx->comm.rank / ctx->comm.grid_cols, o, l); o += ctx->read_base0; } else { o = ctx->read_id_offset; l = ctx->n; }
     if (row0) *row0 = o; if (nrows) *nrows = l;
-    if (ctx->comm.nranks > 1) block_extent(Nt, ctx->comm.grid_cols, ctx->comm.rank % ctx->comm.grid_cols, o, l); else { o = ctx->read_id_offset; l = ctx->n; }
+    if (ctx->comm.nranks > 1) { block_extent(Nt, ctx->comm.grid_cols, ctx->comm.rank % ctx->comm.grid_cols, o, l); o += ctx->read_base0; } else { o = ctx->read_id_offset; l = ctx->n; }
     if (col0) *col0 = o; if (ncols) *ncols = l;
     return 0;
 }
@@ -1369,8 +1503,9 @@ int elba_fe_digests(elba_fe_ctx *ctx, uint64_t out[4])
     u64 *d = ctx->tmp64.as<u64>() + 8;              // [8..11]: the four sums ([0..7] is the scratch of allreduce_u64)
     CK(cudaMemsetAsync(d, 0, 32, st));
     const u64 R = ctx->sz.reliable;
-    // the reliable list is replicated on every GPU: one rank contributes it
-    if (R && ctx->comm.rank == 0) { k_digest_kmers<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), R, d); CKL(); LAUNCHED(ctx); }
+    // the reliable list: every GPU's own share (super-k-mer path on several GPUs), else replicated: one rank contributes it
+    if (ctx->kmers_distributed) { if (ctx->R_local) { k_digest_kmers<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), ctx->R_local, d); CKL(); LAUNCHED(ctx); } }
+    else if (R && ctx->comm.rank == 0) { k_digest_kmers<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_cnt_s.as<u32>(), R, d); CKL(); LAUNCHED(ctx); }
     if (ctx->phase >= 3 && ctx->n) { k_digest_A<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->a_rowptr.as<int64_t>(), ctx->a_col.as<u32>(), ctx->a_pos.as<u32>(), ctx->n, (u64)ctx->read_id_offset, d + 1); CKL(); LAUNCHED(ctx); }
     if (ctx->phase >= 4 && ctx->b_rows) { k_digest_B<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->b_rowptr.as<int64_t>(), ctx->b_col.as<u32>(), ctx->b_num.as<int32_t>(), ctx->b_seeds.as<u32>(), ctx->b_rows,
                                                 (u64)ctx->op.row0, (u64)ctx->op.col0, d + 2, d + 3); CKL(); LAUNCHED(ctx); }
@@ -1391,6 +1526,21 @@ int elba_fe_get_kmers(elba_fe_ctx *ctx, uint64_t *kmer, uint32_t *count)
     if (!ctx) return ELBA_FE_ERR_INVALID;
     if (ctx->phase < 2) return fail(ctx, ELBA_FE_ERR_STATE, "no counts yet");
     u64 R = ctx->sz.reliable;
+    if (ctx->kmers_distributed)
+    {
+        // several GPUs, super-k-mer path: every GPU holds the k-mers it owns (sorted) with their global column ids; the whole
+        // list is assembled on request (COLLECTIVE): all-gather of the counts and ids, then every entry goes to its rank
+        const int W = ctx->comm.nranks; cudaStream_t st = ctx->stream; int rc;
+        CK(ctx->glob_key.ensure(8 * std::max<u64>(R, 1))); CK(ctx->glob_cnt.ensure(4 * std::max<u64>(R, 1)));
+        CK(ctx->glob_gid.ensure(4 * std::max<u64>(R, 1))); CK(ctx->glob_cnt_in.ensure(4 * std::max<u64>(R, 1)));
+        if ((rc = allgatherv(ctx, ctx->rel_gid.p, ctx->glob_gid.p, ctx->rel_counts, 4))) return rc;
+        if ((rc = allgatherv(ctx, ctx->rel_cnt_s.p, ctx->glob_cnt_in.p, ctx->rel_counts, 4))) return rc;
+        (void)W;
+        if (R) { k_place_by_id<<<nblk(R, 256), 256, 0, st>>>(ctx->rel_all_key.as<u64>(), ctx->glob_cnt_in.as<u32>(), ctx->glob_gid.as<u32>(), R, ctx->glob_key.as<u64>(), ctx->glob_cnt.as<u32>()); CKL(); LAUNCHED(ctx); }
+        D2H(kmer, ctx->glob_key.p, 8 * R); D2H(count, ctx->glob_cnt.p, 4 * R);
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
     D2H(kmer, ctx->rel_key_s.p, 8 * R); D2H(count, ctx->rel_cnt_s.p, 4 * R);
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;

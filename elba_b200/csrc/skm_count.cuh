@@ -32,6 +32,25 @@ struct __align__(16) Seed { u32 id, pos, read, pad; };
 static constexpr u32 SEED_HOLE = 0xFFFFFFFFu;
 struct SeedSink2 { Seed *out; u64 *cursor; u64 cap; };
 
+// Records of the buckets this GPU counts.  Bucket b has one sub-slab per source GPU (one GPU: one source):
+// slab[(b * nsrc + s) * rcap ...] holds min(records offered by s, rcap) records in the order of their slots, and
+// fill[s * nb + b] = (instances offered << 32) | records offered by source s (the scatter's reservation word, superkmer.cuh).
+// plan[b] = the same summed over the sources, records = PLAN_SPILL if a source was offered more than rcap (one GPU: plan == fill).
+struct RecSlabs { const SkmRec *slab; const u64 *fill; const u64 *plan; u32 rcap, nsrc, nb; };
+struct RecOverflow { SkmRec *list; u64 *cursor; u64 *inst; u64 cap; };
+static constexpr u32 PLAN_SPILL = 0xFFFFFFFFu;
+
+// several GPUs: plan[b] from the W fill words the sources sent
+__global__ void k_skm_plan(const u64 *__restrict__ fill, u32 nb, u32 nsrc, u32 rcap, u64 *__restrict__ plan)
+{
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    u64 rec = 0, inst = 0; bool spill = false;
+    for (u32 s = 0; s < nsrc; ++s) { const u64 fw = fill[(u64)s * nb + b]; const u32 f = (u32)fw; spill |= f > rcap; rec += f; inst += fw >> 32; }
+    if (rec >= PLAN_SPILL || inst >= (1ull << 32)) spill = true;
+    plan[b] = spill ? ((u64)(u32)min(inst, (u64)0xFFFFFFFFull) << 32) | PLAN_SPILL : (inst << 32) | rec;
+}
+
 static constexpr u32 SK4_CHUNK = 16384;          // entries of a CTA-private chunk of the reliable list / of the seed list
 static constexpr u32 SK4_MAXPROBE = 48;          // probes after which a table counts as too full
 
@@ -113,33 +132,65 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
     const u64 kmask = (k == 32) ? ~0ull : (~0ull << lsh);
     const u32 a_rec = smem_u32(s_rec), a_key = smem_u32(s_key), a_cnt = smem_u32(s_cnt), a_pool = smem_u32(s_pool), a_pn = smem_u32(&s_pool_n);
     u32 my_distinct = 0, my_rel = 0; u64 my_sum = 0;
+    __shared__ u32 s_src_rec[SK_MAXW + 1], s_src_inst[SK_MAXW + 1];               // prefix sums of the sources' records / instances in this bucket
     u32 b = blockIdx.x;
-    u64 fw_cur = b < nb ? __ldg(in.fill + b) : 0ull;
-    u64 fw_nxt = (u64)b + G < nb ? __ldg(in.fill + b + G) : 0ull;
+    u64 fw_cur = b < nb ? __ldg(in.plan + b) : 0ull;
+    u64 fw_nxt = (u64)b + G < nb ? __ldg(in.plan + b + G) : 0ull;
     if (tid == 0)
     {
         s_rel_used = SK4_CHUNK; s_seed_used = SK4_CHUNK; s_rel_base = 0; s_seed_base = 0; s_full = 0; s_pool_n = 0;      // no chunk yet
         mbar_init(s_bar, 1);
     }
     __syncthreads();
-    // does the CTA count the bucket with this fill word in shared memory?  (uniform)
-    auto fits = [&](u64 fw) { const u32 f = (u32)fw, tot = (u32)(fw >> 32); return f != 0 && f <= in.rcap && f <= (u32)RMAX && tot <= CAP; };
+    // does the CTA count the bucket with this plan word in shared memory?  (uniform)
+    const u32 fmax = in.nsrc == 1 ? min(in.rcap, (u32)RMAX) : (u32)RMAX;
+    auto fits = [&](u64 fw) { const u32 f = (u32)fw, tot = (u32)(fw >> 32); return f != 0 && f <= fmax && tot <= CAP; };
+    // thread 0: bring bucket bb (plan word fw) into shared memory, one bulk copy per source, all completing on the mbarrier
+    auto fetch = [&](u64 bb, u64 fw)
+    {
+        mbar_expect_tx(s_bar, (u32)fw * 32u);
+        if (in.nsrc == 1)
+        {
+            s_src_rec[0] = 0; s_src_inst[0] = 0; s_src_rec[1] = (u32)fw; s_src_inst[1] = (u32)(fw >> 32);
+            bulk_g2s(s_rec, in.slab + bb * in.rcap, (u32)fw * 32u, s_bar);
+        }
+        else
+        {
+            u32 nr = 0, ni = 0;
+            for (u32 sidx = 0; sidx < in.nsrc; ++sidx)
+            {
+                const u64 w = __ldg(in.fill + (u64)sidx * in.nb + bb);
+                s_src_rec[sidx] = nr; s_src_inst[sidx] = ni;
+                if ((u32)w) bulk_g2s(s_rec + nr, in.slab + (bb * in.nsrc + sidx) * in.rcap, (u32)w * 32u, s_bar);
+                nr += (u32)w; ni += (u32)(w >> 32);
+            }
+            s_src_rec[in.nsrc] = nr; s_src_inst[in.nsrc] = ni;
+        }
+    };
+    auto prefetch = [&](u64 bb, u64 fw)
+    {
+        if (in.nsrc == 1) { bulk_prefetch_l2(in.slab + bb * in.rcap, (u32)fw * 32u); return; }
+        for (u32 sidx = 0; sidx < in.nsrc; ++sidx)
+        {
+            const u32 fs = (u32)__ldg(in.fill + (u64)sidx * in.nb + bb);
+            if (fs) bulk_prefetch_l2(in.slab + (bb * in.nsrc + sidx) * in.rcap, fs * 32u);
+        }
+    };
     if (tid == 0)
     {
-        if (fits(fw_cur)) { const u32 bytes = (u32)fw_cur * 32u; mbar_expect_tx(s_bar, bytes); bulk_g2s(s_rec, in.slab + (u64)b * in.rcap, bytes, s_bar); }
-        if (fits(fw_nxt)) bulk_prefetch_l2(in.slab + (u64)(b + G) * in.rcap, (u32)fw_nxt * 32u);
+        if (fits(fw_cur)) fetch(b, fw_cur);
+        if (fits(fw_nxt)) prefetch((u64)b + G, fw_nxt);
     }
     u32 parity = 0;
 #pragma unroll 1
     for (; b < nb; b += G)
     {
-        const u64 fw_nn = (u64)b + 2ull * G < nb ? __ldg(in.fill + b + 2u * G) : 0ull;
+        const u64 fw_nn = (u64)b + 2ull * G < nb ? __ldg(in.plan + b + 2u * G) : 0ull;
         const u32 f = (u32)fw_cur, total = (u32)(fw_cur >> 32);
         const bool here = fits(fw_cur);
         bool late_spill = false;
         if (here)
         {
-            const u32 nrec = f;
             // room for this bucket in the CTA's chunks (worst case: every slot of the table reliable / every instance a seed)
             if (tid == 0)
             {
@@ -188,12 +239,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
             u32 ra = a_rec, j = 0, n = 0; u64 x = 0, y = 0;               // ra: shared address of my current record
             if (nv)
             {
-                u32 lo = 0, hi = nrec;                                     // first(lo) <= i0 < first(hi)
+                u32 src = 0;                                               // the source whose records hold instance i0
+                while (i0 >= s_src_inst[src + 1]) ++src;
+                const u32 il = i0 - s_src_inst[src];                       // instance inside that source's sub-slab
+                u32 lo = s_src_rec[src], hi = s_src_rec[src + 1];          // first(lo) <= il < first(hi)
 #pragma unroll 1
-                while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if ((u32)(lds_u64(a_rec + mid * 32u + 24u) >> 8) <= i0) lo = mid; else hi = mid; }
+                while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if ((u32)(lds_u64(a_rec + mid * 32u + 24u) >> 8) <= il) lo = mid; else hi = mid; }
                 ra = a_rec + lo * 32u;
                 lds_v2u64(ra, x, y);
-                n = ((u32)y & 31u) + 1u; j = i0 - (u32)(lds_u64(ra + 24u) >> 8);
+                n = ((u32)y & 31u) + 1u; j = il - (u32)(lds_u64(ra + 24u) >> 8);
             }
 #pragma unroll 1
             for (u32 g = 0; g < c; g += 2)                                 // c is uniform: the warp stays converged at the loop head
@@ -293,12 +347,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
         if (!here || late_spill)
         {
             // the bucket goes to the exact fallback, whole: too many records / instances, or too many distinct k-mers
-            const u32 nrec = min(f, in.rcap);
-            if (nrec)
+#pragma unroll 1
+            for (u32 sidx = 0; sidx < in.nsrc; ++sidx)
             {
+                const u32 nrec = min((u32)__ldg(in.fill + (u64)sidx * in.nb + b), in.rcap);
+                if (nrec == 0) continue;                                   // uniform
                 if (tid == 0) s_spill_base = atomicAdd(ovf.cursor, (u64)nrec);
                 __syncthreads();
-                const SkmRec *__restrict__ recs = in.slab + (u64)b * in.rcap;
+                const SkmRec *__restrict__ recs = in.slab + ((u64)b * in.nsrc + sidx) * in.rcap;
                 u32 ninst = 0;
 #pragma unroll 1
                 for (u32 rr = tid; rr < nrec; rr += THREADS)
@@ -310,6 +366,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
                 }
                 for (int o = 16; o; o >>= 1) ninst += __shfl_xor_sync(0xffffffffu, ninst, o);
                 if (lane == 0 && ninst) atomicAdd(ovf.inst, (u64)ninst);
+                __syncthreads();
             }
         }
         __syncthreads();                                                   // (4) table, records, pool and chunk state are free
@@ -318,12 +375,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
         {
             s_full = 0; s_pool_n = 0;
             const u64 bn = (u64)b + G;
-            if (bn < nb && fits(fw_cur))
-            {
-                fence_async_smem();
-                const u32 bytes = (u32)fw_cur * 32u; mbar_expect_tx(s_bar, bytes); bulk_g2s(s_rec, in.slab + bn * in.rcap, bytes, s_bar);
-            }
-            if (bn + G < nb && fits(fw_nxt)) bulk_prefetch_l2(in.slab + (bn + G) * in.rcap, (u32)fw_nxt * 32u);
+            if (bn < nb && fits(fw_cur)) { fence_async_smem(); fetch(bn, fw_cur); }
+            if (bn + G < nb && fits(fw_nxt)) prefetch(bn + G, fw_nxt);
         }
     }
     // the unused tails of the CTA's last chunks are holes
@@ -457,6 +510,35 @@ __global__ void k_rank_finish(const u32 *__restrict__ idx_sorted, const u32 *__r
     cnt_sorted[r] = cnt_list[i];
 }
 
+// several GPUs: every GPU sorted the reliable k-mers it owns; all[off[r] ...] is rank r's sorted run (all-gathered).  The
+// column id of my k-mer = its rank in my run + the number of smaller k-mers in every other run (k-mers are distinct
+// across the runs: a k-mer has one owner).  Consecutive threads search neighbouring keys: the probes hit L1 / L2.
+struct RankRuns { u64 off[SK_MAXW]; u64 n[SK_MAXW]; u32 nruns, me; };
+__global__ void __launch_bounds__(256) k_rank_global(const u64 *__restrict__ mine, const u32 *__restrict__ idx_sorted, const u32 *__restrict__ cnt_list, u64 n_mine,
+                                                     const u64 *__restrict__ all, RankRuns runs, u32 *__restrict__ perm, u32 *__restrict__ cnt_sorted, u32 *__restrict__ gid)
+{
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_mine) return;
+    const u64 key = mine[r];
+    u64 g = r;
+    for (u32 q = 0; q < runs.nruns; ++q)
+    {
+        if (q == runs.me) continue;
+        const u64 *__restrict__ run = all + runs.off[q];
+        u64 lo = 0, hi = runs.n[q];
+        while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (__ldg(run + mid) < key) lo = mid + 1; else hi = mid; }
+        g += lo;
+    }
+    const u32 i = idx_sorted[r];
+    perm[i] = (u32)g; gid[r] = (u32)g; cnt_sorted[r] = cnt_list[i];
+}
+
+__global__ void k_place_by_id(const u64 *__restrict__ key, const u32 *__restrict__ cnt, const u32 *__restrict__ gid, u64 n, u64 *__restrict__ okey, u32 *__restrict__ ocnt)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const u32 g = gid[i]; okey[g] = key[i]; ocnt[g] = cnt[i]; }
+}
+
 // seeds -> sort keys (read << col_bits | column) and positions; holes get `hole_key` (sorted behind every entry)
 __global__ void __launch_bounds__(256) k_seed_keys(const Seed *__restrict__ seeds, u64 n, const u32 *__restrict__ perm, u32 id_base, int col_bits, u64 hole_key,
                                                    u64 *__restrict__ out_key, u32 *__restrict__ out_pos, u64 *__restrict__ nvalid)
@@ -472,6 +554,71 @@ __global__ void __launch_bounds__(256) k_seed_keys(const Seed *__restrict__ seed
     }
     for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(nvalid, (u64)mine);
+}
+
+// ---- several GPUs: the k-mer owners send (global read, column, pos) to the read owners through peer memory ----------
+// key[r] / pos[r] / cnt[r]: rank r's receive window, mapped here; region [source][cap].  first[r]: the first global read id of
+// rank r's block (first[nranks] = one past the last read).  cursor: local, one per destination.
+struct RouteSink { u64 *key[SK_MAXW]; u32 *pos[SK_MAXW]; u64 *cnt[SK_MAXW]; u64 first[SK_MAXW + 1]; u64 *cursor; u64 cap; u32 nranks, me; };
+
+__global__ void __launch_bounds__(256) k_seed_route(const Seed *__restrict__ seeds, u64 n, const u32 *__restrict__ perm, RouteSink rs)
+{
+    __shared__ u32 s_cnt[SK_MAXW];
+    __shared__ u64 s_base[SK_MAXW];
+    const u64 tile = (u64)blockDim.x * 4;
+    for (u64 t0 = (u64)blockIdx.x * tile; t0 < n; t0 += (u64)gridDim.x * tile)
+    {
+        if (threadIdx.x < SK_MAXW) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint4 sd[4]; u32 dst[4], slot[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const u64 idx = t0 + (u64)i * blockDim.x + threadIdx.x;
+            sd[i] = make_uint4(SEED_HOLE, 0, 0, 0);
+            if (idx < n) sd[i] = __ldcs(reinterpret_cast<const uint4*>(seeds + idx));
+            dst[i] = 0xFFFFFFFFu; slot[i] = 0;
+            if (sd[i].x != SEED_HOLE)
+            {
+                u32 d = 0;
+                while (d + 1 < rs.nranks && (u64)sd[i].z >= rs.first[d + 1]) ++d;      // owner of the read: the blocks are consecutive
+                dst[i] = d;
+                slot[i] = atomicAdd(&s_cnt[d], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < rs.nranks) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(rs.cursor + threadIdx.x, (u64)s_cnt[threadIdx.x]) : 0ull;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (dst[i] != 0xFFFFFFFFu)
+            {
+                const u64 o = s_base[dst[i]] + slot[i];
+                if (o < rs.cap)
+                {
+                    const u64 at = (u64)rs.me * rs.cap + o;
+                    rs.key[dst[i]][at] = ((u64)sd[i].z << 32) | __ldg(perm + sd[i].x);
+                    rs.pos[dst[i]][at] = sd[i].y;
+                }
+            }
+        __syncthreads();
+    }
+    __threadfence_system();
+}
+// after the route kernel: every destination learns how many triples this source stored for it
+__global__ void k_route_publish(RouteSink rs)
+{
+    if (threadIdx.x < rs.nranks) rs.cnt[threadIdx.x][rs.me] = rs.cursor[threadIdx.x];
+    __threadfence_system();
+}
+// the received triples of one source -> sort keys with LOCAL read ids (read << col_bits | column)
+__global__ void k_route_unpack(const u64 *__restrict__ key, const u32 *__restrict__ pos, u64 n, u64 read0, int col_bits, u64 *__restrict__ out_key, u32 *__restrict__ out_pos)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 kk = key[i];
+    out_key[i] = (((kk >> 32) - read0) << col_bits) | (kk & 0xFFFFFFFFull);
+    out_pos[i] = pos[i];
 }
 
 } // namespace elba

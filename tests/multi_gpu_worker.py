@@ -20,6 +20,7 @@ def main():
     fixture, k, lo, up = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     grid = tuple(int(x) for x in sys.argv[5].split("x")) if len(sys.argv) > 5 and sys.argv[5] != "-" else None
     parts = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+    base = int(sys.argv[7]) if len(sys.argv) > 7 else 0      # global id of the first read of rank 0 (the ids need not start at 0)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -32,14 +33,17 @@ def main():
     mine, first = D.local_reads(dna, rank, world)
     ctx = frontend.Context(frontend.Params(k=k, lower=lo, upper=up, device=local, num_partitions=parts))
     D.bootstrap_comm(ctx, dist, device=torch.device("cuda", local), grid=grid)
-    ctx.upload(mine, first)
+    ctx.upload(mine, first + base)
     ctx.run()
     info = ctx.comm_info()
     sizes, gsizes = ctx.sizes(), ctx.sizes_global()
     kmers, counts = ctx.kmers()
     arp, acol, apos = ctx.A()
     trip = ctx.B_triples()
-    payload = dict(rank=rank, info=info, sizes=sizes, kmers=kmers, counts=counts, A=(arp, acol, apos), first=first, n=mine.size(), B=trip, timings=ctx.timings())
+    digests = ctx.digests()
+    trip = (trip[0] - base, trip[1] - base, trip[2], trip[3])
+    info = dict(info, row0=info["row0"] - base, col0=info["col0"] - base)
+    payload = dict(rank=rank, info=info, sizes=sizes, digests=digests, kmers=kmers, counts=counts, A=(arp, acol, apos), first=first, n=mine.size(), B=trip, timings=ctx.timings())
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(payload, gathered, dst=0)
     ok = True
@@ -72,6 +76,11 @@ def main():
             assert np.array_equal(brp, ref.b_rowptr) and np.array_equal(bcol, ref.b_col), "pattern of B"
             assert np.array_equal(bnum, ref.b_num), "numshared"
             assert np.array_equal(bseeds, ref.b_seeds), "seeds"
+            if base == 0:
+                from common import oracle_result_digests
+                want = oracle_result_digests(ref)
+                for g in gathered:
+                    assert g["digests"] == want, ("device digests", g["rank"], g["digests"], want)
             print(f"MULTI-GPU PARITY OK world={world} grid={pr}x{pc} N={dna.size()} R={ref.R} nnzB={ref.nnzB} "
                   f"exchange_ms={[round(g['timings']['exchange_ms'], 3) for g in gathered]}", flush=True)
         except AssertionError as e:

@@ -51,3 +51,21 @@ def test_multi_gpu_superkmer_other_geometries(world):
         pytest.skip(f"needs {world} GPUs")
     _launch(world, ["synth:200000,300,9000,0.02", 25, 2, 6, "-"], 29671 + world)
     _launch(world, ["reads_fa", 21, 2, 8, "-"], 29681 + world)
+
+
+@pytest.mark.parametrize("world,grid", [(2, "-"), (4, "2x2")])
+def test_multi_gpu_nonzero_first_read_id(world, grid):
+    """The global read ids need not start at 0 (elba_fe_upload_reads takes any offset for rank 0)."""
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _launch(world, ["synth:200000,300,9000,0.02", 31, 2, 4, grid, 0, 1000], 29691 + world)
+    _launch(world, ["reads_fa", 17, 2, 8, grid, 0, 77], 29695 + world)
+
+
+@pytest.mark.parametrize("world", [2])
+def test_multi_gpu_without_peer_memory(world):
+    """ELBA_FE_P2P=0: the super-k-mer path needs peer access between the GPUs; without it every k falls back to the hash path
+    with its NCCL all-to-all.  Same bits."""
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _launch(world, ["synth:300000,500,12000,0.01", 31, 2, 4, "-", 16], 29699 + world, env={"ELBA_FE_P2P": "0"})

@@ -77,7 +77,7 @@ struct elba_fe_ctx
     u64 skm_reliable = 0;                                // super-k-mer path: reliable k-mers among the (holey) list entries handed out
     // several GPUs, super-k-mer path: every GPU parses its own reads and writes the records into the owners' slabs (peer memory)
     Window w_slab, w_ovf, w_octr, w_rkey, w_rpos, w_rcnt;     // record slabs, overflow list + its counters, routed seed triples + their counts
-    DevBuf skm_fillin, skm_plan, d_roff, route_cur, rel_gid, glob_key, glob_cnt, glob_gid, glob_cnt_in;
+    DevBuf skm_fillin, skm_plan, skm_stage, d_roff, route_cur, rel_gid, glob_key, glob_cnt, glob_gid, glob_cnt_in;
     std::vector<u64> roff;                                   // [W + 1] first global read id of every rank's block
     int64_t read_base0 = 0;                                  // global id of the first read of rank 0
     bool p2p = false, kmers_distributed = false; u64 R_local = 0; std::vector<u64> rel_counts;
@@ -88,7 +88,7 @@ struct elba_fe_ctx
     u32 lut_slots = 0; u64 rel_cap = 0; u32 filter_words = 0; u64 cand_cap = 0;
     // A
     DevBuf seed_key, seed_pos, seed_key2, seed_pos2, idx, a_key, a_rowptr, a_col, a_pos, at_key, at_key2, at_pos2, at_colptr, at_row, at_pos, prod;
-    int col_bits = 1, read_bits = 1;
+    int col_bits = 1, read_bits = 1; bool at_built = false;
     // B
     DevBuf sp_ptr, sp_ent;               // the right operand as the SpGEMM reads it (k_spgemm_operand)
     DevBuf xd_flag, xd_rowof, xd_prow, xd_pcol, xd_sq, xd_st, xd_nz, xd_out, xd_scratch, xd_max;      // elba_fe_align
@@ -106,6 +106,7 @@ struct elba_fe_ctx
     elba_fe_sizes_t sz;
     elba_fe_timings_t tm;
     cudaEvent_t ev[8];
+    bool trace = false; std::vector<std::pair<const char*, cudaEvent_t>> marks; size_t marks_used = 0;      // ELBA_FE_TRACE=1: sub-phase device times on stderr
     std::vector<EventPair> kev; size_t kev_used = 0;      // per-kernel event pairs (count kernels)
     std::vector<EventPair> sev; size_t sev_used = 0;      // spgemm numeric kernels
     std::vector<EventPair> pev; size_t pev_used = 0;      // partition kernels
@@ -166,6 +167,28 @@ int sort_pairs(elba_fe_ctx *ctx, const u64 *kin, u64 *kout, const u32 *vin, u32 
 }
 
 int grid_for(elba_fe_ctx *c, int per_sm) { return c->sm_count * per_sm; }
+
+// ELBA_FE_TRACE=1: record a named point of the stream; trace_flush prints the device time between consecutive points
+void mark(elba_fe_ctx *c, const char *name)
+{
+    if (!c->trace) return;
+    if (c->marks_used == c->marks.size()) { cudaEvent_t e; cudaEventCreate(&e); c->marks.push_back({name, e}); }
+    c->marks[c->marks_used].first = name;
+    cudaEventRecord(c->marks[c->marks_used++].second, c->stream);
+}
+void trace_flush(elba_fe_ctx *c, const char *phase)
+{
+    if (!c->trace || c->marks_used < 2) { c->marks_used = 0; return; }
+    cudaStreamSynchronize(c->stream);
+    std::string line = std::string("[elba_fe trace] rank ") + std::to_string(c->comm.rank) + " " + phase + ":";
+    for (size_t i = 1; i < c->marks_used; ++i)
+    {
+        float ms = 0; cudaEventElapsedTime(&ms, c->marks[i - 1].second, c->marks[i].second);
+        char b[96]; snprintf(b, sizeof b, " %s %.3f", c->marks[i].first, ms); line += b;
+    }
+    fprintf(stderr, "%s\n", line.c_str());
+    c->marks_used = 0;
+}
 
 // after the reads are resident: per-read tables and totals
 int prepare_reads(elba_fe_ctx *ctx)
@@ -252,6 +275,7 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreate(&ctx->ev_x0); cudaEventCreate(&ctx->ev_x1); cudaEventCreate(&ctx->xd_e0); cudaEventCreate(&ctx->xd_e1);
     if (ctx->tmp64.ensure(8192) != cudaSuccess || ctx->ctr.ensure(128) != cudaSuccess) { elba_fe_destroy(ctx); return fail(nullptr, ELBA_FE_ERR_OOM, "cudaMalloc failed"); }
+    if (const char *e = getenv("ELBA_FE_TRACE")) ctx->trace = atoi(e) != 0;
     if (const char *e = getenv("ELBA_FE_SCRATCH_MB")) { long v = atol(e); if (v >= 8 && v <= 65536) ctx->scratch_mb = (u64)v; }
     // opt in to large dynamic shared memory
     cudaFuncSetAttribute(k_scatter1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S1_TILE + 2 * sizeof(u32) * MAX_P1));
@@ -274,7 +298,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut, &ctx->filter,
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
-        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->skm_fillin, &ctx->skm_plan, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
+        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf, &ctx->seeds, &ctx->perm, &ctx->rel_idx, &ctx->rel_idx_s,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
@@ -379,12 +403,20 @@ static int allgather_u64(elba_fe_ctx *ctx, u64 mine, std::vector<u64> &all)
 // every rank contributes count[r] elements of `esize` bytes; recv holds them in rank order
 static int allgatherv(elba_fe_ctx *ctx, const void *send, void *recv, const std::vector<u64> &count, size_t esize)
 {
-    const int W = ctx->comm.nranks;
+    // every rank sends its block to every other rank and receives theirs: W - 1 point-to-point transfers in each direction in
+    // one group (NVSwitch gives every pair full bandwidth); the own block is a local copy
+    const int W = ctx->comm.nranks, me = ctx->comm.rank;
+    u64 off = 0, myoff = 0;
+    for (int r = 0; r < me; ++r) myoff += count[r];
+    if (count[me]) CK(cudaMemcpyAsync((char*)recv + myoff * esize, send, count[me] * esize, cudaMemcpyDeviceToDevice, ctx->stream));
     NC(ctx->comm.api->GroupStart());
-    u64 off = 0;
     for (int r = 0; r < W; ++r)
     {
-        if (count[r]) NC(ctx->comm.api->Broadcast(send, (char*)recv + off * esize, count[r] * esize, ncclUint8, r, ctx->comm.comm, ctx->stream));
+        if (r != me)
+        {
+            if (count[me]) NC(ctx->comm.api->Send(send, count[me] * esize, ncclUint8, r, ctx->comm.comm, ctx->stream));
+            if (count[r]) NC(ctx->comm.api->Recv((char*)recv + off * esize, count[r] * esize, ncclUint8, r, ctx->comm.comm, ctx->stream));
+        }
         off += count[r];
     }
     NC(ctx->comm.api->GroupEnd());
@@ -555,7 +587,7 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     if ((rc = window_ensure(ctx, ctx->w_ovf, sizeof(SkmRec) * ovf_cap))) return rc;
     if ((rc = window_ensure(ctx, ctx->w_octr, 64))) return rc;
     CK(ctx->skm_fill.ensure(sizeof(u64) * NBg));
-    if (W > 1) { CK(ctx->skm_fillin.ensure(sizeof(u64) * NBg)); CK(ctx->skm_plan.ensure(sizeof(u64) * NB)); }
+    if (W > 1) { CK(ctx->skm_fillin.ensure(sizeof(u64) * NBg)); CK(ctx->skm_plan.ensure(sizeof(u64) * NB)); CK(ctx->skm_stage.ensure(sizeof(SkmRec) * NBg * rcap)); }
     ctx->skm_ovf_cap = ovf_cap;
     u64 *d_octr = ctx->w_octr.buf.as<u64>();                              // [0] records, [1] instances in my overflow list
     // seed list: {list index, pos, read} of every instance of a reliable k-mer; the size of the last pass, else a guess
@@ -572,11 +604,13 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     // several GPUs: nobody writes into a slab (or bumps an overflow counter) that its owner still reads from the previous pass
     if ((rc = stream_barrier(ctx))) return rc;
     RecSink sink; std::memset(&sink, 0, sizeof sink);
-    for (int r = 0; r < W; ++r) { sink.slab[r] = (SkmRec*)ctx->w_slab.peer[r]; sink.ovf[r] = (SkmRec*)ctx->w_ovf.peer[r]; sink.ovf_ctr[r] = (u64*)ctx->w_octr.peer[r]; }
+    for (int r = 0; r < W; ++r) { sink.ovf[r] = (SkmRec*)ctx->w_ovf.peer[r]; sink.ovf_ctr[r] = (u64*)ctx->w_octr.peer[r]; }
+    sink.slab = ctx->w_slab.buf.as<SkmRec>(); sink.stage = ctx->skm_stage.as<SkmRec>();
     sink.fill = ctx->skm_fill.as<u64>(); sink.rcap = (u32)rcap; sink.nb_own = (u32)NB; sink.nsrc = (u32)W; sink.me = (u32)me;
     sink.read_base = plan.read_base; sink.ovf_cap = ovf_cap;
     if (W > 1) CK(cudaEventRecord(ctx->ev_x0, st));
     const u32 nmax = skm_nmax(k);
+    mark(ctx, "setup");
     EventPair &pp = next_pair(ctx->pev, ctx->pev_used);
     CK(cudaEventRecord(pp.a, st));
     if (rv.nchunks)
@@ -600,9 +634,16 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
         CKL(); LAUNCHED(ctx);
     }
     CK(cudaEventRecord(pp.b, st));
+    mark(ctx, "scatter");
     RecSlabs in; in.slab = ctx->w_slab.buf.as<SkmRec>(); in.fill = ctx->skm_fill.as<u64>(); in.plan = in.fill; in.rcap = (u32)rcap; in.nsrc = (u32)W; in.nb = (u32)NB;
     if (W > 1)
     {
+        // the staged records of the other GPUs' buckets go into their owners' slabs through peer memory
+        RecForward fw; std::memset(&fw, 0, sizeof fw);
+        for (int r = 0; r < W; ++r) fw.slab[r] = (SkmRec*)ctx->w_slab.peer[r];
+        fw.stage = ctx->skm_stage.as<SkmRec>(); fw.fill = ctx->skm_fill.as<u64>(); fw.rcap = (u32)rcap; fw.nb_own = (u32)NB; fw.nsrc = (u32)W; fw.me = (u32)me;
+        k_skm_forward<<<grid_for(ctx, 8), 256, 0, st>>>(fw); CKL(); LAUNCHED(ctx);
+        mark(ctx, "forward");
         // the reservation words follow the records: rank d gets, from every source, the fill words of its own buckets.  Stream
         // order makes this exchange the barrier behind the peer-memory stores of the scatter.
         NC(ctx->comm.api->GroupStart());
@@ -616,6 +657,7 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
         k_skm_plan<<<nblk(NB, 256), 256, 0, st>>>(ctx->skm_fillin.as<u64>(), (u32)NB, (u32)W, (u32)rcap, ctx->skm_plan.as<u64>()); CKL(); LAUNCHED(ctx);
         k_remote_records<<<grid_for(ctx, 2), 256, 0, st>>>(ctx->skm_fill.as<u64>(), NBg, (u32)NB, (u32)me, d_ctr + 9); CKL(); LAUNCHED(ctx);
         in.fill = ctx->skm_fillin.as<u64>(); in.plan = ctx->skm_plan.as<u64>();
+        mark(ctx, "fill_exchange");
     }
     RecOverflow ovf; ovf.list = ctx->w_ovf.buf.as<SkmRec>(); ovf.cursor = d_octr; ovf.inst = d_octr + 1; ovf.cap = ovf_cap;
     EventPair &ep = next_pair(ctx->kev, ctx->kev_used);
@@ -627,6 +669,7 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     }
     CKL(); LAUNCHED(ctx);
     CK(cudaEventRecord(ep.b, st));
+    mark(ctx, "count_kernel");
     u64 o[2] = {0, 0};
     CK(cudaMemcpyAsync(o, d_octr, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -650,6 +693,7 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
         k_skm4_collect_global<<<grid_for(ctx, 8), 256, 0, st>>>(T.tab, T.slots, lower, upper, ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap); CKL(); LAUNCHED(ctx);
         k_skm4_emit_global<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->w_ovf.buf.as<SkmRec>(), d_octr, ovf_cap, k, T, lower, upper, seeds); CKL(); LAUNCHED(ctx);
     }
+    mark(ctx, "fallback");
     ctx->seeds_fused = false;
     {
         // [0] list entries handed out (chunks with holes + what the fallback appended), [1] sum of reliable counts, [2] distinct,
@@ -686,6 +730,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
     ReadsView rv = view(ctx);
     CK(cudaEventRecord(ctx->ev[2], st));
     ctx->seeds_fused = false;
+    mark(ctx, "begin");
 
     // counters: [0] R cursor, [1] sum of reliable counts, [2] distinct, [3] (u32) table-overflow flag, [4] (u32) level-1 overflow flag
     CK(ctx->ctr.ensure(128));
@@ -977,19 +1022,22 @@ int elba_fe_count(elba_fe_ctx *ctx)
         if (R_list) { k_iota_u32<<<nblk(R_list, 256), 256, 0, st>>>(ctx->rel_idx.as<u32>(), R_list); CKL(); LAUNCHED(ctx); }
         int rc1 = sort_pairs(ctx, rk, ctx->rel_key_s.as<u64>(), ctx->rel_idx.as<u32>(), ctx->rel_idx_s.as<u32>(), R_list, 64 - 2 * k, 64);
         if (rc1) return rc1;
+        mark(ctx, "sort_own_kmers");
         if ((rc1 = allgather_u64(ctx, Rl, ctx->rel_counts))) return rc1;
         u64 Rt = 0; for (u64 v : ctx->rel_counts) Rt += v;
         if (Rt >= 0xFFFFFFFFull) return fail(ctx, ELBA_FE_ERR_INVALID, "more than 2^32 reliable k-mers");
         CK(ctx->rel_all_key.ensure(8 * std::max<u64>(Rt, 1)));
         if ((rc1 = allgatherv(ctx, ctx->rel_key_s.p, ctx->rel_all_key.p, ctx->rel_counts, 8))) return rc1;
+        mark(ctx, "allgather_runs");
         RankRuns runs; std::memset(&runs, 0, sizeof runs);
         { u64 o = 0; for (int r = 0; r < W; ++r) { runs.off[r] = o; runs.n[r] = ctx->rel_counts[r]; o += ctx->rel_counts[r]; } }
         runs.nruns = (u32)W; runs.me = (u32)me;
-        if (Rl) { k_rank_global<<<nblk(Rl, 256), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_idx_s.as<u32>(), rc_, Rl, ctx->rel_all_key.as<u64>(), runs,
+        if (Rl) { k_rank_global<<<nblk(Rl, RG_KEYS), 256, 0, st>>>(ctx->rel_key_s.as<u64>(), ctx->rel_idx_s.as<u32>(), rc_, Rl, ctx->rel_all_key.as<u64>(), runs,
                       ctx->perm.as<u32>(), ctx->rel_cnt_s.as<u32>(), ctx->rel_gid.as<u32>()); CKL(); LAUNCHED(ctx); }
         ctx->R_local = Rl; ctx->kmers_distributed = true; ctx->seed_id_base = 0;
         ctx->sz.reliable = Rt;
         CK(cudaEventRecord(ctx->ev[3], st));
+        mark(ctx, "rank_global"); trace_flush(ctx, "count");
         ctx->phase = 2;
         return 0;
     }
@@ -1044,6 +1092,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
                                                        ctx->filter.as<u64>(), ctx->filter_words); CKL(); LAUNCHED(ctx); }
     }
     CK(cudaEventRecord(ctx->ev[3], st));
+    mark(ctx, "column_ids"); trace_flush(ctx, "count");
     ctx->phase = 2;
     return 0;
 }
@@ -1068,7 +1117,8 @@ static int gather_operands(elba_fe_ctx *ctx)
     if (N) { k_pack_rows<<<nblk((u64)N * 32, 256), 256, 0, st>>>(ctx->a_rowptr.as<int64_t>(), ctx->a_col.as<u32>(), N, (u64)ctx->read_id_offset, ctx->pack_key.as<u64>()); CKL(); LAUNCHED(ctx); }
     if ((rc = allgatherv(ctx, ctx->pack_key.p, ctx->g_key.p, nz, 8))) return rc;
     if ((rc = allgatherv(ctx, ctx->a_pos.p, ctx->g_pos.p, nz, 4))) return rc;
-    ctx->panel_bytes = 12 * (tot - nnzA);
+    ctx->panel_bytes += 12 * (tot - nnzA);
+    mark(ctx, "allgather_A");
     return operands_from_gathered(ctx, tot);
 }
 
@@ -1112,6 +1162,20 @@ static int operands_from_gathered(elba_fe_ctx *ctx, u64 tot)
     return 0;
 }
 
+// A^T of the rows of this GPU: the same entries sorted by (column, read) (src/main.cpp:272-273)
+static int build_local_transpose(elba_fe_ctx *ctx)
+{
+    cudaStream_t st = ctx->stream;
+    const u64 nnzA = ctx->sz.nnzA, R = ctx->sz.reliable;
+    const int cb = ctx->col_bits, rb = ctx->read_bits;
+    int rc;
+    if ((rc = sort_pairs(ctx, ctx->at_key.as<u64>(), ctx->at_key2.as<u64>(), ctx->a_pos.as<u32>(), ctx->at_pos.as<u32>(), nnzA, 0, cb + rb))) return rc;
+    k_segment_ptr<<<nblk(R + 1, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, R, rb, ctx->at_colptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
+    if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, rb, cb, ctx->at_row.as<u32>(), nullptr); CKL(); LAUNCHED(ctx); }
+    ctx->at_built = true;
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 int elba_fe_build_A(elba_fe_ctx *ctx)
 {
@@ -1123,7 +1187,8 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     const u64 R = ctx->sz.reliable; u64 npre = ctx->sz.nnzA_pre; const u32 N = ctx->n;
     const int W = ctx->comm.nranks;
     CK(cudaEventRecord(ctx->ev[4], st));
-    ctx->lev_used = 0;
+    mark(ctx, "begin");
+    ctx->lev_used = 0; ctx->panel_bytes = 0;
     const int cb = bits_for(std::max<u64>(R, 2)), rb = bits_for(std::max<u64>(N, 2));
     ctx->col_bits = cb; ctx->read_bits = rb;
     u64 *d_ctr = ctx->ctr.as<u64>();
@@ -1240,6 +1305,7 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
         CK(ctx->seed_key2.ensure(8 * ns1)); CK(ctx->seed_pos2.ensure(4 * ns1));
     }
 
+    mark(ctx, "seeds_to_triples");
     int rc;
     u64 nnzA = 0;
     // sort by (read, column); merge duplicates keeping the largest position
@@ -1257,16 +1323,18 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     if (npre) { k_dedupe_write<<<nblk(npre, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), ctx->seed_pos2.as<u32>(), ctx->idx.as<u64>(), npre, ctx->a_key.as<u64>(), ctx->a_pos.as<u32>()); CKL(); LAUNCHED(ctx); }
     k_segment_ptr<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, N, cb, ctx->a_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
     if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, cb, rb, ctx->a_col.as<u32>(), ctx->at_key.as<u64>()); CKL(); LAUNCHED(ctx); }
-    // transpose: the same entries sorted by (column, read)
-    if ((rc = sort_pairs(ctx, ctx->at_key.as<u64>(), ctx->at_key2.as<u64>(), ctx->a_pos.as<u32>(), ctx->at_pos.as<u32>(), nnzA, 0, cb + rb))) return rc;
-    k_segment_ptr<<<nblk(R + 1, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, R, rb, ctx->at_colptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
-    if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, rb, cb, ctx->at_row.as<u32>(), nullptr); CKL(); LAUNCHED(ctx); }
+    mark(ctx, "sort_dedupe_csr");
+    // transpose: the same entries sorted by (column, read).  Several GPUs: the right operand of the SpGEMM is built from the
+    // gathered rows (gather_operands); the transpose of the own rows is only made when somebody asks for it (elba_fe_get_AT)
+    ctx->at_built = false;
+    if (W == 1) { if ((rc = build_local_transpose(ctx))) return rc; }
     // operands of B = A (x) A^T: one GPU multiplies A by its own transpose
     ctx->op.l_rowptr = ctx->a_rowptr.as<int64_t>(); ctx->op.l_col = ctx->a_col.as<u32>(); ctx->op.l_pos = ctx->a_pos.as<u32>(); ctx->op.l_rows = N; ctx->op.l_nnz = nnzA;
     ctx->op.r_colptr = ctx->at_colptr.as<int64_t>(); ctx->op.r_row = ctx->at_row.as<u32>(); ctx->op.r_pos = ctx->at_pos.as<u32>();
     ctx->op.r_nnz = nnzA;
     ctx->op.row0 = ctx->op.col0 = ctx->read_id_offset;
-    if (W > 1) { rc = gather_operands(ctx); if (rc) return rc; }
+    mark(ctx, "csc");
+    if (W > 1) { rc = gather_operands(ctx); if (rc) return rc; mark(ctx, "gather_operands"); }
     if (ctx->op.r_nnz >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "the right SpGEMM operand of one GPU exceeds 2^32 entries");
     CK(ctx->sp_ptr.ensure(4 * (R + 2))); CK(ctx->sp_ent.ensure(8 * std::max<u64>(ctx->op.r_nnz, 1)));
     k_spgemm_operand<<<nblk(std::max<u64>(R + 1, ctx->op.r_nnz), 256), 256, 0, st>>>(ctx->op.r_colptr, R, ctx->op.r_row, ctx->op.r_pos, ctx->op.r_nnz,
@@ -1281,6 +1349,7 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaStreamSynchronize(st));
     ctx->sz.products = F;
+    mark(ctx, "spgemm_operand+row_products"); trace_flush(ctx, "build_A");
     ctx->phase = 3;
     return 0;
 }
@@ -1295,6 +1364,7 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
     const u32 N = ctx->op.l_rows; const u64 nnzA = ctx->op.l_nnz;       // rows of this GPU's block of B
     ctx->b_rows = N;
     CK(cudaEventRecord(ctx->ev[6], st));
+    mark(ctx, "begin");
     ctx->sev_used = 0;
     CK(ctx->row_off.ensure(8 * ((size_t)N + 1))); CK(ctx->row_nnz.ensure(4 * ((size_t)N + 1)));
     CK(ctx->small_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->mid_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->big_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->ovf_rows.ensure(4 * ((size_t)N + 1)));
@@ -1368,6 +1438,7 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
         CKL(); LAUNCHED(ctx);
     }
     CK(cudaEventRecord(ctx->ev[7], st));
+    mark(ctx, "spgemm"); trace_flush(ctx, "spgemm");
     ctx->phase = 4;
     return 0;
 }
@@ -1559,6 +1630,7 @@ int elba_fe_get_AT(elba_fe_ctx *ctx, int64_t *colptr, uint32_t *row, uint32_t *p
 {
     if (!ctx) return ELBA_FE_ERR_INVALID;
     if (ctx->phase < 3) return fail(ctx, ELBA_FE_ERR_STATE, "A not built");
+    if (!ctx->at_built) { int rc = build_local_transpose(ctx); if (rc) return rc; }
     D2H(colptr, ctx->at_colptr.p, 8 * (ctx->sz.reliable + 1)); D2H(row, ctx->at_row.p, 4 * ctx->sz.nnzA); D2H(pos, ctx->at_pos.p, 4 * ctx->sz.nnzA);
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -514,23 +514,44 @@ __global__ void k_rank_finish(const u32 *__restrict__ idx_sorted, const u32 *__r
 // column id of my k-mer = its rank in my run + the number of smaller k-mers in every other run (k-mers are distinct
 // across the runs: a k-mer has one owner).  Consecutive threads search neighbouring keys: the probes hit L1 / L2.
 struct RankRuns { u64 off[SK_MAXW]; u64 n[SK_MAXW]; u32 nruns, me; };
+static constexpr int RG_KEYS = 1024;     // keys of my run one CTA ranks
 __global__ void __launch_bounds__(256) k_rank_global(const u64 *__restrict__ mine, const u32 *__restrict__ idx_sorted, const u32 *__restrict__ cnt_list, u64 n_mine,
                                                      const u64 *__restrict__ all, RankRuns runs, u32 *__restrict__ perm, u32 *__restrict__ cnt_sorted, u32 *__restrict__ gid)
 {
-    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_mine) return;
-    const u64 key = mine[r];
-    u64 g = r;
-    for (u32 q = 0; q < runs.nruns; ++q)
+    // my run is sorted: the keys of this CTA fall into one narrow range of every other run; two long searches per run and CTA
+    // bound that range, the per-key searches then stay inside it (a few KB: L1)
+    __shared__ u64 s_lo[SK_MAXW], s_hi[SK_MAXW];
+    const u64 b0 = (u64)blockIdx.x * RG_KEYS;
+    if (b0 >= n_mine) return;
+    const u64 b1 = min(b0 + (u64)RG_KEYS, n_mine);
+    if (threadIdx.x < runs.nruns && threadIdx.x != runs.me)
     {
-        if (q == runs.me) continue;
-        const u64 *__restrict__ run = all + runs.off[q];
-        u64 lo = 0, hi = runs.n[q];
-        while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (__ldg(run + mid) < key) lo = mid + 1; else hi = mid; }
-        g += lo;
+        const u64 *__restrict__ run = all + runs.off[threadIdx.x];
+        const u64 kf = mine[b0], kl = mine[b1 - 1];
+        u64 lo = 0, hi = runs.n[threadIdx.x];
+        while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (__ldg(run + mid) < kf) lo = mid + 1; else hi = mid; }
+        s_lo[threadIdx.x] = lo;
+        hi = runs.n[threadIdx.x];
+        u64 l2 = lo;
+        while (l2 < hi) { const u64 mid = (l2 + hi) >> 1; if (__ldg(run + mid) < kl) l2 = mid + 1; else hi = mid; }
+        s_hi[threadIdx.x] = l2;
     }
-    const u32 i = idx_sorted[r];
-    perm[i] = (u32)g; gid[r] = (u32)g; cnt_sorted[r] = cnt_list[i];
+    __syncthreads();
+    for (u64 r = b0 + threadIdx.x; r < b1; r += blockDim.x)
+    {
+        const u64 key = mine[r];
+        u64 g = r;
+        for (u32 q = 0; q < runs.nruns; ++q)
+        {
+            if (q == runs.me) continue;
+            const u64 *__restrict__ run = all + runs.off[q];
+            u64 lo = s_lo[q], hi = s_hi[q];
+            while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (__ldg(run + mid) < key) lo = mid + 1; else hi = mid; }
+            g += lo;
+        }
+        const u32 i = idx_sorted[r];
+        perm[i] = (u32)g; gid[r] = (u32)g; cnt_sorted[r] = cnt_list[i];
+    }
 }
 
 __global__ void k_place_by_id(const u64 *__restrict__ key, const u32 *__restrict__ cnt, const u32 *__restrict__ gid, u64 n, u64 *__restrict__ okey, u32 *__restrict__ ocnt)

@@ -93,17 +93,20 @@ __device__ __forceinline__ u32 skm_mix(u32 v)
 
 static constexpr int SK_MAXW = 16;                    // GPUs the peer-memory record exchange addresses
 
-// Where records go.  Every GPU parses ITS OWN reads; a record goes straight into the slab of the GPU that owns its bucket:
-// on one GPU a plain store, on several a 32-byte store through NVLink into the owner's memory (slab[owner] is that GPU's slab
-// mapped into this process with the CUDA IPC calls): the scatter IS the personalised all-to-all of the reference
-// (src/KmerOps.cpp:151 and :274, both exchanges in one record), fused into the kernel that produces the data, 4.6 B per
-// instance on the wire.  An owner's bucket has one sub-slab per source GPU, [local bucket][source][rcap], so that the slot
-// reservation stays a LOCAL atomic: fill[global bucket] counts what THIS GPU offered (records in the low half, instances in
-// the high half).  Records beyond rcap go to the owner's overflow list (a remote atomic, rare), and the owner then counts
-// that whole bucket with the global-table fallback.
+// Where records go.  Every GPU parses ITS OWN reads.  An owner's bucket has one sub-slab per source GPU,
+// [local bucket][source][rcap], so that the slot reservation stays a LOCAL atomic: fill[global bucket] counts what THIS GPU
+// offered (records in the low half, instances in the high half).  Records of this GPU's own buckets go straight into its
+// slab; records of other GPUs' buckets are staged locally in the same shape (stage[global bucket][rcap]) and then pushed
+// into the owners' slabs through peer memory by k_skm_forward: bucket after bucket, only the filled part, in address order.
+// (Storing every 32-byte record straight into peer memory was measured first: 2.5 s instead of 9 ms on two B200 --
+// sector-random stores into a 25 GB window of imported memory do not go through NVLink at any useful rate.)
+// Together the two kernels are the personalised all-to-all of the reference (src/KmerOps.cpp:151 and :274, both exchanges
+// in one record), 4.6 B per instance on the wire, with no packing pass and no host-visible counts.
+// Records beyond rcap go to the owner's overflow list (a remote atomic, rare), and the owner then counts that whole bucket
+// with the global-table fallback.
 struct RecSink
 {
-    SkmRec *slab[SK_MAXW]; u64 *fill; u32 rcap, nb_own, nsrc, me, read_base;
+    SkmRec *slab; SkmRec *stage; u64 *fill; u32 rcap, nb_own, nsrc, me, read_base;
     SkmRec *ovf[SK_MAXW]; u64 *ovf_ctr[SK_MAXW];      // owner's overflow list and its counters: [0] records, [1] instances
     u64 ovf_cap;
 };
@@ -218,7 +221,12 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
                 {
                     const u32 slot = (u32)fw[i];
                     const u64 spare = ((fw[i] >> 32) << 8) | n[i];
-                    if (slot < sink.rcap) skm_store(sink.slab[own[i]] + (((u64)b[i] * sink.nsrc + sink.me) * sink.rcap + slot), rec[i].x, rec[i].y, meta0 + s0[i], spare);
+                    if (slot < sink.rcap)
+                    {
+                        SkmRec *dst = own[i] == sink.me ? sink.slab + (((u64)b[i] * sink.nsrc + sink.me) * sink.rcap + slot)
+                                                        : sink.stage + (((u64)own[i] * sink.nb_own + b[i]) * sink.rcap + slot);
+                        skm_store(dst, rec[i].x, rec[i].y, meta0 + s0[i], spare);
+                    }
                     else
                     {
                         u64 *ctr = sink.ovf_ctr[own[i]];
@@ -229,7 +237,34 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
                 }
         }
     }
-    __threadfence_system();           // several GPUs: the records are in the owners' memory before this kernel counts as done
+}
+
+// Several GPUs: the staged records of the other GPUs' buckets go into the owners' slabs (slab[r] = rank r's slab mapped into
+// this process, CUDA IPC).  One warp per (owner, bucket): min(records offered, rcap) records = one contiguous run of 32-byte
+// records on both sides, moved as 16-byte pieces; the buckets of one owner are visited in address order.
+struct RecForward { SkmRec *slab[SK_MAXW]; const SkmRec *stage; const u64 *fill; u32 rcap, nb_own, nsrc, me; };
+
+__global__ void __launch_bounds__(256) k_skm_forward(RecForward f)
+{
+    // Neighbouring warps write to DIFFERENT owners, starting behind this GPU in rank order: at any moment a GPU's stores are
+    // spread over all its peers, and every GPU receives from all the others at once at 1 / (W - 1) of their rate.  (Sweeping
+    // the owners one after the other in the same order on every GPU made all of them write into the same GPU at the same
+    // time: 108 GB/s per GPU on eight B200 instead of the link rate.)
+    const u32 lane = threadIdx.x & 31;
+    const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const u32 peers = f.nsrc - 1;
+    const u64 total = (u64)f.nb_own * peers;
+    for (u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total; g += nwarps)
+    {
+        const u32 bl = (u32)(g / peers), step = (u32)(g - (u64)bl * peers);
+        u32 own = f.me + 1 + step; if (own >= f.nsrc) own -= f.nsrc;
+        const u64 gb = (u64)own * f.nb_own + bl;                       // global bucket
+        const u32 n = min((u32)__ldg(f.fill + gb), f.rcap);
+        const uint4 *__restrict__ src = reinterpret_cast<const uint4*>(f.stage + gb * f.rcap);
+        uint4 *__restrict__ dst = reinterpret_cast<uint4*>(f.slab[own] + ((u64)bl * f.nsrc + f.me) * f.rcap);
+        for (u32 i = lane; i < 2 * n; i += 32) dst[i] = __ldcs(src + i);
+    }
+    __threadfence_system();           // the records are in the owners' memory before this kernel counts as done
 }
 
 // ---- counting ----------------------------------------------------------------------------------

@@ -130,20 +130,33 @@ def check_digests(workload: str, scale: float, input_digest: str, digests: dict,
     return "match (" + gold.get("pinned_by", "golden") + ")"
 
 
-def cpu_reference_sample(name: str):
-    """A bounded sample of the same workload shape for the CPU leg: (DnaBuffer, k, lower, upper, description)."""
+# share of a synthetic workload the CPU arms run (the reference's own code needs minutes per 10^9 k-mer instances):
+# config 3 in full (the same reads the GPU arm times), config 4 at 10 %, config 5 at 0.4 %
+CPU_SAMPLE = {"ecoli30x_clr": 1.0, "celegans40x_hifi": 0.10, "human10x_clr": 0.004}
+
+
+def cpu_reference_sample(name: str, frac: float | None = None):
+    """The input of the CPU leg: (DnaBuffer, k, lower, upper, description, same_as_gpu_arm).  frac = 1: the very reads the GPU
+    arm times (same generator, same seeds); frac < 1: the same shape (coverage, read length, error rate) over a genome and a
+    read count both scaled by frac.  Generated on the GPU when there is one (seconds instead of minutes)."""
     from elba_b200.dnabuffer import DnaBuffer
     from elba_b200 import synth
     w = WORKLOADS[name]
     if "fixture" in w:
         dna = DnaBuffer.load(os.path.join(ROOT, "tests", "golden", w["fixture"] + ".npz"))
-        return dna, w["k"], w["lower"], w["upper"], f"all {dna.size()} reads of {w['fixture']}"
+        return dna, w["k"], w["lower"], w["upper"], f"all {dna.size()} reads of {w['fixture']}", True
     s = synth.SHAPES[w["shape"]]
-    target_bases = 40_000_000
-    scale = min(1.0, target_bases / (s["reads"] * s["mean"]))
-    genome, reads = max(int(s["genome"] * scale), 100_000), max(int(s["reads"] * scale), 64)
-    dna = synth.make_dnabuffer(genome, reads, s["mean"], s["sd"], s["err"], seed=313)
-    return dna, s["k"], s["lower"], s["upper"], f"{reads} reads over a {genome} bp genome: the {w['shape']} shape (same coverage, read length, error rate) scaled by {scale:.4g}"
+    frac = CPU_SAMPLE.get(w["shape"], 0.05) if frac is None else frac
+    genome, reads = max(int(s["genome"] * frac), 100_000), max(int(s["reads"] * frac), 64)
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    buf, off, lens = synth.make_reads_block(genome, reads, s["mean"], s["sd"], s["err"], 313, dev, 0, reads)
+    dna = synth.to_dnabuffer(buf, off, lens)
+    del buf, off, lens
+    if frac >= 1.0:
+        desc = f"all {reads} reads of the workload (the same reads the GPU arm times)"
+    else:
+        desc = f"{reads} reads over a {genome} bp genome: the {w['shape']} shape (same coverage, read length, error rate) scaled by {frac:.4g}"
+    return dna, s["k"], s["lower"], s["upper"], desc, frac >= 1.0 and dev.type == "cuda"
 
 
 def run_cpu_reference(dna, k, lo, up, ranks: int):
@@ -185,7 +198,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        dna, k, lo, up, sample = cpu_reference_sample(args.workload)
+        dna, k, lo, up, sample, same = cpu_reference_sample(args.workload)
         ranks, cores = square_ranks()
         times = []
         for i in range(args.warmup + args.steps):
@@ -197,6 +210,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": args.workload, "desc": w["desc"], "k": k, "lower": lo, "upper": up},
+                "same_input_as_gpu_arm": same,
                 "cpu_baseline": {"value": val, "unit": "reads/s", "cores": used, "kind": kind, "host_cores": cores,
                                  "sample": sample + "; reference KmerOps.cpp/SharedSeeds.cpp compiled unmodified, MPI ranks emulated as threads, CombBLAS restated (oracle/stubs)",
                                  "stage_secs": secs},
@@ -362,12 +376,17 @@ def main():
             except Exception as ex:          # never lose the bench line over a reporting extra
                 line["roofline_nvlink"] = {"error": str(ex)}
         if world == 1 and not args.no_cpu_baseline:
-            dna, ck, cl, cu, sample = cpu_reference_sample(args.workload)
             ranks, cores = square_ranks()
+            dna, ck, cl, cu, sample, same = cpu_reference_sample(args.workload)
             rps, kind, used, secs = run_cpu_reference(dna, ck, cl, cu, ranks)
-            line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": used, "kind": kind, "host_cores": cores,
+            line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": used, "kind": kind, "host_cores": cores, "same_input_as_gpu_arm": same,
                                     "sample": sample + "; reference KmerOps.cpp/SharedSeeds.cpp compiled unmodified, MPI ranks emulated as threads, CombBLAS restated (oracle/stubs)",
                                     "stage_secs": secs}
+            if "shape" in w and not same:
+                # the rate at a quarter of the sample: how flat the CPU rate is in the input size (hash maps leave the caches)
+                dna2, _, _, _, sample2, _ = cpu_reference_sample(args.workload, CPU_SAMPLE.get(w["shape"], 0.05) / 4)
+                rps2, _, _, _ = run_cpu_reference(dna2, ck, cl, cu, ranks)
+                line["cpu_baseline"]["rate_by_sample"] = [{"sample": sample2, "reads_per_s": rps2}, {"sample": sample, "reads_per_s": rps}]
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist is not None:

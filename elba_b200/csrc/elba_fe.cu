@@ -65,6 +65,9 @@ struct elba_fe_ctx
     // reads
     DevBuf packed, off, len64, len32, chunk_start, kmer_start, nks_start;
     u32 n = 0; u64 packed_bytes = 0, nchunks = 0, M = 0, Ms = 0; int64_t read_id_offset = 0;
+    // an upload from host memory arrives in slices on a second stream; the scatter of slice s starts when slice s + 1 is there
+    static constexpr int UP_SLICES = 8;
+    int up_n = 0; u64 up_chunk_end[UP_SLICES] = {}; cudaEvent_t up_ev[UP_SLICES] = {}; cudaEvent_t up_t0 = nullptr;
     // counting
     DevBuf table, cand, ctr, partbuf, phist, pcursor, rel_key, rel_cnt, rel_key_s, rel_cnt_s, lut, filter;
     DevBuf plan, bfill, ovf, scratch[2];
@@ -272,6 +275,8 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     // random 16-byte table probes: do not let L2 pull whole 128-byte lines from HBM for them (profiles/r1_count_v0.md)
     cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
+    for (auto &e : ctx->up_ev) cudaEventCreate(&e);
+    cudaEventCreate(&ctx->up_t0);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreate(&ctx->ev_x0); cudaEventCreate(&ctx->ev_x1); cudaEventCreate(&ctx->xd_e0); cudaEventCreate(&ctx->xd_e1);
     if (ctx->tmp64.ensure(8192) != cudaSuccess || ctx->ctr.ensure(128) != cudaSuccess) { elba_fe_destroy(ctx); return fail(nullptr, ELBA_FE_ERR_OOM, "cudaMalloc failed"); }
@@ -310,6 +315,8 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
     if (ctx->comm.comm) ctx->comm.api->CommDestroy(ctx->comm.comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    for (auto &e : ctx->up_ev) if (e) cudaEventDestroy(e);
+    if (ctx->up_t0) cudaEventDestroy(ctx->up_t0);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_x0) cudaEventDestroy(ctx->ev_x0);
@@ -331,6 +338,13 @@ int elba_fe_set_stream(elba_fe_ctx *ctx, void *cuda_stream)
 
 int elba_fe_synchronize(elba_fe_ctx *ctx) { if (!ctx) return ELBA_FE_ERR_INVALID; CK(cudaStreamSynchronize(ctx->stream)); return 0; }
 
+// every consumer of the arena other than the sliced scatter: the whole upload must have arrived
+static int wait_reads(elba_fe_ctx *ctx)
+{
+    if (ctx->up_n > 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->up_ev[ctx->up_n - 1], 0));
+    return 0;
+}
+
 static int stage_reads(elba_fe_ctx *ctx, const uint8_t *packed, uint64_t packed_bytes, const uint64_t *byte_off, const uint64_t *len,
                        uint64_t nreads, int64_t read_id_offset, cudaMemcpyKind kind)
 {
@@ -341,20 +355,57 @@ static int stage_reads(elba_fe_ctx *ctx, const uint8_t *packed, uint64_t packed_
     CK(cudaSetDevice(ctx->cfg.device));
     ctx->phase = 0;
     ctx->n = (u32)nreads; ctx->packed_bytes = packed_bytes; ctx->read_id_offset = read_id_offset;
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], st));
     CK(ctx->packed.ensure(packed_bytes + 64));
     CK(ctx->off.ensure(sizeof(u64) * (size_t)(nreads + 1)));
     CK(ctx->len64.ensure(sizeof(u64) * (size_t)(nreads + 1)));
-    CK(cudaMemsetAsync(ctx->packed.as<uint8_t>() + packed_bytes, 0, 64, ctx->stream));
-    if (packed_bytes) CK(cudaMemcpyAsync(ctx->packed.p, packed, packed_bytes, kind, ctx->stream));
+    // A large arena coming from the host travels in slices on the second stream while the read tables are prepared and the
+    // first slices are already parsed (count_superkmers).  The caller's buffer must stay valid until the next call that
+    // synchronises (elba_fe_count / elba_fe_run do).
+    const bool sliced = kind == cudaMemcpyHostToDevice && packed_bytes >= (64ull << 20) && nreads >= 4096;
+    ctx->up_n = 0;
+    std::vector<u64> slice_read;                         // first read of every slice (host side: byte_off is a host array here)
+    if (sliced)
+    {
+        const int S = elba_fe_ctx::UP_SLICES;
+        CK(cudaEventRecord(ctx->ev_fork, st));           // the previous pass has finished with the old arena before it is overwritten
+        CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        CK(cudaEventRecord(ctx->up_t0, ctx->aux));
+        slice_read.assign(S + 1, nreads);
+        slice_read[0] = 0;
+        for (int i = 1; i < S; ++i) slice_read[i] = (u64)(std::lower_bound(byte_off, byte_off + nreads, packed_bytes / S * (u64)i) - byte_off);
+        for (int i = 0; i < S; ++i)
+        {
+            const u64 b0 = slice_read[i] < nreads ? byte_off[slice_read[i]] : packed_bytes, b1 = slice_read[i + 1] < nreads ? byte_off[slice_read[i + 1]] : packed_bytes;
+            if (b1 > b0) CK(cudaMemcpyAsync(ctx->packed.as<uint8_t>() + b0, packed + b0, b1 - b0, kind, ctx->aux));
+            if (i == S - 1) CK(cudaMemsetAsync(ctx->packed.as<uint8_t>() + packed_bytes, 0, 64, ctx->aux));
+            CK(cudaEventRecord(ctx->up_ev[i], ctx->aux));
+        }
+        ctx->up_n = S;
+    }
+    else
+    {
+        CK(cudaMemsetAsync(ctx->packed.as<uint8_t>() + packed_bytes, 0, 64, st));
+        if (packed_bytes) CK(cudaMemcpyAsync(ctx->packed.p, packed, packed_bytes, kind, st));
+    }
     if (nreads)
     {
-        CK(cudaMemcpyAsync(ctx->off.p, byte_off, sizeof(u64) * nreads, kind, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->len64.p, len, sizeof(u64) * nreads, kind, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->off.p, byte_off, sizeof(u64) * nreads, kind, st));
+        CK(cudaMemcpyAsync(ctx->len64.p, len, sizeof(u64) * nreads, kind, st));
     }
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[1], st));
     int rc = prepare_reads(ctx);
     if (rc) return rc;
+    if (sliced)
+    {
+        // chunk index where every slice ends (the scatter is launched per slice)
+        const int S = elba_fe_ctx::UP_SLICES;
+        u64 ends[elba_fe_ctx::UP_SLICES];
+        for (int i = 0; i < S; ++i) CK(cudaMemcpyAsync(&ends[i], ctx->chunk_start.as<u64>() + slice_read[i + 1], 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < S; ++i) ctx->up_chunk_end[i] = ends[i];
+    }
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->tm.upload_ms = ms;
     return 0;
 }
@@ -615,23 +666,34 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     CK(cudaEventRecord(pp.a, st));
     if (rv.nchunks)
     {
-        const u32 g1 = (u32)std::min<u64>((rv.nchunks + SK_THREADS - 1) / SK_THREADS, (u64)grid_for(ctx, 4));
-        const u64 iters = (rv.nchunks + (u64)g1 * SK_THREADS - 1) / ((u64)g1 * SK_THREADS);
         int contig = 1, nr = SK_NR;
         if (const char *e = getenv("ELBA_FE_SKM_ORDER")) contig = std::strcmp(e, "strided") != 0;
         if (const char *e = getenv("ELBA_FE_SKM_NR")) nr = atoi(e);
-        const u64 it1 = iters;
-        switch (Wm)
+        // one launch over all chunks, or one per slice of an upload that is still arriving (slice s needs slice s + 1: a chunk's
+        // 64-base window may reach into the next read)
+        const int nlaunch = ctx->up_n > 0 ? ctx->up_n : 1;
+        u64 gb = 0;
+        for (int sl = 0; sl < nlaunch; ++sl)
         {
-            case 8:  k_skm_scatter<8, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig); break;
-            case 12: k_skm_scatter<12, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig); break;
-            case 16: if (nr == 1) k_skm_scatter<16, 1><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig);
-                     else k_skm_scatter<16, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig);
-                     break;
-            case 17: k_skm_scatter<17, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig); break;
-            default: return fail(ctx, ELBA_FE_ERR_INVALID, "no super-k-mer kernel for this minimizer window");
+            const u64 ge = ctx->up_n > 0 ? ctx->up_chunk_end[sl] : rv.nchunks;
+            if (ctx->up_n > 0) CK(cudaStreamWaitEvent(st, ctx->up_ev[std::min(sl + 1, ctx->up_n - 1)], 0));
+            const u64 nch = ge - gb;
+            if (nch == 0) continue;
+            const u32 g1 = (u32)std::min<u64>((nch + SK_THREADS - 1) / SK_THREADS, (u64)grid_for(ctx, 4));
+            const u64 it1 = (nch + (u64)g1 * SK_THREADS - 1) / ((u64)g1 * SK_THREADS);
+            switch (Wm)
+            {
+                case 8:  k_skm_scatter<8, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig, gb, ge); break;
+                case 12: k_skm_scatter<12, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig, gb, ge); break;
+                case 16: if (nr == 1) k_skm_scatter<16, 1><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig, gb, ge);
+                         else k_skm_scatter<16, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig, gb, ge);
+                         break;
+                case 17: k_skm_scatter<17, SK_NR><<<g1, SK_THREADS, 0, st>>>(rv, k, m, nmax, sink, it1, contig, gb, ge); break;
+                default: return fail(ctx, ELBA_FE_ERR_INVALID, "no super-k-mer kernel for this minimizer window");
+            }
+            CKL(); LAUNCHED(ctx);
+            gb = ge;
         }
-        CKL(); LAUNCHED(ctx);
     }
     CK(cudaEventRecord(pp.b, st));
     mark(ctx, "scatter");
@@ -774,6 +836,7 @@ int elba_fe_count(elba_fe_ctx *ctx)
         if (use_skm && !ok) use_skm = false;                             // read blocks not consecutive over the ranks / no peer access: hash path
         if (use_skm) { plan.Ms = ctx->Ms_total; plan.read_base = (u32)ctx->read_id_offset; plan.nranks = W; plan.rank = me; }
     }
+    if (!use_skm) { int rcw = wait_reads(ctx); if (rcw) return rcw; }                 // only the super-k-mer scatter follows an upload slice by slice
     if (W > 1) { P1 = (P1 + W - 1) / W * W; if (P1 > MAX_P1) P1 = MAX_P1 / W * W; }      // every rank owns P1 / W partitions
     const u32 Pown = P1 / (u32)W;
     ctx->sz.partitions = P1;
@@ -1189,6 +1252,7 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     CK(cudaEventRecord(ctx->ev[4], st));
     mark(ctx, "begin");
     ctx->lev_used = 0; ctx->panel_bytes = 0;
+    { int rcw = wait_reads(ctx); if (rcw) return rcw; }
     const int cb = bits_for(std::max<u64>(R, 2)), rb = bits_for(std::max<u64>(N, 2));
     ctx->col_bits = cb; ctx->read_bits = rb;
     u64 *d_ctr = ctx->ctr.as<u64>();
@@ -1466,6 +1530,7 @@ int elba_fe_timings(elba_fe_ctx *ctx, elba_fe_timings_t *out)
     if (!ctx || !out) return ELBA_FE_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
     float ms;
+    if (ctx->up_n > 0 && cudaEventElapsedTime(&ms, ctx->up_t0, ctx->up_ev[ctx->up_n - 1]) == cudaSuccess) ctx->tm.upload_ms = ms;      // the sliced H2D copy on the second stream
     if (ctx->phase >= 2 && cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->tm.count_ms = ms;
     if (ctx->phase >= 3 && cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) ctx->tm.build_ms = ms;
     if (ctx->phase >= 4 && cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) ctx->tm.spgemm_ms = ms;
@@ -1691,6 +1756,7 @@ int elba_fe_align(elba_fe_ctx *ctx, int mat, int mis, int gap, int dropoff, uint
     cudaStream_t st = ctx->stream;
     const u64 nnz = ctx->sz.nnzB; const u32 N = ctx->b_rows;
     ctx->xd_done = false;
+    { int rcw = wait_reads(ctx); if (rcw) return rcw; }
     CK(cudaEventRecord(ctx->xd_e0, st));
     CK(ctx->xd_flag.ensure(8 * (nnz + 2))); CK(ctx->xd_rowof.ensure(4 * (nnz + 1))); CK(ctx->xd_max.ensure(64));
     k_xdrop_select<<<nblk(nnz + 1, 256), 256, 0, st>>>(ctx->b_rowptr.as<int64_t>(), ctx->b_col.as<u32>(), N, nnz, ctx->op.row0, ctx->op.col0,
@@ -1758,6 +1824,7 @@ int elba_fe_hll(elba_fe_ctx *ctx, uint8_t *registers, double *estimate)
     if (!ctx) return ELBA_FE_ERR_INVALID;
     if (ctx->phase < 1) return fail(ctx, ELBA_FE_ERR_STATE, "no reads uploaded");
     CK(cudaSetDevice(ctx->cfg.device));
+    { int rcw = wait_reads(ctx); if (rcw) return rcw; }
     CK(ctx->hll_regs.ensure(4 * ELBA_FE_HLL_REGISTERS));
     CK(cudaMemsetAsync(ctx->hll_regs.p, 0, 4 * ELBA_FE_HLL_REGISTERS, ctx->stream));
     if (ctx->nchunks) { k_hll<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(view(ctx), ctx->cfg.k, ctx->cfg.stride, ctx->hll_regs.as<u32>()); CKL(); LAUNCHED(ctx); }
@@ -1790,6 +1857,7 @@ int elba_fe_bloom(elba_fe_ctx *ctx, int64_t entries, double error, int64_t *bits
     if (bits < 1) return fail(ctx, ELBA_FE_ERR_INVALID, "Bloom filter has no bits");
     CK(cudaSetDevice(ctx->cfg.device));
     size_t words = (size_t)(bytes + 3) / 4;
+    { int rcw = wait_reads(ctx); if (rcw) return rcw; }
     CK(ctx->bloom.ensure(4 * words));
     CK(cudaMemsetAsync(ctx->bloom.p, 0, 4 * words, ctx->stream));
     if (ctx->nchunks) { k_bloom_add<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(view(ctx), ctx->cfg.k, ctx->cfg.stride, ctx->bloom.as<u32>(), (u64)bits, hashes); CKL(); LAUNCHED(ctx); }
@@ -1804,6 +1872,7 @@ int elba_fe_get_kmer_stream(elba_fe_ctx *ctx, uint64_t *out)
     if (ctx->phase < 1) return fail(ctx, ELBA_FE_ERR_STATE, "no reads uploaded");
     CK(cudaSetDevice(ctx->cfg.device));
     DevBuf tmp;
+    { int rcw = wait_reads(ctx); if (rcw) return rcw; }
     CK(tmp.ensure(8 * std::max<u64>(ctx->M, 1)));
     if (ctx->nchunks) { k_kmer_stream<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(view(ctx), ctx->cfg.k, tmp.as<u64>()); LAUNCHED(ctx); }
     cudaError_t e = cudaGetLastError();

@@ -118,7 +118,7 @@ static constexpr int SK_NR = 2;                       // records whose bucket re
 // is SK_THREADS chunks further in the same or the next read: the read is found once by binary search and then followed.
 // Otherwise the grid strides over the chunks together and every chunk is located by its own binary search.
 template <int W, int NR>
-__global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int k, int m, u32 nmax, RecSink sink, u64 iters, int contig)
+__global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int k, int m, u32 nmax, RecSink sink, u64 iters, int contig, u64 g_begin, u64 g_end)
 {
     static_assert(W >= 1 && W <= 17, "the m-mers of a chunk must fit the 64 loaded bases");
     __shared__ u32 s_mn[CHUNK * SK_THREADS];          // minimizer of window start s of this thread's chunk: [s][tid]
@@ -128,14 +128,15 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
     const u32 tid = threadIdx.x;
     const u32 maskL = (m >= 16) ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> (2 * m));
     const u32 vs = 2u * (u32)(16 - m);
-    u64 g = contig ? (u64)blockIdx.x * iters * SK_THREADS + tid : (u64)blockIdx.x * SK_THREADS + tid;
+    // this launch handles the chunks [g_begin, g_end): all of them, or the reads of one slice of an upload still in flight
+    u64 g = g_begin + (contig ? (u64)blockIdx.x * iters * SK_THREADS + tid : (u64)blockIdx.x * SK_THREADS + tid);
     const u64 gstep = contig ? (u64)SK_THREADS : (u64)gridDim.x * SK_THREADS;
-    if (g >= rv.nchunks) return;
+    if (g >= g_end) return;
     u32 read = find_read(rv.chunk_start, rv.n, g);
     u64 cs0 = __ldg(rv.chunk_start + read), cs1 = __ldg(rv.chunk_start + read + 1);
     u64 roff = __ldg(rv.off + read);
     u32 rnk = __ldg(rv.len + read) - (u32)k + 1;
-    for (u64 it = 0; it < iters && g < rv.nchunks; ++it, g += gstep)
+    for (u64 it = 0; it < iters && g < g_end; ++it, g += gstep)
     {
         if (g >= cs1)
         {

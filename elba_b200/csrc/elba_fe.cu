@@ -365,6 +365,12 @@ static int stage_reads(elba_fe_ctx *ctx, const uint8_t *packed, uint64_t packed_
     // synchronises (elba_fe_count / elba_fe_run do).
     const bool sliced = kind == cudaMemcpyHostToDevice && packed_bytes >= (64ull << 20) && nreads >= 4096;
     ctx->up_n = 0;
+    // the read tables first: a copy engine serves its copies in issue order, and the table preparation must not queue behind the arena
+    if (nreads)
+    {
+        CK(cudaMemcpyAsync(ctx->off.p, byte_off, sizeof(u64) * nreads, kind, st));
+        CK(cudaMemcpyAsync(ctx->len64.p, len, sizeof(u64) * nreads, kind, st));
+    }
     std::vector<u64> slice_read;                         // first read of every slice (host side: byte_off is a host array here)
     if (sliced)
     {
@@ -388,11 +394,6 @@ static int stage_reads(elba_fe_ctx *ctx, const uint8_t *packed, uint64_t packed_
     {
         CK(cudaMemsetAsync(ctx->packed.as<uint8_t>() + packed_bytes, 0, 64, st));
         if (packed_bytes) CK(cudaMemcpyAsync(ctx->packed.p, packed, packed_bytes, kind, st));
-    }
-    if (nreads)
-    {
-        CK(cudaMemcpyAsync(ctx->off.p, byte_off, sizeof(u64) * nreads, kind, st));
-        CK(cudaMemcpyAsync(ctx->len64.p, len, sizeof(u64) * nreads, kind, st));
     }
     CK(cudaEventRecord(ctx->ev[1], st));
     int rc = prepare_reads(ctx);

@@ -114,6 +114,38 @@ def test_config4_celegans_full_seeds_valid_and_golden_digests():
     assert check_seeds_valid(dna, s["k"], brp, bcol, bseeds, max_checks=20000) == 0
 
 
+def test_sliced_upload_from_host_gives_the_same_bits():
+    """A large arena uploaded from host memory travels in slices on a second stream and the scatter follows slice by slice
+    (elba_fe_upload_reads); the result must equal the run on reads already resident in HBM.  Both counting paths."""
+    import torch
+    from elba_b200 import frontend, synth
+    tensors, s = _synthetic("celegans40x_hifi", 0.08)
+    ctx = _run_device(tensors, s["k"], s["lower"], s["upper"])
+    want, want_sizes = ctx.digests(), ctx.sizes()
+    ctx.close()
+    dna = synth.to_dnabuffer(*tensors)
+    assert dna.buf.nbytes >= 64 << 20, "the test must be large enough for the sliced upload"
+    hbuf, hoff, hlen = (torch.from_numpy(a).pin_memory() for a in (dna.buf, dna.offsets.astype(np.int64), dna.lengths.astype(np.int64)))
+    for env in ({}, {"ELBA_FE_COUNT_PATH": "hash"}):
+        old = {a: os.environ.get(a) for a in env}
+        os.environ.update(env)
+        try:
+            ctx = frontend.Context(frontend.Params(k=s["k"], lower=s["lower"], upper=s["upper"], device=0))
+            for _ in range(2):                      # twice: the second upload overwrites the arena of the first pass
+                ctx.upload_raw(hbuf.data_ptr(), hbuf.numel(), hoff.data_ptr(), hlen.data_ptr(), dna.size(), 0)
+                ctx.run()
+                assert ctx.digests() == want, env
+            got = ctx.sizes()
+            assert all(got[a] == want_sizes[a] for a in ("num_kmers", "distinct", "reliable", "nnzA", "products", "nnzB")), env
+            ctx.close()
+        finally:
+            for a, b in old.items():
+                if b is None:
+                    os.environ.pop(a, None)
+                else:
+                    os.environ[a] = b
+
+
 @pytest.mark.parametrize("k,stride", [(17, 3), (31, 2), (21, 5)])
 def test_stride_vs_oracle(k, stride):
     """-s: only window starts p with p % stride == 0 (README.md:85); the reference hard-wires 1, the oracle restates the rule."""

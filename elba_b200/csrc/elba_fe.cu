@@ -51,7 +51,7 @@ struct EventPair { cudaEvent_t a = nullptr, b = nullptr; };
 struct Window { DevBuf buf; void *peer[elba::SK_MAXW] = {}; bool mapped = false; };
 
 // geometry of the bucket count kernel (skm_count.cuh): 4 CTAs x 256 threads per SM, 2048-slot tables, 960-record staging buffers
-constexpr int SK4_THREADS = 256, SK4_SLOTS = 2048, SK4_RMAX = 752, SK4_POOL = 2048, SK4_MINB = 4;
+constexpr int SK4_THREADS = 256, SK4_SLOTS = 2048, SK4_RMAX = 736, SK4_POOL = 1536, SK4_RETRY = 64, SK4_MINB = 4;
 
 } // namespace
 
@@ -288,7 +288,7 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaFuncSetAttribute(k_scatter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_scatter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(u64) * S2_TILE + 2 * sizeof(u32) * MAX_P2));
     cudaFuncSetAttribute(k_count_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(u64) + sizeof(u32)) * BUCKET_SLOTS));
-    if (cudaFuncSetAttribute(k_skm_count4<SK4_THREADS, SK4_SLOTS, SK4_RMAX, SK4_POOL, SK4_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk4_smem(SK4_SLOTS, SK4_RMAX, SK4_POOL)) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_skm_count4<SK4_THREADS, SK4_SLOTS, SK4_RMAX, SK4_POOL, SK4_RETRY, SK4_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk4_smem(SK4_SLOTS, SK4_RMAX, SK4_POOL, SK4_RETRY, SK4_THREADS)) != cudaSuccess)
     { elba_fe_destroy(ctx); return fail(nullptr, ELBA_FE_ERR_CUDA, "cudaFuncSetAttribute(k_skm_count4) failed"); }
     *out = ctx;
     return 0;
@@ -617,7 +617,7 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     // mean bucket: a third of the table in DISTINCT k-mers (distinct / instances of the last pass, else a guess), records well inside the staging
     // buffer, instances within 2 / 5 of the capacity (a bucket is a handful of genomic super-k-mers times the coverage: CV ~ 0.4)
     const double dm = ctx->hist_dm > 0.0 ? std::min(1.0, std::max(0.05, ctx->hist_dm)) : 0.3;
-    u64 mean_inst = (u64)std::min({ (double)bcap * 0.4, 0.36 * (double)slots / dm, (double)SK4_RMAX / 2.2 * avg_run });
+    u64 mean_inst = (u64)std::min({ (double)bcap * 0.4, 0.36 * (double)slots / dm, (double)SK4_RMAX / 2.7 * avg_run });      // measured: profiles/r2_v11_tune_bucket_mean.log
     mean_inst = std::max<u64>(mean_inst, 64);
     if (const char *e = getenv("ELBA_FE_SKM_MEAN")) { long v = atol(e); if (v >= 64 && v <= (long)bcap) mean_inst = (u64)v; }
     u64 NBg = std::max<u64>(1, (Ms + mean_inst - 1) / mean_inst);
@@ -727,7 +727,7 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     CK(cudaEventRecord(ep.a, st));
     {
         const u32 gc = (u32)std::min<u64>(NB, gc_max);
-        k_skm_count4<SK4_THREADS, SK4_SLOTS, SK4_RMAX, SK4_POOL, SK4_MINB><<<gc, SK4_THREADS, sk4_smem(SK4_SLOTS, SK4_RMAX, SK4_POOL), st>>>(in, (u32)NB, k, ovf, lower, upper,
+        k_skm_count4<SK4_THREADS, SK4_SLOTS, SK4_RMAX, SK4_POOL, SK4_RETRY, SK4_MINB><<<gc, SK4_THREADS, sk4_smem(SK4_SLOTS, SK4_RMAX, SK4_POOL, SK4_RETRY, SK4_THREADS), st>>>(in, (u32)NB, k, ovf, lower, upper,
             ctx->rel_key.as<u64>(), ctx->rel_cnt.as<u32>(), d_ctr, rel_cap, seeds);
     }
     CKL(); LAUNCHED(ctx);

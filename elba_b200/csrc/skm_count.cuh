@@ -55,7 +55,7 @@ static constexpr u32 SK4_CHUNK = 16384;          // entries of a CTA-private chu
 static constexpr u32 SK4_MAXPROBE = 48;          // probes after which a table counts as too full
 
 __host__ __device__ constexpr u32 sk4_cap(u32 threads) { return threads * 24u; }                  // instances of one bucket (24 per thread)
-__host__ __device__ constexpr size_t sk4_smem(u32 slots, u32 rmax, u32 pool) { return (size_t)rmax * 32 + (size_t)slots * 12 + (size_t)pool * 4 + 64; }
+__host__ __device__ constexpr size_t sk4_smem(u32 slots, u32 rmax, u32 pool, u32 retry, u32 threads) { return (size_t)rmax * 32 + (size_t)slots * 12 + (size_t)pool * 4 + (size_t)(threads / 32) * retry * 4 + 64; }
 
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
@@ -110,7 +110,7 @@ __device__ __forceinline__ u32 sk4_slot(u64 x)
 // count was still below `upper`: only those can be instances of a reliable k-mer (a k-mer with more than `upper` instances
 // is dropped whatever its later instances do), so pass 2 looks at the pool (a few hundred entries) instead of walking all
 // instances again, and no per-instance state lives in registers: the instance loop is a rolled loop of two instances.
-template <int THREADS, int SLOTS, int RMAX, int POOL, int MINB>
+template <int THREADS, int SLOTS, int RMAX, int POOL, int RETRY, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 nb, int k, RecOverflow ovf, u32 lower, u32 upper,
                                                            u64 *__restrict__ out_kmer, u32 *__restrict__ out_cnt,
                                                            u64 *__restrict__ counters, u64 cap, SeedSink2 seeds)
@@ -123,14 +123,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
     u64 *s_key = reinterpret_cast<u64*>(s_raw4 + (size_t)RMAX * 32);               // [SLOTS]
     u32 *s_cnt = reinterpret_cast<u32*>(s_key + SLOTS);                            // [SLOTS] count (low 16) | list index inside the chunk (high 16)
     u32 *s_pool = s_cnt + SLOTS;                                                   // [POOL] slot << 16 | record << 5 | k-mer in the record
-    u64 *s_bar = reinterpret_cast<u64*>(s_pool + POOL);
+    u32 *s_retry = s_pool + POOL;                                                  // [warps][RETRY] record << 5 | k-mer in the record
+    u64 *s_bar = reinterpret_cast<u64*>(s_retry + (THREADS / 32) * RETRY);
     __shared__ u64 s_spill_base, s_rel_base, s_seed_base, s_pad_rel_base, s_pad_seed_base;
     __shared__ u32 s_rel_used, s_seed_used, s_pad_rel_from, s_pad_seed_from, s_full, s_pool_n;
     const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 G = gridDim.x;
     const int lsh = 2 * (32 - k);
     const u64 kmask = (k == 32) ? ~0ull : (~0ull << lsh);
-    const u32 a_rec = smem_u32(s_rec), a_key = smem_u32(s_key), a_cnt = smem_u32(s_cnt), a_pool = smem_u32(s_pool), a_pn = smem_u32(&s_pool_n);
+    const u32 a_rec = smem_u32(s_rec), a_key = smem_u32(s_key), a_cnt = smem_u32(s_cnt), a_pool = smem_u32(s_pool), a_pn = smem_u32(&s_pool_n), a_rl = smem_u32(s_retry);
+    const u32 lt_mask = lanemask_lt();
     u32 my_distinct = 0, my_rel = 0; u64 my_sum = 0;
     __shared__ u32 s_src_rec[SK_MAXW + 1], s_src_inst[SK_MAXW + 1];               // prefix sums of the sources' records / instances in this bucket
     u32 b = blockIdx.x;
@@ -249,6 +251,34 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
                 lds_v2u64(ra, x, y);
                 n = ((u32)y & 31u) + 1u; j = il - (u32)(lds_u64(ra + 24u) >> 8);
             }
+            // Main loop: every lane takes one CAS at the home slot of its k-mer, the warp stays converged.  Lanes that find
+            // another k-mer there (a fifth of them at these load factors) do NOT probe on the spot -- that loop would run for
+            // a handful of lanes while the rest of the warp waits, every iteration -- but leave a reference in the warp's
+            // private retry list; the list is worked off after the loop with all lanes busy.
+            u32 nretry = 0;                                                // entries in this warp's list (uniform over the warp)
+            const u32 a_retry = a_rl + (tid >> 5) * (RETRY * 4u);
+            auto insert_probing = [&](u64 key, u32 sa) -> u32              // probes from the slot after sa; returns the slot address
+            {
+                u32 stepp = 0; u64 pv;
+#pragma unroll 1
+                do
+                {
+                    if (++stepp > SK4_MAXPROBE) { s_full = 1; break; }
+                    sa = a_key + (((sa - a_key) + stepp * 8u) & (SLOTS * 8u - 8u));      // triangular probing: every slot once
+                    pv = atoms_cas_u64(sa, EMPTY_KEY, key);
+                } while (pv != EMPTY_KEY && pv != key);
+                return sa;
+            };
+            auto count_and_pool = [&](u32 sa, u32 ref)
+            {
+                const u32 slot = (sa - a_key) >> 3;
+                const u32 old = atoms_add_u32(a_cnt + slot * 4u, 1u);
+                if (old < upper)                                           // can still belong to a reliable k-mer: remember the instance
+                {
+                    const u32 p = atoms_add_u32(a_pn, 1u);                // ptxas turns the same-address atomic of a warp into one reservation
+                    if (p < (u32)POOL) sts_u32(a_pool + p * 4u, (slot << 16) | ref);
+                }
+            };
 #pragma unroll 1
             for (u32 g = 0; g < c; g += 2)                                 // c is uniform: the warp stays converged at the loop head
             {
@@ -265,38 +295,44 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
                     REF[q] = (ra - a_rec) | j;                             // record * 32 | k-mer in the record
                     j += have[q] ? 1u : 0u;
                 }
-                // one CAS per instance, every lane of the warp together: claims an empty slot or returns the resident k-mer
 #pragma unroll
                 for (int q = 0; q < 2; ++q) P[q] = have[q] ? atoms_cas_u64(S[q], EMPTY_KEY, K[q]) : K[q];
-                u32 OLD[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q)
                 {
-                    u32 sa = S[q];
-                    if (P[q] != EMPTY_KEY && P[q] != K[q])                 // the slot holds another k-mer: triangular probing, every slot once
+                    const bool coll = P[q] != EMPTY_KEY && P[q] != K[q];  // the home slot holds another k-mer
+                    const unsigned m = __ballot_sync(0xffffffffu, coll);
+                    bool later = false;
+                    if (m)
                     {
-                        u32 stepp = 0; u64 pv;
-#pragma unroll 1
-                        do
-                        {
-                            if (++stepp > SK4_MAXPROBE) { s_full = 1; break; }
-                            sa = a_key + (((sa - a_key) + stepp * 8u) & (SLOTS * 8u - 8u));
-                            pv = atoms_cas_u64(sa, EMPTY_KEY, K[q]);
-                        } while (pv != EMPTY_KEY && pv != K[q]);
+                        const u32 pos = nretry + __popc(m & lt_mask);
+                        later = coll && pos < (u32)RETRY;
+                        if (later) sts_u32(a_retry + pos * 4u, REF[q]);
+                        nretry += __popc(m);
+                        if (coll && !later) S[q] = insert_probing(K[q], S[q]);         // the list is full (rare): probe here
+                        __syncwarp();
                     }
-                    __syncwarp();                                          // the lanes that probed rejoin the others here, not iterations later
-                    S[q] = (sa - a_key) >> 3;                              // slot index
-                    OLD[q] = have[q] ? atoms_add_u32(a_cnt + S[q] * 4u, 1u) : 0xFFFFFFFFu;
+                    if (have[q] && !later) count_and_pool(S[q], REF[q]);
                 }
-                // references of the instances that can still belong to a reliable k-mer (they arrived while the count was
-                // below `upper`); ptxas turns the same-address atomic of a warp into one reservation (vote + popc + one ATOMS)
-#pragma unroll
-                for (int q = 0; q < 2; ++q)
-                    if (OLD[q] < upper)
-                    {
-                        const u32 p = atoms_add_u32(a_pn, 1u);
-                        if (p < (u32)POOL) sts_u32(a_pool + p * 4u, (S[q] << 16) | REF[q]);
-                    }
+                __syncwarp();
+            }
+            // the retry list: one entry per lane, the k-mer is cut out of its record again
+            nretry = min(nretry, (u32)RETRY);
+            __syncwarp();
+#pragma unroll 1
+            for (u32 i = 0; i < nretry; i += 32)
+            {
+                const bool mine = i + lane < nretry;
+                if (mine)
+                {
+                    const u32 ref = lds_u32(a_retry + (i + lane) * 4u);
+                    u64 rx, ry;
+                    lds_v2u64(a_rec + (ref & ~31u), rx, ry);
+                    const u32 sh = 2 * (ref & 31u);
+                    const u64 key = canonical_of((sh ? ((rx << sh) | (ry >> (64 - sh))) : rx) & kmask, lsh);
+                    const u32 sa = insert_probing(key, a_key + sk4_slot<SLOTS>(key) * 8u);
+                    count_and_pool(sa, ref);
+                }
                 __syncwarp();
             }
             __syncthreads();                                               // (2) every count is final

@@ -49,7 +49,7 @@ for v in a.variants:
         if first is None:
             first = sig
         print(f"[tune] {v or 'default':40s} wall {best['wall_ms']:8.2f} ms  " + "  ".join(f"{n[:-3]} {best.get(n, 0):7.2f}" for n in keys)
-              + f"  launches {best.get('kernel_launches')}  sizes {sig} {'==' if sig == first else '!= FIRST VARIANT'}", flush=True)
+              + f"  launches {best.get('kernel_launches')}  buckets {sz['partitions']} spilled instances {sz['overflow_instances']}  sizes {sig} {'==' if sig == first else '!= FIRST VARIANT'}", flush=True)
         if a.align:
             t1 = time.perf_counter()
             rows, cols, out = ctx.align()

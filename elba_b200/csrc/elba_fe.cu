@@ -6,6 +6,7 @@
 #include "sketch.cuh"
 #include "matrix_build.cuh"
 #include "spgemm.cuh"
+#include "spgemm2.cuh"
 #include "superkmer.cuh"
 #include "skm_count.cuh"
 #include "xdrop.cuh"
@@ -93,7 +94,9 @@ struct elba_fe_ctx
     DevBuf seed_key, seed_pos, seed_key2, seed_pos2, idx, a_key, a_rowptr, a_col, a_pos, at_key, at_key2, at_pos2, at_colptr, at_row, at_pos, prod;
     int col_bits = 1, read_bits = 1; bool at_built = false;
     // B
-    DevBuf sp_ptr, sp_ent;               // the right operand as the SpGEMM reads it (k_spgemm_operand)
+    DevBuf sp_ptr, sp_ent;               // the right operand by column as the SpGEMM reads it: 32-bit column pointers, {row, pos} entries
+    DevBuf lp_ptr, lp_ent, sp_col, sp_col2, sp_val, sp_val2, tup_cnt, tup_cur, tuples;      // left operand by column (several GPUs); sort scratch; tuple regions
+    const u32 *op_l_cptr = nullptr; const uint2 *op_l_cent = nullptr; u32 op_r_rows = 0;
     DevBuf xd_flag, xd_rowof, xd_prow, xd_pcol, xd_sq, xd_st, xd_nz, xd_out, xd_scratch, xd_max;      // elba_fe_align
     u64 xd_pairs = 0; bool xd_done = false; cudaEvent_t xd_e0 = nullptr, xd_e1 = nullptr;
     DevBuf t_col, t_num, t_seeds, row_off, row_nnz, bins, small_rows, mid_rows, big_rows, ovf_rows, gscratch, b_rowptr, b_col, b_num, b_seeds;
@@ -159,6 +162,17 @@ template <class T> int exclusive_scan_inplace(elba_fe_ctx *ctx, T *d, u64 n)
 }
 
 int sort_pairs(elba_fe_ctx *ctx, const u64 *kin, u64 *kout, const u32 *vin, u32 *vout, u64 n, int begin_bit, int end_bit)
+{
+    if (n == 0) return 0;
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, kin, kout, vin, vout, (int64_t)n, begin_bit, end_bit, ctx->stream));
+    CK(ctx->cubtmp.ensure(need));
+    CK(cub::DeviceRadixSort::SortPairs(ctx->cubtmp.p, need, kin, kout, vin, vout, (int64_t)n, begin_bit, end_bit, ctx->stream));
+    ctx->tm.kernel_launches += (u32)((end_bit - begin_bit + 7) / 8 + 1);
+    return 0;
+}
+
+int sort_pairs_u32_u64(elba_fe_ctx *ctx, const u32 *kin, u32 *kout, const u64 *vin, u64 *vout, u64 n, int begin_bit, int end_bit)
 {
     if (n == 0) return 0;
     size_t need = 0;
@@ -303,7 +317,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut, &ctx->filter,
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
-        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
+        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->lp_ptr, &ctx->lp_ent, &ctx->sp_col, &ctx->sp_col2, &ctx->sp_val, &ctx->sp_val2, &ctx->tup_cnt, &ctx->tup_cur, &ctx->tuples, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf, &ctx->seeds, &ctx->perm, &ctx->rel_idx, &ctx->rel_idx_s,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
@@ -1212,17 +1226,27 @@ static int operands_from_gathered(elba_fe_ctx *ctx, u64 tot)
     CK(ctx->l_col.ensure(4 * std::max<u64>(ln, 1)));
     k_sub_base<<<nblk((u64)nr + 1, 256), 256, 0, st>>>(ctx->l_rowptr.as<int64_t>(), (u64)nr, lb); CKL(); LAUNCHED(ctx);
     if (ln) { k_slice_left<<<nblk(ln, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), (u64)lb, ln, ctx->l_col.as<u32>()); CKL(); LAUNCHED(ctx); }
-    // right: rows C_j, re-sorted by (column, read)
-    const int cb = bits_for(std::max<u64>(R, 2)), rbits = bits_for(std::max<u64>((u64)ncb, 2));
-    CK(ctx->r_key.ensure(8 * std::max<u64>(rn, 1))); CK(ctx->r_key2.ensure(8 * std::max<u64>(rn, 1))); CK(ctx->r_pos.ensure(4 * std::max<u64>(rn, 1)));
-    CK(ctx->r_row.ensure(4 * std::max<u64>(rn, 1))); CK(ctx->r_colptr.ensure(8 * (R + 2)));
-    if (rn) { k_slice_right<<<nblk(rn, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), (u64)rb, rn, (u64)col0, rbits, ctx->r_key.as<u64>()); CKL(); LAUNCHED(ctx); }
-    if ((rc = sort_pairs(ctx, ctx->r_key.as<u64>(), ctx->r_key2.as<u64>(), ctx->g_pos.as<u32>() + rb, ctx->r_pos.as<u32>(), rn, 0, cb + rbits))) return rc;
-    k_segment_ptr<<<nblk(R + 1, 256), 256, 0, st>>>(ctx->r_key2.as<u64>(), rn, R, rbits, ctx->r_colptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
-    if (rn) { k_split_swap<<<nblk(rn, 256), 256, 0, st>>>(ctx->r_key2.as<u64>(), rn, rbits, cb, ctx->r_row.as<u32>(), nullptr); CKL(); LAUNCHED(ctx); }
+    // both operands by column for the expand step (spgemm2.cuh): the slices are sorted by read, a STABLE sort by the column id
+    // alone (4 radix passes instead of 6) leaves the reads ascending inside every column
+    const int cb = bits_for(std::max<u64>(R, 2));
+    if (ln >= (1ull << 32) || rn >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "an SpGEMM operand of one GPU exceeds 2^32 entries");
+    const u64 mx = std::max<u64>(std::max(ln, rn), 1);
+    CK(ctx->sp_col.ensure(4 * mx)); CK(ctx->sp_col2.ensure(4 * mx)); CK(ctx->sp_val.ensure(8 * mx)); CK(ctx->sp_val2.ensure(8 * mx));
+    CK(ctx->lp_ptr.ensure(4 * (R + 2))); CK(ctx->lp_ent.ensure(8 * std::max<u64>(ln, 1)));
+    CK(ctx->sp_ptr.ensure(4 * (R + 2))); CK(ctx->sp_ent.ensure(8 * std::max<u64>(rn, 1)));
+    for (int side = 0; side < 2; ++side)
+    {
+        const u64 b0 = side ? (u64)rb : (u64)lb, n = side ? rn : ln, r0 = side ? (u64)col0 : (u64)row0;
+        u32 *cptr = side ? ctx->sp_ptr.as<u32>() : ctx->lp_ptr.as<u32>(); uint2 *ent = side ? ctx->sp_ent.as<uint2>() : ctx->lp_ent.as<uint2>();
+        if (n) { k_sp2_slice<<<nblk(n, 256), 256, 0, st>>>(ctx->g_key.as<u64>(), ctx->g_pos.as<u32>(), b0, n, r0, ctx->sp_col.as<u32>(), ctx->sp_val.as<u64>()); CKL(); LAUNCHED(ctx); }
+        if ((rc = sort_pairs_u32_u64(ctx, ctx->sp_col.as<u32>(), ctx->sp_col2.as<u32>(), ctx->sp_val.as<u64>(), ctx->sp_val2.as<u64>(), n, 0, cb))) return rc;
+        k_sp2_colptr<<<nblk(n + 1, 256), 256, 0, st>>>(ctx->sp_col2.as<u32>(), n, R, cptr); CKL(); LAUNCHED(ctx);
+        if (n) { k_sp2_unpack_val<<<nblk(n, 256), 256, 0, st>>>(ctx->sp_val2.as<u64>(), n, ent); CKL(); LAUNCHED(ctx); }
+    }
     ctx->op.l_rowptr = ctx->l_rowptr.as<int64_t>(); ctx->op.l_col = ctx->l_col.as<u32>(); ctx->op.l_pos = ctx->g_pos.as<u32>() + lb; ctx->op.l_rows = (u32)nr; ctx->op.l_nnz = ln;
-    ctx->op.r_colptr = ctx->r_colptr.as<int64_t>(); ctx->op.r_row = ctx->r_row.as<u32>(); ctx->op.r_pos = ctx->r_pos.as<u32>(); ctx->op.r_nnz = rn;
-    ctx->op.row0 = row0; ctx->op.col0 = col0;
+    ctx->op.r_colptr = nullptr; ctx->op.r_row = nullptr; ctx->op.r_pos = nullptr; ctx->op.r_nnz = rn;
+    ctx->op.row0 = row0; ctx->op.col0 = col0; ctx->op_r_rows = (u32)ncb;
+    ctx->op_l_cptr = ctx->lp_ptr.as<u32>(); ctx->op_l_cent = ctx->lp_ent.as<uint2>();
     return 0;
 }
 
@@ -1400,15 +1424,20 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     ctx->op.row0 = ctx->op.col0 = ctx->read_id_offset;
     mark(ctx, "csc");
     if (W > 1) { rc = gather_operands(ctx); if (rc) return rc; mark(ctx, "gather_operands"); }
-    if (ctx->op.r_nnz >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "the right SpGEMM operand of one GPU exceeds 2^32 entries");
-    CK(ctx->sp_ptr.ensure(4 * (R + 2))); CK(ctx->sp_ent.ensure(8 * std::max<u64>(ctx->op.r_nnz, 1)));
-    k_spgemm_operand<<<nblk(std::max<u64>(R + 1, ctx->op.r_nnz), 256), 256, 0, st>>>(ctx->op.r_colptr, R, ctx->op.r_row, ctx->op.r_pos, ctx->op.r_nnz,
-        ctx->sp_ptr.as<u32>(), ctx->sp_ent.as<uint2>());
-    CKL(); LAUNCHED(ctx);
+    if (W == 1)
+    {
+        // one GPU: both operands of the expand step are A's transpose: 32-bit column pointers, {row, pos} side by side
+        if (ctx->op.r_nnz >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "the SpGEMM operand of one GPU exceeds 2^32 entries");
+        CK(ctx->sp_ptr.ensure(4 * (R + 2))); CK(ctx->sp_ent.ensure(8 * std::max<u64>(ctx->op.r_nnz, 1)));
+        k_spgemm_operand<<<nblk(std::max<u64>(R + 1, ctx->op.r_nnz), 256), 256, 0, st>>>(ctx->op.r_colptr, R, ctx->op.r_row, ctx->op.r_pos, ctx->op.r_nnz,
+            ctx->sp_ptr.as<u32>(), ctx->sp_ent.as<uint2>());
+        CKL(); LAUNCHED(ctx);
+        ctx->op_l_cptr = ctx->sp_ptr.as<u32>(); ctx->op_l_cent = ctx->sp_ent.as<uint2>(); ctx->op_r_rows = N;
+    }
     // products per row, F
     CK(ctx->prod.ensure(8 * ((size_t)ctx->op.l_rows + 1)));
     CK(cudaMemsetAsync(d_ctr, 0, 64, st));
-    if (ctx->op.l_rows) { k_row_products<<<nblk((u64)ctx->op.l_rows * 32, 256), 256, 0, st>>>(ctx->op.l_rowptr, ctx->op.l_col, ctx->op.r_colptr, ctx->op.l_rows, ctx->prod.as<u64>(), d_ctr); CKL(); LAUNCHED(ctx); }
+    if (ctx->op.l_rows) { k_row_products32<<<nblk((u64)ctx->op.l_rows * 32, 256), 256, 0, st>>>(ctx->op.l_rowptr, ctx->op.l_col, ctx->sp_ptr.as<u32>(), ctx->op.l_rows, ctx->prod.as<u64>(), d_ctr); CKL(); LAUNCHED(ctx); }
     u64 F = 0;
     CK(cudaMemcpyAsync(&F, d_ctr, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[5], st));
@@ -1416,6 +1445,18 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     ctx->sz.products = F;
     mark(ctx, "spgemm_operand+row_products"); trace_flush(ctx, "build_A");
     ctx->phase = 3;
+    return 0;
+}
+
+// rows with more distinct columns than the shared-memory table holds: global-memory tables (the rows are in ctx->ovf_rows)
+static int spgemm_overflow_rows(elba_fe_ctx *ctx, const Sp2Args &A, u64 novf, u64 maxprod)
+{
+    cudaStream_t st = ctx->stream;
+    u64 TS = next_pow2(2 * std::min<u64>(maxprod, (u64)ctx->op_r_rows) + 2);
+    if (TS < 2 * SPG_BLOCK_TS) TS = 2 * SPG_BLOCK_TS;
+    const u32 grid = (u32)std::min<u64>(novf, 64);
+    CK(ctx->gscratch.ensure(sizeof(u32) * 5 * TS * grid));
+    k_sp2_global<<<grid, SPG_BLOCK_THREADS, 0, st>>>(A, ctx->ovf_rows.as<u32>(), (u32)novf, ctx->gscratch.as<u32>(), (u32)TS); CKL(); LAUNCHED(ctx);
     return 0;
 }
 
@@ -1427,6 +1468,7 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
     CK(cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = ctx->stream;
     const u32 N = ctx->op.l_rows; const u64 nnzA = ctx->op.l_nnz;       // rows of this GPU's block of B
+    const u64 R = ctx->sz.reliable, F = ctx->sz.products;
     ctx->b_rows = N;
     CK(cudaEventRecord(ctx->ev[6], st));
     mark(ctx, "begin");
@@ -1434,6 +1476,33 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
     CK(ctx->row_off.ensure(8 * ((size_t)N + 1))); CK(ctx->row_nnz.ensure(4 * ((size_t)N + 1)));
     CK(ctx->small_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->mid_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->big_rows.ensure(4 * ((size_t)N + 1))); CK(ctx->ovf_rows.ensure(4 * ((size_t)N + 1)));
     CK(ctx->bins.ensure(64)); CK(ctx->b_rowptr.ensure(8 * ((size_t)N + 2)));
+    CK(ctx->tup_cnt.ensure(8 * ((size_t)N + 2))); CK(ctx->tup_cur.ensure(4 * ((size_t)N + 1)));
+    // the tuple regions: row i gets exactly its products (minus the pairs of a read with itself, diagonal blocks only)
+    k_sp2_tuple_counts<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->prod.as<u64>(), ctx->op.l_rowptr, N, ctx->op.row0, ctx->op.col0, ctx->op_r_rows, ctx->tup_cnt.as<u64>()); CKL(); LAUNCHED(ctx);
+    int rc = exclusive_scan_inplace(ctx, ctx->tup_cnt.as<u64>(), (u64)N + 1);
+    if (rc) return rc;
+    // rounds: the tuples of all rows at once if they fit the budget (16 B each), else consecutive row ranges
+    u64 budget = 48ull << 30;
+    if (const char *e = getenv("ELBA_FE_TUPLE_MB")) { long long v = atoll(e); if (v >= 1) budget = (u64)v << 20; }
+    std::vector<u32> cut{0, N};
+    u64 tup_cap = std::max<u64>(F, 1);
+    if (F * sizeof(Sp2Tuple) > budget && N > 1)
+    {
+        std::vector<u64> off((size_t)N + 1);
+        CK(cudaMemcpyAsync(off.data(), ctx->tup_cnt.p, 8 * ((size_t)N + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        cut.assign(1, 0); tup_cap = 1;
+        const u64 per = budget / sizeof(Sp2Tuple);
+        u32 r = 0;
+        while (r < N)
+        {
+            u32 e = r + 1;                                              // at least one row per round, whatever its size
+            while (e < N && off[e + 1] - off[r] <= per) ++e;
+            tup_cap = std::max(tup_cap, off[e] - off[r]);
+            cut.push_back(e); r = e;
+        }
+    }
+    CK(ctx->tuples.ensure(sizeof(Sp2Tuple) * tup_cap));
     u64 cap = std::max<u64>(ctx->b_cap_hint, std::max<u64>(nnzA + N, 1024));
     u64 *d_ctr = ctx->ctr.as<u64>();
     u64 h[4] = {0, 0, 0, 0};
@@ -1442,44 +1511,59 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
         CK(ctx->t_col.ensure(4 * cap)); CK(ctx->t_num.ensure(4 * cap)); CK(ctx->t_seeds.ensure(16 * cap));
         CK(cudaMemsetAsync(d_ctr, 0, 64, st)); CK(cudaMemsetAsync(ctx->bins.p, 0, 64, st));
         u32 *d_bins = ctx->bins.as<u32>(); u64 *d_maxprod = reinterpret_cast<u64*>(d_bins + 4);
-        SpgemmArgs A;
+        Sp2Operands op; op.l_cptr = ctx->op_l_cptr; op.l_cent = ctx->op_l_cent; op.r_cptr = ctx->sp_ptr.as<u32>(); op.r_cent = ctx->sp_ent.as<uint2>();
+        op.ncol = R; op.row0 = ctx->op.row0; op.col0 = ctx->op.col0; op.l_rows = N; op.r_rows = ctx->op_r_rows;
+        Sp2Args A;
         A.a_rowptr = ctx->op.l_rowptr; A.a_col = ctx->op.l_col; A.a_pos = ctx->op.l_pos;
-        A.at_ptr = ctx->sp_ptr.as<u32>(); A.at_ent = ctx->sp_ent.as<uint2>();
+        A.tup_off = ctx->tup_cnt.as<u64>(); A.tuples = ctx->tuples.as<Sp2Tuple>(); A.ra = 0; A.rb = N;
+        A.row0 = ctx->op.row0; A.col0 = ctx->op.col0; A.r_rows = ctx->op_r_rows;
         A.nrows = N; A.seed_count = ctx->cfg.seed_count;
         A.t_col = ctx->t_col.as<u32>(); A.t_num = ctx->t_num.as<int32_t>(); A.t_seeds = ctx->t_seeds.as<u32>(); A.cap = cap;
         A.counters = d_ctr; A.row_off = ctx->row_off.as<u64>(); A.row_nnz = ctx->row_nnz.as<u32>();
-        // rows with up to mid_max products would go to the two-warp kernel (k_spgemm_mid).  Measured on C. elegans 40X
-        // (profiles/r1_v8_spgemm.md): 11 two-warp rows per SM are SLOWER than 4 eight-warp rows (8.7 vs 7.3 ms), so the
-        // bin is off unless asked for.
-        u32 mid_max = 0;
-        if (const char *e = getenv("ELBA_FE_SPGEMM_MID")) { long v = atol(e); if (v >= 0 && v <= (long)SPG_MID_MAXPROD) mid_max = (u32)v; }
         if (N)
         {
-            k_spgemm_bin<<<nblk(N, 256), 256, 0, st>>>(ctx->prod.as<u64>(), N, ctx->small_rows.as<u32>(), ctx->mid_rows.as<u32>(), ctx->big_rows.as<u32>(), d_bins, A.row_off, A.row_nnz, d_maxprod, mid_max);
+            // rows by their product count: a warp per light row (256-slot table), a CTA per heavy row (2048 slots), global tables beyond
+            k_spgemm_bin<<<nblk(N, 256), 256, 0, st>>>(ctx->prod.as<u64>(), N, ctx->small_rows.as<u32>(), ctx->mid_rows.as<u32>(), ctx->big_rows.as<u32>(), d_bins, A.row_off, A.row_nnz, d_maxprod, 0u, SP2_WARP_MAXPROD);
             CKL(); LAUNCHED(ctx);
             EventPair &sp = next_pair(ctx->sev, ctx->sev_used);
             CK(cudaEventRecord(sp.a, st));
-            k_spgemm_warp<<<grid_for(ctx, 4), 32 * SPG_WARPS_PER_CTA, 0, st>>>(A, ctx->small_rows.as<u32>(), d_bins); CKL(); LAUNCHED(ctx);
-            k_spgemm_mid<<<grid_for(ctx, 11), SPG_MID_THREADS, 0, st>>>(A, ctx->mid_rows.as<u32>(), d_bins + 2); CKL(); LAUNCHED(ctx);
-            k_spgemm_block<<<grid_for(ctx, 4), SPG_BLOCK_THREADS, 0, st>>>(A, ctx->big_rows.as<u32>(), d_bins + 1, ctx->ovf_rows.as<u32>()); CKL(); LAUNCHED(ctx);
+            for (size_t rd = 0; rd + 1 < cut.size(); ++rd)
+            {
+                A.ra = cut[rd]; A.rb = cut[rd + 1];
+                CK(cudaMemsetAsync(ctx->tup_cur.p, 0, 4 * ((size_t)N + 1), st));
+                if (R) { k_sp2_expand<<<grid_for(ctx, 8), 256, 0, st>>>(op, A.tup_off, ctx->tup_cur.as<u32>(), A.ra, A.rb, ctx->tuples.as<Sp2Tuple>()); CKL(); LAUNCHED(ctx); }
+                if (cut.size() == 2) mark(ctx, "expand");
+                k_sp2_warp<<<grid_for(ctx, 8), 32 * SP2_WARPS, 0, st>>>(A, ctx->small_rows.as<u32>(), d_bins, ctx->big_rows.as<u32>(), d_bins + 1); CKL(); LAUNCHED(ctx);
+                if (cut.size() == 2) mark(ctx, "rows_warp");
+                k_sp2_block<<<grid_for(ctx, 4), SPG_BLOCK_THREADS, 0, st>>>(A, ctx->big_rows.as<u32>(), d_bins + 1, ctx->ovf_rows.as<u32>()); CKL(); LAUNCHED(ctx);
+                if (cut.size() == 2) mark(ctx, "rows_cta");
+                if (cut.size() > 2)
+                {
+                    // several rounds: the rows of this round that overflowed the shared-memory table, before their tuples are overwritten
+                    u64 hc[3];
+                    CK(cudaMemcpyAsync(hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+                    u64 hbm[3];
+                    CK(cudaMemcpyAsync(hbm, ctx->bins.p, sizeof hbm, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    if (hc[2])
+                    {
+                        int rc2 = spgemm_overflow_rows(ctx, A, hc[2], hbm[2]); if (rc2) return rc2;
+                        CK(cudaMemsetAsync(d_ctr + 2, 0, 8, st));
+                    }
+                }
+            }
             CK(cudaEventRecord(sp.b, st));
         }
         u64 hb[6];
         CK(cudaMemcpyAsync(h, d_ctr, sizeof h, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(hb, ctx->bins.p, sizeof hb, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        u64 novf = h[2];
-        if (novf)
+        if (h[2] && cut.size() == 2)
         {
-            // rows with more distinct columns than the shared-memory table holds: global-memory tables
-            u64 maxprod = hb[2];
-            u64 TS = next_pow2(2 * std::min<u64>(maxprod, (u64)N) + 2);
-            if (TS < 2 * SPG_BLOCK_TS) TS = 2 * SPG_BLOCK_TS;
-            u32 grid = (u32)std::min<u64>(novf, 64);
-            CK(ctx->gscratch.ensure(sizeof(u32) * 5 * TS * grid));
             EventPair &sp = next_pair(ctx->sev, ctx->sev_used);
             CK(cudaEventRecord(sp.a, st));
-            k_spgemm_global<<<grid, SPG_BLOCK_THREADS, 0, st>>>(A, ctx->ovf_rows.as<u32>(), (u32)novf, ctx->gscratch.as<u32>(), (u32)TS); CKL(); LAUNCHED(ctx);
+            A.ra = 0; A.rb = N;
+            int rc2 = spgemm_overflow_rows(ctx, A, h[2], hb[2]); if (rc2) return rc2;
             CK(cudaEventRecord(sp.b, st));
             CK(cudaMemcpyAsync(h, d_ctr, sizeof h, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -1494,7 +1578,7 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
     // CSR order
     CK(ctx->b_col.ensure(4 * std::max<u64>(nnzB, 1))); CK(ctx->b_num.ensure(4 * std::max<u64>(nnzB, 1))); CK(ctx->b_seeds.ensure(16 * std::max<u64>(nnzB, 1)));
     k_u32_to_u64<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->row_nnz.as<u32>(), N, reinterpret_cast<u64*>(ctx->b_rowptr.p)); CKL(); LAUNCHED(ctx);
-    int rc = exclusive_scan_inplace(ctx, reinterpret_cast<u64*>(ctx->b_rowptr.p), (u64)N + 1);
+    rc = exclusive_scan_inplace(ctx, reinterpret_cast<u64*>(ctx->b_rowptr.p), (u64)N + 1);
     if (rc) return rc;
     if (N)
     {

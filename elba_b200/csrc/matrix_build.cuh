@@ -68,6 +68,19 @@ __global__ void k_row_products(const int64_t *__restrict__ rowptr, const u32 *__
     if (lane == 0) { prod[warp] = s; if (s) atomicAdd(total, s); }
 }
 
+// the same with the 32-bit column pointers of the column-major operand
+__global__ void k_row_products32(const int64_t *__restrict__ rowptr, const u32 *__restrict__ col, const u32 *__restrict__ cptr,
+                                 u32 nrows, u64 *__restrict__ prod, u64 *__restrict__ total)
+{
+    u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nrows) return;
+    int64_t b = rowptr[warp], e = rowptr[warp + 1];
+    u64 s = 0;
+    for (int64_t p = b + lane; p < e; p += 32) { u32 c = col[p]; s += (u64)(__ldg(cptr + c + 1) - __ldg(cptr + c)); }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) { prod[warp] = s; if (s) atomicAdd(total, s); }
+}
+
 // the right operand of the SpGEMM as the kernel reads it: 32-bit column pointers (half the footprint: most of it stays in
 // L2) and {row, pos} side by side, so one column is one sector instead of three
 __global__ void k_spgemm_operand(const int64_t *__restrict__ colptr, u64 ncol, const u32 *__restrict__ row, const u32 *__restrict__ pos, u64 nnz,

@@ -195,13 +195,13 @@ __device__ bool spgemm_row(const SpgemmArgs &A, u32 row, u32 tid, u32 nth,
 // bin rows by product count
 __global__ void k_spgemm_bin(const u64 *__restrict__ prod, u32 nrows, u32 *__restrict__ small_rows, u32 *__restrict__ mid_rows, u32 *__restrict__ big_rows,
                              u32 *__restrict__ nbins /*[0] small, [1] big, [2] mid; [4..5] max products (u64)*/, u64 *__restrict__ row_off, u32 *__restrict__ row_nnz,
-                             u64 *__restrict__ maxprod, u32 mid_max)
+                             u64 *__restrict__ maxprod, u32 mid_max, u32 small_max = SPG_WARP_MAXPROD)
 {
     u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
     u64 p = prod[r];
     if (p == 0) { row_off[r] = 0; row_nnz[r] = 0; return; }
-    if (p <= SPG_WARP_MAXPROD) small_rows[atomicAdd(&nbins[0], 1u)] = r;
+    if (p <= small_max) small_rows[atomicAdd(&nbins[0], 1u)] = r;
     else if (p <= mid_max) mid_rows[atomicAdd(&nbins[2], 1u)] = r;
     else { big_rows[atomicAdd(&nbins[1], 1u)] = r; atomicMax(maxprod, p); }
 }

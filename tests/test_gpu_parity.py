@@ -155,6 +155,33 @@ def test_heavy_rows_and_hot_kmers():
     assert ref.nnzB > 1800 * 1600, "test must overflow the 2048-slot table"
 
 
+def test_spgemm_in_rounds(fixtures):
+    """The products of A (x) A^T are generated as 16-byte tuples grouped by output row; when they do not fit the budget the rows
+    are multiplied in consecutive ranges (ELBA_FE_TUPLE_MB).  Same bits, also for rows that overflow the shared-memory table."""
+    import os
+    from elba_b200.dnabuffer import DnaBuffer
+    from oracle import oracle as O
+    old = os.environ.get("ELBA_FE_TUPLE_MB")
+    os.environ["ELBA_FE_TUPLE_MB"] = "1"
+    try:
+        dna = fixtures("reads_fa")
+        _compare(_run_cuda(dna, 17, 2, 8), O.run(dna, 17, 2, 8), "rounds, reads.fa")
+        rng = np.random.default_rng(3)
+        core = rng.integers(0, 4, 120)
+        seqs = []
+        for i in range(700):
+            c = core.copy()
+            c[rng.integers(0, 120, 3)] = rng.integers(0, 4, 3)
+            seqs.append("".join("ACGT"[x] for x in np.concatenate([rng.integers(0, 4, 50), c, rng.integers(0, 4, 50)])))
+        dna = DnaBuffer.from_strings(seqs)
+        _compare(_run_cuda(dna, 17, 2, 2000), O.run(dna, 17, 2, 2000), "rounds, heavy rows")
+    finally:
+        if old is None:
+            os.environ.pop("ELBA_FE_TUPLE_MB", None)
+        else:
+            os.environ["ELBA_FE_TUPLE_MB"] = old
+
+
 def test_skewed_partitions():
     """Heavy hitters: poly-A reads put > 1 M instances of ONE k-mer into one level-1 partition.  The optimistic
     partition layout overflows (exact-histogram layout), then that partition's sub-bucket overflows (global-table

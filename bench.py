@@ -333,13 +333,16 @@ def main():
         bytes_sp = 8.0 * sizes_local["products"] + 8.0 * sizes_local["nnzA"] + 28.0 * sizes_local["nnzB_pre"]      # rank 0's block
         ach_sp = bytes_sp / t_sp / 1e9 if t_sp > 0 else 0.0
         Mg = max(M / world, 1)
-        skm = sizes["table_slots"] in (4096, 8192) and k >= 20 and sizes["partitions"] > 4096       # the super-k-mer path ran (superkmer.cuh)
-        names = (("k_skm_scatter", "k_skm_count", "k_resolve") if skm else ("k_scatter1", "k_scatter2+k_count_buckets", "k_probe_filter+k_resolve"))
-        chain = (("all-gather of the 2-bit reads -> " if world > 1 else "") +
-                 "k_skm_scatter -> k_skm_count (pass 2 fused: reliable list + seed list) -> k_unmix, radix sort, k_lookup_build -> k_resolve" if skm else
+        skm = sizes["table_slots"] == 2048 and k >= 20       # the super-k-mer path ran (superkmer.cuh, skm_count.cuh)
+        names = (("k_skm_scatter", "k_skm_count4", "k_seed_keys") if skm else ("k_scatter1", "k_scatter2+k_count_buckets", "k_probe_filter+k_resolve"))
+        chain = (("k_skm_scatter (own reads) -> k_skm_forward (records into the owners' slabs through peer memory) -> " if world > 1 else "k_skm_scatter -> ") +
+                 "k_skm_count4 (bulk-copied slabs, pass 2 fused: reliable list + seed list) -> radix sort of the reliable k-mers, k_rank_finish" +
+                 (" / k_rank_global" if world > 1 else "") + " -> k_seed_keys" if skm else
                  "k_scatter1 -> k_scatter2 -> k_count_buckets -> k_unmix, radix sort, k_lookup_build -> k_probe_filter -> k_resolve")
         kt = {names[0]: tm["partition_ms"], names[1]: tm["count_kernel_ms"], names[2]: tm["lookup_ms"]}
-        kt["glue (sorts, column table, fallbacks, host syncs)"] = max(0.0, 1000.0 * t_count - sum(kt.values()))
+        if world > 1:
+            kt["k_skm_forward + fill words" if skm else "all-to-all"] = tm.get("exchange_ms", 0.0)
+        kt["rest (column ids: sort + rank, fallback for spilled buckets, host)"] = max(0.0, 1000.0 * t_count - sum(kt.values()))
         traffic = ncu_traffic(args.workload) if world == 1 and args.scale == 1.0 else None
         roofline = {"bound": "hbm", "kernel": "counting chain per GPU = everything the reference does in get_kmer_count_map_keys/values: " + chain,
                     "dominant_kernel": max(kt, key=kt.get), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -359,8 +362,13 @@ def main():
             "input_digest": input_digest, "digests": digests, "digest_check": check_digests(args.workload, args.scale, input_digest, digests, digests_e2e),
             "phases_ms": {a: round(b, 4) for a, b in tm.items() if a.endswith("_ms")},
             "roofline": roofline,
-            "roofline_spgemm": {"bound": "hbm", "kernel": "k_spgemm_warp + k_spgemm_block", "achieved": ach_sp, "peak": peak, "unit": "GB/s", "frac": ach_sp / peak,
-                                "algorithmic_bytes": bytes_sp, "seconds": t_sp},
+            "roofline_spgemm": {"bound": "hbm", "kernel": "k_sp2_expand + k_sp2_warp + k_sp2_block (rank 0's block of B)", "achieved": ach_sp, "peak": peak, "unit": "GB/s", "frac": ach_sp / peak,
+                                "algorithmic_bytes": bytes_sp, "algorithmic_bytes_formula": "8 F + 8 nnzA + 28 nnzB_pre (SURVEY.md 8d)", "seconds": t_sp,
+                                "traffic": ((traffic or {}).get("spgemm_dram_bytes"))},
+            "roofline_build_A": {"bound": "hbm", "kernel": "seed keys, radix sorts by (read, column) and (column, read), dedupe, CSR + CSC (rank 0)",
+                                 "achieved": 40.0 * sizes_local["nnzA"] / (tm["build_ms"] / 1e3) / 1e9 if tm["build_ms"] > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                                 "frac": (40.0 * sizes_local["nnzA"] / (tm["build_ms"] / 1e3) / 1e9 / peak) if tm["build_ms"] > 0 else 0.0,
+                                 "algorithmic_bytes": 40.0 * sizes_local["nnzA"], "algorithmic_bytes_formula": "40 B per nnzA (SURVEY.md 8d)", "seconds": tm["build_ms"] / 1e3},
             "e2e": {"value": tot_reads / (ms_e2e / 1000.0), "unit": "reads/s", "h2d_bytes_per_step": int(io[0].item()),
                     "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_e2e},
             "gpu_launches": int(tm["kernel_launches"]), "clocks": clocks,
@@ -369,9 +377,9 @@ def main():
             # NVLink side of the roofline: what this rank received in the counting exchange over its device time
             try:
                 xb, xs = float(tm.get("exchange_mbytes", 0.0)) * 1e6, float(tm.get("exchange_ms", 0.0)) / 1e3
-                line["roofline_nvlink"] = {"bound": "nvlink", "exchange": ("all-gather of the 2-bit reads and read tables" if skm else "all-to-all of the level-1 k-mer partitions"),
-                                           "bytes_per_gpu": xb, "seconds": xs, "achieved": (xb / xs / 1e9) if xs > 0 else 0.0, "peak": 900.0, "unit": "GB/s",
-                                           "frac": (xb / xs / 1e9 / 900.0) if xs > 0 else 0.0, "peak_source": "NVLink 5, 900 GB/s per direction per GPU (nominal)",
+                line["roofline_nvlink"] = {"bound": "nvlink", "exchange": ("super-k-mer records pushed into the owners' slabs through peer memory (k_skm_forward) + fill words" if skm else "all-to-all of the level-1 k-mer partitions"),
+                                           "bytes_per_gpu": xb, "seconds": xs, "achieved": (xb / xs / 1e9) if xs > 0 else 0.0, "peak": 770.0, "unit": "GB/s",
+                                           "frac": (xb / xs / 1e9 / 770.0) if xs > 0 else 0.0, "peak_source": "measured peer copy, 770 GB/s per direction per GPU (B200_PROFILING.md; nominal 900)",
                                            "panel_bytes_per_gpu": float(tm.get("panel_mbytes", 0.0)) * 1e6}
             except Exception as ex:          # never lose the bench line over a reporting extra
                 line["roofline_nvlink"] = {"error": str(ex)}

@@ -95,7 +95,7 @@ struct elba_fe_ctx
     int col_bits = 1, read_bits = 1; bool at_built = false;
     // B
     DevBuf sp_ptr, sp_ent;               // the right operand by column as the SpGEMM reads it: 32-bit column pointers, {row, pos} entries
-    DevBuf lp_ptr, lp_ent, sp_col, sp_col2, sp_val, sp_val2, tup_cnt, tup_cur, tuples;      // left operand by column (several GPUs); sort scratch; tuple regions
+    DevBuf at_ptr32, at_ent, lp_ptr, lp_ent, sp_col, sp_col2, sp_val, sp_val2, tup_cnt, tup_cur, tuples;      // left operand by column (several GPUs); sort scratch; tuple regions
     const u32 *op_l_cptr = nullptr; const uint2 *op_l_cent = nullptr; u32 op_r_rows = 0;
     DevBuf xd_flag, xd_rowof, xd_prow, xd_pcol, xd_sq, xd_st, xd_nz, xd_out, xd_scratch, xd_max;      // elba_fe_align
     u64 xd_pairs = 0; bool xd_done = false; cudaEvent_t xd_e0 = nullptr, xd_e1 = nullptr;
@@ -317,7 +317,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut, &ctx->filter,
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
-        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->lp_ptr, &ctx->lp_ent, &ctx->sp_col, &ctx->sp_col2, &ctx->sp_val, &ctx->sp_val2, &ctx->tup_cnt, &ctx->tup_cur, &ctx->tuples, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
+        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->at_ptr32, &ctx->at_ent, &ctx->lp_ptr, &ctx->lp_ent, &ctx->sp_col, &ctx->sp_col2, &ctx->sp_val, &ctx->sp_val2, &ctx->tup_cnt, &ctx->tup_cur, &ctx->tuples, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf, &ctx->seeds, &ctx->perm, &ctx->rel_idx, &ctx->rel_idx_s,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
@@ -674,7 +674,6 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     sink.slab = ctx->w_slab.buf.as<SkmRec>(); sink.stage = ctx->skm_stage.as<SkmRec>();
     sink.fill = ctx->skm_fill.as<u64>(); sink.rcap = (u32)rcap; sink.nb_own = (u32)NB; sink.nsrc = (u32)W; sink.me = (u32)me;
     sink.read_base = plan.read_base; sink.ovf_cap = ovf_cap;
-    if (W > 1) CK(cudaEventRecord(ctx->ev_x0, st));
     const u32 nmax = skm_nmax(k);
     mark(ctx, "setup");
     EventPair &pp = next_pair(ctx->pev, ctx->pev_used);
@@ -719,6 +718,7 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
         RecForward fw; std::memset(&fw, 0, sizeof fw);
         for (int r = 0; r < W; ++r) fw.slab[r] = (SkmRec*)ctx->w_slab.peer[r];
         fw.stage = ctx->skm_stage.as<SkmRec>(); fw.fill = ctx->skm_fill.as<u64>(); fw.rcap = (u32)rcap; fw.nb_own = (u32)NB; fw.nsrc = (u32)W; fw.me = (u32)me;
+        CK(cudaEventRecord(ctx->ev_x0, st));                 // exchange_ms = the push through peer memory + the fill words
         k_skm_forward<<<grid_for(ctx, 8), 256, 0, st>>>(fw); CKL(); LAUNCHED(ctx);
         mark(ctx, "forward");
         // the reservation words follow the records: rank d gets, from every source, the fill words of its own buckets.  Stream
@@ -1250,17 +1250,21 @@ static int operands_from_gathered(elba_fe_ctx *ctx, u64 tot)
     return 0;
 }
 
-// A^T of the rows of this GPU: the same entries sorted by (column, read) (src/main.cpp:272-273)
-static int build_local_transpose(elba_fe_ctx *ctx)
+// A^T of the rows of this GPU (src/main.cpp:272-273) in the form the SpGEMM reads: 32-bit column pointers, {row, pos} entries.
+// A is sorted by (read, column): a STABLE sort by the column id alone (4 radix passes of a 32-bit key instead of 6 of a 64-bit
+// one) leaves the reads ascending inside every column; the column pointers come from the boundaries of the sorted ids.
+static int build_local_transpose(elba_fe_ctx *ctx, u32 *cptr, uint2 *ent)
 {
     cudaStream_t st = ctx->stream;
     const u64 nnzA = ctx->sz.nnzA, R = ctx->sz.reliable;
-    const int cb = ctx->col_bits, rb = ctx->read_bits;
+    const int cb = ctx->col_bits;
     int rc;
-    if ((rc = sort_pairs(ctx, ctx->at_key.as<u64>(), ctx->at_key2.as<u64>(), ctx->a_pos.as<u32>(), ctx->at_pos.as<u32>(), nnzA, 0, cb + rb))) return rc;
-    k_segment_ptr<<<nblk(R + 1, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, R, rb, ctx->at_colptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
-    if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->at_key2.as<u64>(), nnzA, rb, cb, ctx->at_row.as<u32>(), nullptr); CKL(); LAUNCHED(ctx); }
-    ctx->at_built = true;
+    const u64 na = std::max<u64>(nnzA, 1);
+    CK(ctx->sp_col.ensure(4 * na)); CK(ctx->sp_col2.ensure(4 * na)); CK(ctx->sp_val.ensure(8 * na)); CK(ctx->sp_val2.ensure(8 * na));
+    if (nnzA) { k_csr_to_colsort<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), ctx->a_pos.as<u32>(), nnzA, cb, ctx->sp_col.as<u32>(), ctx->sp_val.as<u64>()); CKL(); LAUNCHED(ctx); }
+    if ((rc = sort_pairs_u32_u64(ctx, ctx->sp_col.as<u32>(), ctx->sp_col2.as<u32>(), ctx->sp_val.as<u64>(), ctx->sp_val2.as<u64>(), nnzA, 0, cb))) return rc;
+    k_sp2_colptr<<<nblk(nnzA + 1, 256), 256, 0, st>>>(ctx->sp_col2.as<u32>(), nnzA, R, cptr); CKL(); LAUNCHED(ctx);
+    if (nnzA) { k_sp2_unpack_val<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->sp_val2.as<u64>(), nnzA, ent); CKL(); LAUNCHED(ctx); }
     return 0;
 }
 
@@ -1407,33 +1411,25 @@ int elba_fe_build_A(elba_fe_ctx *ctx)
     ctx->sz.nnzA = nnzA;
     const u64 na = std::max<u64>(nnzA, 1);
     CK(ctx->a_key.ensure(8 * na)); CK(ctx->a_pos.ensure(4 * na)); CK(ctx->a_col.ensure(4 * na)); CK(ctx->a_rowptr.ensure(8 * ((size_t)N + 2)));
-    CK(ctx->at_key.ensure(8 * na)); CK(ctx->at_key2.ensure(8 * na)); CK(ctx->at_pos2.ensure(4 * na)); CK(ctx->at_row.ensure(4 * na)); CK(ctx->at_pos.ensure(4 * na));
-    CK(ctx->at_colptr.ensure(8 * (R + 2)));
     if (npre) { k_dedupe_write<<<nblk(npre, 256), 256, 0, st>>>(ctx->seed_key2.as<u64>(), ctx->seed_pos2.as<u32>(), ctx->idx.as<u64>(), npre, ctx->a_key.as<u64>(), ctx->a_pos.as<u32>()); CKL(); LAUNCHED(ctx); }
     k_segment_ptr<<<nblk((u64)N + 1, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, N, cb, ctx->a_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
-    if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, cb, rb, ctx->a_col.as<u32>(), ctx->at_key.as<u64>()); CKL(); LAUNCHED(ctx); }
+    if (nnzA) { k_split_swap<<<nblk(nnzA, 256), 256, 0, st>>>(ctx->a_key.as<u64>(), nnzA, cb, rb, ctx->a_col.as<u32>(), nullptr); CKL(); LAUNCHED(ctx); }
     mark(ctx, "sort_dedupe_csr");
-    // transpose: the same entries sorted by (column, read).  Several GPUs: the right operand of the SpGEMM is built from the
-    // gathered rows (gather_operands); the transpose of the own rows is only made when somebody asks for it (elba_fe_get_AT)
+    // transpose: the same entries by column.  One GPU: it is both operands of the expand step.  Several GPUs: the operands are
+    // built from the gathered rows (gather_operands); the transpose of the own rows is only made when somebody asks for it (elba_fe_get_AT)
     ctx->at_built = false;
-    if (W == 1) { if ((rc = build_local_transpose(ctx))) return rc; }
-    // operands of B = A (x) A^T: one GPU multiplies A by its own transpose
     ctx->op.l_rowptr = ctx->a_rowptr.as<int64_t>(); ctx->op.l_col = ctx->a_col.as<u32>(); ctx->op.l_pos = ctx->a_pos.as<u32>(); ctx->op.l_rows = N; ctx->op.l_nnz = nnzA;
-    ctx->op.r_colptr = ctx->at_colptr.as<int64_t>(); ctx->op.r_row = ctx->at_row.as<u32>(); ctx->op.r_pos = ctx->at_pos.as<u32>();
-    ctx->op.r_nnz = nnzA;
+    ctx->op.r_colptr = nullptr; ctx->op.r_row = nullptr; ctx->op.r_pos = nullptr; ctx->op.r_nnz = nnzA;
     ctx->op.row0 = ctx->op.col0 = ctx->read_id_offset;
-    mark(ctx, "csc");
-    if (W > 1) { rc = gather_operands(ctx); if (rc) return rc; mark(ctx, "gather_operands"); }
     if (W == 1)
     {
-        // one GPU: both operands of the expand step are A's transpose: 32-bit column pointers, {row, pos} side by side
-        if (ctx->op.r_nnz >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "the SpGEMM operand of one GPU exceeds 2^32 entries");
-        CK(ctx->sp_ptr.ensure(4 * (R + 2))); CK(ctx->sp_ent.ensure(8 * std::max<u64>(ctx->op.r_nnz, 1)));
-        k_spgemm_operand<<<nblk(std::max<u64>(R + 1, ctx->op.r_nnz), 256), 256, 0, st>>>(ctx->op.r_colptr, R, ctx->op.r_row, ctx->op.r_pos, ctx->op.r_nnz,
-            ctx->sp_ptr.as<u32>(), ctx->sp_ent.as<uint2>());
-        CKL(); LAUNCHED(ctx);
+        if (nnzA >= (1ull << 32)) return fail(ctx, ELBA_FE_ERR_INVALID, "the SpGEMM operand of one GPU exceeds 2^32 entries");
+        CK(ctx->sp_ptr.ensure(4 * (R + 2))); CK(ctx->sp_ent.ensure(8 * na));
+        if ((rc = build_local_transpose(ctx, ctx->sp_ptr.as<u32>(), ctx->sp_ent.as<uint2>()))) return rc;
         ctx->op_l_cptr = ctx->sp_ptr.as<u32>(); ctx->op_l_cent = ctx->sp_ent.as<uint2>(); ctx->op_r_rows = N;
     }
+    mark(ctx, "csc");
+    if (W > 1) { rc = gather_operands(ctx); if (rc) return rc; mark(ctx, "gather_operands"); }
     // products per row, F
     CK(ctx->prod.ensure(8 * ((size_t)ctx->op.l_rows + 1)));
     CK(cudaMemsetAsync(d_ctr, 0, 64, st));
@@ -1780,7 +1776,23 @@ int elba_fe_get_AT(elba_fe_ctx *ctx, int64_t *colptr, uint32_t *row, uint32_t *p
 {
     if (!ctx) return ELBA_FE_ERR_INVALID;
     if (ctx->phase < 3) return fail(ctx, ELBA_FE_ERR_STATE, "A not built");
-    if (!ctx->at_built) { int rc = build_local_transpose(ctx); if (rc) return rc; }
+    if (!ctx->at_built)
+    {
+        // the API's form of the transpose (64-bit column pointers, rows and positions apart), made on request
+        const u64 R = ctx->sz.reliable, na = std::max<u64>(ctx->sz.nnzA, 1);
+        CK(ctx->at_colptr.ensure(8 * (R + 2))); CK(ctx->at_row.ensure(4 * na)); CK(ctx->at_pos.ensure(4 * na));
+        const u32 *cptr = ctx->sp_ptr.as<u32>(); const uint2 *ent = ctx->sp_ent.as<uint2>();
+        if (ctx->comm.nranks > 1)
+        {
+            // several GPUs: sp_ptr / sp_ent hold the gathered right operand; transpose the own rows into the left-operand scratch
+            CK(ctx->at_ptr32.ensure(4 * (R + 2))); CK(ctx->at_ent.ensure(8 * na));
+            int rc = build_local_transpose(ctx, ctx->at_ptr32.as<u32>(), ctx->at_ent.as<uint2>()); if (rc) return rc;
+            cptr = ctx->at_ptr32.as<u32>(); ent = ctx->at_ent.as<uint2>();
+        }
+        k_transpose_api<<<nblk(std::max<u64>(R + 1, ctx->sz.nnzA), 256), 256, 0, ctx->stream>>>(cptr, ent, R, ctx->sz.nnzA, ctx->at_colptr.as<int64_t>(), ctx->at_row.as<u32>(), ctx->at_pos.as<u32>());
+        CKL(); LAUNCHED(ctx);
+        ctx->at_built = true;
+    }
     D2H(colptr, ctx->at_colptr.p, 8 * (ctx->sz.reliable + 1)); D2H(row, ctx->at_row.p, 4 * ctx->sz.nnzA); D2H(pos, ctx->at_pos.p, 4 * ctx->sz.nnzA);
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -339,6 +339,23 @@ __global__ void k_sp2_colptr(const u32 *__restrict__ col_sorted, u64 n, u64 ncol
     for (u64 c = c_prev; c < c_here; ++c) cptr[c] = (u32)i;               // columns (c_prev .. col[i]] start at i; empty ones in between too
 }
 
+// A (key = read << col_bits | column, sorted) -> sort key (column) and value (read << 32 | pos) of the stable sort by column
+__global__ void k_csr_to_colsort(const u64 *__restrict__ key, const u32 *__restrict__ pos, u64 n, int col_bits, u32 *__restrict__ col, u64 *__restrict__ val)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 kk = key[i];
+    col[i] = (u32)(kk & ((1ull << col_bits) - 1));
+    val[i] = ((kk >> col_bits) << 32) | pos[i];
+}
+// the column-major operand in the C ABI's form: 64-bit column pointers, rows and positions in separate arrays
+__global__ void k_transpose_api(const u32 *__restrict__ cptr, const uint2 *__restrict__ ent, u64 ncol, u64 nnz, int64_t *__restrict__ colptr, u32 *__restrict__ row, u32 *__restrict__ pos)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= ncol) colptr[i] = (int64_t)cptr[i];
+    if (i < nnz) { const uint2 e = ent[i]; row[i] = e.x; pos[i] = e.y; }
+}
+
 // slice [b, b + n) of the gathered A (key = global read << 32 | column, sorted by read): sort keys / values for the column-major operand
 __global__ void k_sp2_slice(const u64 *__restrict__ key, const u32 *__restrict__ pos, u64 b, u64 n, u64 r0, u32 *__restrict__ col, u64 *__restrict__ val)
 {

@@ -206,9 +206,10 @@ typedef struct {
     uint32_t kernel_launches; /* kernels of this library launched since create/reset */
     float partition_ms;     /* histogram + scatter kernels */
     float lookup_ms;        /* second sweep (seed emission) kernel */
-    float exchange_ms;      /* several GPUs: the all-to-all of the k-mer partitions */
+    float exchange_ms;      /* several GPUs: the k-mer exchange: super-k-mer records pushed into the owners' slabs through peer memory + the
+                               fill words (k >= 20), or the all-to-all of the level-1 partitions (k < 20) */
     float exchange_mbytes;  /* MB this rank sent in it */
-    float panel_mbytes;     /* MB this rank received in the all-gather of A's row blocks */
+    float panel_mbytes;     /* MB this rank received as routed seed triples and in the all-gather of A's row blocks */
     float align_ms;         /* elba_fe_align: pair selection + the X-drop kernel */
     float reserved[2];
 } elba_fe_timings_t;

@@ -81,11 +81,11 @@ struct elba_fe_ctx
     u64 skm_reliable = 0;                                // super-k-mer path: reliable k-mers among the (holey) list entries handed out
     // several GPUs, super-k-mer path: every GPU parses its own reads and writes the records into the owners' slabs (peer memory)
     Window w_slab, w_ovf, w_octr, w_rkey, w_rpos, w_rcnt;     // record slabs, overflow list + its counters, routed seed triples + their counts
-    DevBuf skm_fillin, skm_plan, skm_stage, d_roff, route_cur, rel_gid, glob_key, glob_cnt, glob_gid, glob_cnt_in;
+    DevBuf agpad, skm_fillin, skm_plan, skm_stage, d_roff, route_cur, rel_gid, glob_key, glob_cnt, glob_gid, glob_cnt_in;
     std::vector<u64> roff;                                   // [W + 1] first global read id of every rank's block
     int64_t read_base0 = 0;                                  // global id of the first read of rank 0
     bool p2p = false, kmers_distributed = false; u64 R_local = 0; std::vector<u64> rel_counts;
-    u64 Ms_total = 0, route_cap = 0;
+    u64 Ms_total = 0, Ms_max = 0, route_cap = 0; u64 setup_sig[3] = {0, 0, 0}; bool setup_valid = false;
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_x0 = nullptr, ev_x1 = nullptr;
     u64 exchange_bytes = 0, panel_bytes = 0;
     u64 scratch_mb = 64;
@@ -317,7 +317,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut, &ctx->filter,
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
-        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->at_ptr32, &ctx->at_ent, &ctx->lp_ptr, &ctx->lp_ent, &ctx->sp_col, &ctx->sp_col2, &ctx->sp_val, &ctx->sp_val2, &ctx->tup_cnt, &ctx->tup_cur, &ctx->tuples, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
+        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->at_ptr32, &ctx->at_ent, &ctx->lp_ptr, &ctx->lp_ent, &ctx->sp_col, &ctx->sp_col2, &ctx->sp_val, &ctx->sp_val2, &ctx->tup_cnt, &ctx->tup_cur, &ctx->tuples, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->agpad, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf, &ctx->seeds, &ctx->perm, &ctx->rel_idx, &ctx->rel_idx_s,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
@@ -469,9 +469,29 @@ static int allgather_u64(elba_fe_ctx *ctx, u64 mine, std::vector<u64> &all)
 // every rank contributes count[r] elements of `esize` bytes; recv holds them in rank order
 static int allgatherv(elba_fe_ctx *ctx, const void *send, void *recv, const std::vector<u64> &count, size_t esize)
 {
-    // every rank sends its block to every other rank and receives theirs: W - 1 point-to-point transfers in each direction in
-    // one group (NVSwitch gives every pair full bandwidth); the own block is a local copy
     const int W = ctx->comm.nranks, me = ctx->comm.rank;
+    u64 mx = 0, tot = 0;
+    for (int r = 0; r < W; ++r) { mx = std::max(mx, count[r]); tot += count[r]; }
+    if (tot == 0) return 0;
+    if (mx * (u64)W <= tot + tot / 4 + 4096 && ctx->comm.api->AllGather)
+    {
+        // balanced blocks (the usual case): one ncclAllGather of blocks padded to the largest (NVSwitch: every GPU receives from all
+        // others at once), then the blocks are closed up by device-to-device copies
+        const size_t blk = (size_t)mx * esize;
+        CK(ctx->agpad.ensure(blk * (size_t)(W + 1)));
+        char *pad = ctx->agpad.as<char>();
+        if (count[me]) CK(cudaMemcpyAsync(pad + blk * (size_t)W, send, count[me] * esize, cudaMemcpyDeviceToDevice, ctx->stream));
+        NC(ctx->comm.api->AllGather(pad + blk * (size_t)W, pad, blk, ncclUint8, ctx->comm.comm, ctx->stream));
+        u64 off = 0;
+        for (int r = 0; r < W; ++r)
+        {
+            if (count[r]) CK(cudaMemcpyAsync((char*)recv + off * esize, pad + blk * (size_t)r, count[r] * esize, cudaMemcpyDeviceToDevice, ctx->stream));
+            off += count[r];
+        }
+        return 0;
+    }
+    // uneven blocks: every rank sends its block to every other rank and receives theirs, W - 1 point-to-point transfers in each
+    // direction in one group; the own block is a local copy
     u64 off = 0, myoff = 0;
     for (int r = 0; r < me; ++r) myoff += count[r];
     if (count[me]) CK(cudaMemcpyAsync((char*)recv + myoff * esize, send, count[me] * esize, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -573,15 +593,21 @@ static int stream_barrier(elba_fe_ctx *ctx)
 static int multi_setup(elba_fe_ctx *ctx, bool &ok)
 {
     const int W = ctx->comm.nranks;
-    std::vector<u64> nr, ro, ms;
     int rc;
+    // the layout of the reads over the ranks rarely changes between passes: one scalar collective says whether anybody's did
+    const u64 sig[3] = { (u64)ctx->n, (u64)ctx->read_id_offset, ctx->Ms };
+    u64 changed = !ctx->setup_valid || sig[0] != ctx->setup_sig[0] || sig[1] != ctx->setup_sig[1] || sig[2] != ctx->setup_sig[2];
+    if ((rc = allreduce_u64(ctx, &changed, 1, ncclMax))) return rc;
+    if (!changed) { ok = ctx->p2p; return 0; }
+    ctx->setup_valid = false;
+    std::vector<u64> nr, ro, ms;
     if ((rc = allgather_u64(ctx, ctx->n, nr))) return rc;
     if ((rc = allgather_u64(ctx, (u64)ctx->read_id_offset, ro))) return rc;
     if ((rc = allgather_u64(ctx, ctx->Ms, ms))) return rc;
-    u64 Nt = 0, Mt = 0; ok = W <= SK_MAXW;
-    for (int r = 0; r < W; ++r) { if (ro[r] != ro[0] + Nt) ok = false; Nt += nr[r]; Mt += ms[r]; }
+    u64 Nt = 0, Mt = 0, Mx = 0; ok = W <= SK_MAXW;
+    for (int r = 0; r < W; ++r) { if (ro[r] != ro[0] + Nt) ok = false; Nt += nr[r]; Mt += ms[r]; Mx = std::max(Mx, ms[r]); }
     if (ro[0] + Nt >= 0xFFFFFFF0ull) ok = false;
-    ctx->N_total = Nt; ctx->Ms_total = Mt; ctx->read_base0 = (int64_t)ro[0];
+    ctx->N_total = Nt; ctx->Ms_total = Mt; ctx->Ms_max = Mx; ctx->read_base0 = (int64_t)ro[0];
     ctx->roff.assign(W + 1, ro[0] + Nt);
     for (int r = 0; r < W; ++r) ctx->roff[r] = ro[r];
     if (ok)
@@ -603,6 +629,7 @@ static int multi_setup(elba_fe_ctx *ctx, bool &ok)
         if (!can) ok = false;
     }
     ctx->p2p = ok;
+    ctx->setup_sig[0] = sig[0]; ctx->setup_sig[1] = sig[1]; ctx->setup_sig[2] = sig[2]; ctx->setup_valid = true;
     return 0;
 }
 
@@ -819,13 +846,13 @@ int elba_fe_count(elba_fe_ctx *ctx)
     const int W = ctx->comm.nranks, me = ctx->comm.rank;
     // instances over all GPUs decide the partitioning; the largest local share decides the slab capacity
     u64 Ms_total = Ms, Ms_max = Ms;
+    bool p2p_ok = false;
+    ctx->p2p = W > 1 ? ctx->p2p : false;
     if (W > 1)
     {
-        int rc0;
-        if ((rc0 = allreduce_u64(ctx, &Ms_total, 1, ncclSum))) return rc0;
-        if ((rc0 = allreduce_u64(ctx, &Ms_max, 1, ncclMax))) return rc0;
-        u64 nt = ctx->n; if ((rc0 = allreduce_u64(ctx, &nt, 1, ncclSum))) return rc0;
-        ctx->N_total = nt;
+        int rc0 = multi_setup(ctx, p2p_ok);          // collective: read layout over the ranks, totals, peer access
+        if (rc0) return rc0;
+        Ms_total = ctx->Ms_total; Ms_max = ctx->Ms_max;
     }
     else ctx->N_total = ctx->n;
     // balanced digits: P1 ~ P2 ~ sqrt(#sub-buckets); both scatters then write runs of similar length
@@ -841,14 +868,12 @@ int elba_fe_count(elba_fe_ctx *ctx)
     bool use_skm = !direct && stride == 1 && skm_geometry(k, skm_m, skm_W);
     if (const char *e = getenv("ELBA_FE_COUNT_PATH")) { if (!std::strcmp(e, "hash")) use_skm = false; }
     SkmPlan plan; plan.rv = rv; plan.Ms = Ms; plan.read_base = 0; plan.nranks = 1; plan.rank = 0;
-    ctx->p2p = false; ctx->kmers_distributed = false; ctx->read_base0 = ctx->read_id_offset;
-    if (W > 1)
+    ctx->kmers_distributed = false;
+    if (W == 1) ctx->read_base0 = ctx->read_id_offset;
+    else
     {
-        // every GPU parses ITS OWN reads; the records go straight into the owners' slabs through peer memory (superkmer.cuh)
-        bool ok = false;
-        int rc0 = multi_setup(ctx, ok);
-        if (rc0) return rc0;
-        if (use_skm && !ok) use_skm = false;                             // read blocks not consecutive over the ranks / no peer access: hash path
+        // every GPU parses ITS OWN reads; the records go into the owners' slabs through peer memory (superkmer.cuh)
+        if (use_skm && !p2p_ok) use_skm = false;                         // read blocks not consecutive over the ranks / no peer access: hash path
         if (use_skm) { plan.Ms = ctx->Ms_total; plan.read_base = (u32)ctx->read_id_offset; plan.nranks = W; plan.rank = me; }
     }
     if (!use_skm) { int rcw = wait_reads(ctx); if (rcw) return rcw; }                 // only the super-k-mer scatter follows an upload slice by slice

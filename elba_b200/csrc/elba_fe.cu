@@ -81,7 +81,7 @@ struct elba_fe_ctx
     u64 skm_reliable = 0;                                // super-k-mer path: reliable k-mers among the (holey) list entries handed out
     // several GPUs, super-k-mer path: every GPU parses its own reads and writes the records into the owners' slabs (peer memory)
     Window w_slab, w_ovf, w_octr, w_rkey, w_rpos, w_rcnt;     // record slabs, overflow list + its counters, routed seed triples + their counts
-    DevBuf agpad, skm_fillin, skm_plan, skm_stage, d_roff, route_cur, rel_gid, glob_key, glob_cnt, glob_gid, glob_cnt_in;
+    DevBuf agpad, skm_fillin, skm_plan, skm_stage, skm_foff, skm_inoff, d_roff, route_cur, rel_gid, glob_key, glob_cnt, glob_gid, glob_cnt_in;
     std::vector<u64> roff;                                   // [W + 1] first global read id of every rank's block
     int64_t read_base0 = 0;                                  // global id of the first read of rank 0
     bool p2p = false, kmers_distributed = false; u64 R_local = 0; std::vector<u64> rel_counts;
@@ -317,7 +317,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->table, &ctx->cand, &ctx->ctr, &ctx->partbuf, &ctx->phist, &ctx->pcursor, &ctx->rel_key, &ctx->rel_cnt, &ctx->rel_key_s, &ctx->rel_cnt_s, &ctx->lut, &ctx->filter,
         &ctx->seed_key, &ctx->seed_pos, &ctx->seed_key2, &ctx->seed_pos2, &ctx->idx, &ctx->a_key, &ctx->a_rowptr, &ctx->a_col, &ctx->a_pos,
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
-        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->at_ptr32, &ctx->at_ent, &ctx->lp_ptr, &ctx->lp_ent, &ctx->sp_col, &ctx->sp_col2, &ctx->sp_val, &ctx->sp_val2, &ctx->tup_cnt, &ctx->tup_cur, &ctx->tuples, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->agpad, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
+        &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->at_ptr32, &ctx->at_ent, &ctx->lp_ptr, &ctx->lp_ent, &ctx->sp_col, &ctx->sp_col2, &ctx->sp_val, &ctx->sp_val2, &ctx->tup_cnt, &ctx->tup_cur, &ctx->tuples, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->agpad, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->skm_foff, &ctx->skm_inoff, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf, &ctx->seeds, &ctx->perm, &ctx->rel_idx, &ctx->rel_idx_s,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
@@ -738,13 +738,17 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
     }
     CK(cudaEventRecord(pp.b, st));
     mark(ctx, "scatter");
-    RecSlabs in; in.slab = ctx->w_slab.buf.as<SkmRec>(); in.fill = ctx->skm_fill.as<u64>(); in.plan = in.fill; in.rcap = (u32)rcap; in.nsrc = (u32)W; in.nb = (u32)NB;
+    RecSlabs in; in.slab = ctx->w_slab.buf.as<SkmRec>(); in.fill = ctx->skm_fill.as<u64>(); in.plan = in.fill; in.off = nullptr; in.rcap = (u32)rcap; in.nsrc = (u32)W; in.nb = (u32)NB; in.me = (u32)me;
     if (W > 1)
     {
-        // the staged records of the other GPUs' buckets go into their owners' slabs through peer memory
+        // the staged records of the other GPUs' buckets go into their owners' slabs through peer memory, packed: where a bucket
+        // starts inside the region = the exclusive scan of the record counts (the owner redoes that scan from the fill words)
+        CK(ctx->skm_foff.ensure(8 * (NBg + 1))); CK(ctx->skm_inoff.ensure(8 * (NBg + 1)));
+        k_skm_forward_counts<<<nblk(NBg + 1, 256), 256, 0, st>>>(ctx->skm_fill.as<u64>(), NBg, (u32)rcap, ctx->skm_foff.as<u64>()); CKL(); LAUNCHED(ctx);
+        if ((rc = exclusive_scan_inplace(ctx, ctx->skm_foff.as<u64>(), NBg + 1))) return rc;
         RecForward fw; std::memset(&fw, 0, sizeof fw);
         for (int r = 0; r < W; ++r) fw.slab[r] = (SkmRec*)ctx->w_slab.peer[r];
-        fw.stage = ctx->skm_stage.as<SkmRec>(); fw.fill = ctx->skm_fill.as<u64>(); fw.rcap = (u32)rcap; fw.nb_own = (u32)NB; fw.nsrc = (u32)W; fw.me = (u32)me;
+        fw.stage = ctx->skm_stage.as<SkmRec>(); fw.fill = ctx->skm_fill.as<u64>(); fw.off = ctx->skm_foff.as<u64>(); fw.rcap = (u32)rcap; fw.nb_own = (u32)NB; fw.nsrc = (u32)W; fw.me = (u32)me;
         CK(cudaEventRecord(ctx->ev_x0, st));                 // exchange_ms = the push through peer memory + the fill words
         k_skm_forward<<<grid_for(ctx, 8), 256, 0, st>>>(fw); CKL(); LAUNCHED(ctx);
         mark(ctx, "forward");
@@ -759,6 +763,9 @@ static int count_superkmers(elba_fe_ctx *ctx, const SkmPlan &plan, int m, int Wm
         NC(ctx->comm.api->GroupEnd());
         CK(cudaEventRecord(ctx->ev_x1, st));
         k_skm_plan<<<nblk(NB, 256), 256, 0, st>>>(ctx->skm_fillin.as<u64>(), (u32)NB, (u32)W, (u32)rcap, ctx->skm_plan.as<u64>()); CKL(); LAUNCHED(ctx);
+        k_skm_forward_counts<<<nblk(NBg + 1, 256), 256, 0, st>>>(ctx->skm_fillin.as<u64>(), NBg, (u32)rcap, ctx->skm_inoff.as<u64>()); CKL(); LAUNCHED(ctx);
+        if ((rc = exclusive_scan_inplace(ctx, ctx->skm_inoff.as<u64>(), NBg + 1))) return rc;
+        in.off = ctx->skm_inoff.as<u64>();
         k_remote_records<<<grid_for(ctx, 2), 256, 0, st>>>(ctx->skm_fill.as<u64>(), NBg, (u32)NB, (u32)me, d_ctr + 9); CKL(); LAUNCHED(ctx);
         in.fill = ctx->skm_fillin.as<u64>(); in.plan = ctx->skm_plan.as<u64>();
         mark(ctx, "fill_exchange");

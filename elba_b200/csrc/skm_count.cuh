@@ -32,11 +32,21 @@ struct __align__(16) Seed { u32 id, pos, read, pad; };
 static constexpr u32 SEED_HOLE = 0xFFFFFFFFu;
 struct SeedSink2 { Seed *out; u64 *cursor; u64 cap; };
 
-// Records of the buckets this GPU counts.  Bucket b has one sub-slab per source GPU (one GPU: one source):
-// slab[(b * nsrc + s) * rcap ...] holds min(records offered by s, rcap) records in the order of their slots, and
+// Records of the buckets this GPU counts.  The slab has one region per source GPU (one GPU: one source): region s starts at
+// slab + s * nb * rcap.  The GPU's OWN region holds bucket b at b * rcap (the scatter's slots); the region of another source
+// is packed: bucket b at off[s * nb + b] - off[s * nb] (exclusive scan of min(records offered, rcap)).  Either way the bucket's
+// min(records offered by s, rcap) records lie contiguously in the order of their slots, and
 // fill[s * nb + b] = (instances offered << 32) | records offered by source s (the scatter's reservation word, superkmer.cuh).
 // plan[b] = the same summed over the sources, records = PLAN_SPILL if a source was offered more than rcap (one GPU: plan == fill).
-struct RecSlabs { const SkmRec *slab; const u64 *fill; const u64 *plan; u32 rcap, nsrc, nb; };
+struct RecSlabs
+{
+    const SkmRec *slab; const u64 *fill; const u64 *plan; const u64 *off; u32 rcap, nsrc, nb, me;
+    __device__ __forceinline__ const SkmRec *bucket(u32 s, u64 b) const
+    {
+        const SkmRec *region = slab + (u64)s * nb * rcap;
+        return (s == me) ? region + b * rcap : region + (__ldg(off + (u64)s * nb + b) - __ldg(off + (u64)s * nb));
+    }
+};
 struct RecOverflow { SkmRec *list; u64 *cursor; u64 *inst; u64 cap; };
 static constexpr u32 PLAN_SPILL = 0xFFFFFFFFu;
 
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
         if (in.nsrc == 1)
         {
             s_src_rec[0] = 0; s_src_inst[0] = 0; s_src_rec[1] = (u32)fw; s_src_inst[1] = (u32)(fw >> 32);
-            bulk_g2s(s_rec, in.slab + bb * in.rcap, (u32)fw * 32u, s_bar);
+            bulk_g2s(s_rec, in.bucket(0, bb), (u32)fw * 32u, s_bar);
         }
         else
         {
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
             {
                 const u64 w = __ldg(in.fill + (u64)sidx * in.nb + bb);
                 s_src_rec[sidx] = nr; s_src_inst[sidx] = ni;
-                if ((u32)w) bulk_g2s(s_rec + nr, in.slab + (bb * in.nsrc + sidx) * in.rcap, (u32)w * 32u, s_bar);
+                if ((u32)w) bulk_g2s(s_rec + nr, in.bucket(sidx, bb), min((u32)w, in.rcap) * 32u, s_bar);
                 nr += (u32)w; ni += (u32)(w >> 32);
             }
             s_src_rec[in.nsrc] = nr; s_src_inst[in.nsrc] = ni;
@@ -171,11 +181,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
     };
     auto prefetch = [&](u64 bb, u64 fw)
     {
-        if (in.nsrc == 1) { bulk_prefetch_l2(in.slab + bb * in.rcap, (u32)fw * 32u); return; }
+        if (in.nsrc == 1) { bulk_prefetch_l2(in.bucket(0, bb), (u32)fw * 32u); return; }
         for (u32 sidx = 0; sidx < in.nsrc; ++sidx)
         {
             const u32 fs = (u32)__ldg(in.fill + (u64)sidx * in.nb + bb);
-            if (fs) bulk_prefetch_l2(in.slab + (bb * in.nsrc + sidx) * in.rcap, fs * 32u);
+            if (fs) bulk_prefetch_l2(in.bucket(sidx, bb), min(fs, in.rcap) * 32u);
         }
     };
     if (tid == 0)
@@ -390,7 +400,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_skm_count4(RecSlabs in, u32 n
                 if (nrec == 0) continue;                                   // uniform
                 if (tid == 0) s_spill_base = atomicAdd(ovf.cursor, (u64)nrec);
                 __syncthreads();
-                const SkmRec *__restrict__ recs = in.slab + ((u64)b * in.nsrc + sidx) * in.rcap;
+                const SkmRec *__restrict__ recs = in.bucket(sidx, b);
                 u32 ninst = 0;
 #pragma unroll 1
                 for (u32 rr = tid; rr < nrec; rr += THREADS)

@@ -93,8 +93,8 @@ __device__ __forceinline__ u32 skm_mix(u32 v)
 
 static constexpr int SK_MAXW = 16;                    // GPUs the peer-memory record exchange addresses
 
-// Where records go.  Every GPU parses ITS OWN reads.  An owner's bucket has one sub-slab per source GPU,
-// [local bucket][source][rcap], so that the slot reservation stays a LOCAL atomic: fill[global bucket] counts what THIS GPU
+// Where records go.  Every GPU parses ITS OWN reads.  An owner's slab has one region per source GPU (its own region holds
+// one sub-slab of rcap records per bucket, the others are packed by k_skm_forward), so that the slot reservation stays a LOCAL atomic: fill[global bucket] counts what THIS GPU
 // offered (records in the low half, instances in the high half).  Records of this GPU's own buckets go straight into its
 // slab; records of other GPUs' buckets are staged locally in the same shape (stage[global bucket][rcap]) and then pushed
 // into the owners' slabs through peer memory by k_skm_forward: bucket after bucket, only the filled part, in address order.
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
                     const u64 spare = ((fw[i] >> 32) << 8) | n[i];
                     if (slot < sink.rcap)
                     {
-                        SkmRec *dst = own[i] == sink.me ? sink.slab + (((u64)b[i] * sink.nsrc + sink.me) * sink.rcap + slot)
+                        SkmRec *dst = own[i] == sink.me ? sink.slab + (((u64)sink.me * sink.nb_own + b[i]) * sink.rcap + slot)
                                                         : sink.stage + (((u64)own[i] * sink.nb_own + b[i]) * sink.rcap + slot);
                         skm_store(dst, rec[i].x, rec[i].y, meta0 + s0[i], spare);
                     }
@@ -243,26 +243,40 @@ __global__ void __launch_bounds__(SK_THREADS, 4) k_skm_scatter(ReadsView rv, int
 // Several GPUs: the staged records of the other GPUs' buckets go into the owners' slabs (slab[r] = rank r's slab mapped into
 // this process, CUDA IPC).  One warp per (owner, bucket): min(records offered, rcap) records = one contiguous run of 32-byte
 // records on both sides, moved as 16-byte pieces; the buckets of one owner are visited in address order.
-struct RecForward { SkmRec *slab[SK_MAXW]; const SkmRec *stage; const u64 *fill; u32 rcap, nb_own, nsrc, me; };
+struct RecForward { SkmRec *slab[SK_MAXW]; const SkmRec *stage; const u64 *fill; const u64 *off; u32 rcap, nb_own, nsrc, me; };
+
+// records this GPU offered to global bucket g that the owner will read: min(offered, rcap) (the rest went to the overflow list)
+__global__ void k_skm_forward_counts(const u64 *__restrict__ fill, u64 nbg, u32 rcap, u64 *__restrict__ cnt)
+{
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g <= nbg) cnt[g] = g < nbg ? (u64)min((u32)fill[g], rcap) : 0ull;
+}
 
 __global__ void __launch_bounds__(256) k_skm_forward(RecForward f)
 {
-    // Neighbouring warps write to DIFFERENT owners, starting behind this GPU in rank order: at any moment a GPU's stores are
-    // spread over all its peers, and every GPU receives from all the others at once at 1 / (W - 1) of their rate.  (Sweeping
-    // the owners one after the other in the same order on every GPU made all of them write into the same GPU at the same
-    // time: 108 GB/s per GPU on eight B200 instead of the link rate.)
+    // The owner's slab has one REGION per source GPU (region s = slab + s * nb_own * rcap).  The source packs the records of
+    // the owner's buckets into its region one bucket after the other (off = exclusive scan of the counts above): what crosses
+    // NVLink towards one owner is ONE contiguous stream, written by neighbouring warps at neighbouring addresses.  Neighbouring
+    // groups of warps serve different owners, starting behind this GPU in rank order, so that every GPU receives from all
+    // the others at once.  (Measured on the way, profiles/r2_v8_*, r2_v17_*: 32-byte stores straight from the scatter:
+    // 3.8 GB/s; strided 1.3 KB runs per bucket: 73 GB/s per GPU on eight B200.)
     const u32 lane = threadIdx.x & 31;
     const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
     const u32 peers = f.nsrc - 1;
-    const u64 total = (u64)f.nb_own * peers;
+    constexpr u32 RUN = 64;                                       // consecutive buckets of one owner a group of warps takes
+    const u64 nrun = ((u64)f.nb_own + RUN - 1) / RUN;
+    const u64 total = nrun * RUN * peers;                         // (run, owner step, bucket in run)
     for (u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total; g += nwarps)
     {
-        const u32 bl = (u32)(g / peers), step = (u32)(g - (u64)bl * peers);
+        const u64 run = g / ((u64)RUN * peers); const u32 rem = (u32)(g - run * RUN * peers);
+        const u32 step = rem / RUN; const u64 bl = run * RUN + (rem - step * RUN);
+        if (bl >= f.nb_own) continue;
         u32 own = f.me + 1 + step; if (own >= f.nsrc) own -= f.nsrc;
-        const u64 gb = (u64)own * f.nb_own + bl;                       // global bucket
+        const u64 gb = (u64)own * f.nb_own + bl;                  // global bucket
         const u32 n = min((u32)__ldg(f.fill + gb), f.rcap);
         const uint4 *__restrict__ src = reinterpret_cast<const uint4*>(f.stage + gb * f.rcap);
-        uint4 *__restrict__ dst = reinterpret_cast<uint4*>(f.slab[own] + ((u64)bl * f.nsrc + f.me) * f.rcap);
+        const u64 o = __ldg(f.off + gb) - __ldg(f.off + (u64)own * f.nb_own);       // records before this bucket in the region
+        uint4 *__restrict__ dst = reinterpret_cast<uint4*>(f.slab[own] + ((u64)f.me * f.nb_own * f.rcap + o));
         for (u32 i = lane; i < 2 * n; i += 32) dst[i] = __ldcs(src + i);
     }
     __threadfence_system();           // the records are in the owners' memory before this kernel counts as done

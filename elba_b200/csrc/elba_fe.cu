@@ -11,6 +11,8 @@
 #include "skm_count.cuh"
 #include "xdrop.cuh"
 #include "digest.cuh"
+#include "fasta_ingest.cuh"
+#include "dcsc.cuh"
 #include "comm.cuh"
 #include <cub/cub.cuh>
 #include <string>
@@ -102,6 +104,8 @@ struct elba_fe_ctx
     DevBuf t_col, t_num, t_seeds, row_off, row_nnz, bins, small_rows, mid_rows, big_rows, ovf_rows, gscratch, b_rowptr, b_col, b_num, b_seeds;
     u64 b_cap_hint = 0;
     DevBuf cubtmp, hll_regs, bloom;
+    DevBuf fa_raw, fa_rec, fa_items;                       // elba_fe_ingest_fasta: the raw FASTA chunk, its .fai records, first work item of every read
+    DevBuf dc_key, dc_key2, dc_val, dc_val2, dc_head, dc_jc, dc_cp, dc_ir, dc_num, dc_seeds; u64 dc_nzc = 0; bool dc_built = false;      // B by column (DCSC)
     // multi-GPU
     Comm comm;
     u64 N_total = 0;
@@ -319,6 +323,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
         &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->at_ptr32, &ctx->at_ent, &ctx->lp_ptr, &ctx->lp_ent, &ctx->sp_col, &ctx->sp_col2, &ctx->sp_val, &ctx->sp_val2, &ctx->tup_cnt, &ctx->tup_cur, &ctx->tuples, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->agpad, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->skm_foff, &ctx->skm_inoff, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
+        &ctx->fa_raw, &ctx->fa_rec, &ctx->fa_items, &ctx->dc_key, &ctx->dc_key2, &ctx->dc_val, &ctx->dc_val2, &ctx->dc_head, &ctx->dc_jc, &ctx->dc_cp, &ctx->dc_ir, &ctx->dc_num, &ctx->dc_seeds,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf, &ctx->seeds, &ctx->perm, &ctx->rel_idx, &ctx->rel_idx_s,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
         &ctx->r_key, &ctx->r_key2, &ctx->r_pos, &ctx->r_colptr, &ctx->r_row, &ctx->r_ptr };
@@ -436,6 +441,118 @@ int elba_fe_set_reads_device(elba_fe_ctx *ctx, const uint8_t *d_packed, uint64_t
 {
     // device-to-device into the context's padded, aligned arena (the parse kernels read whole 32-bit words past a read's last byte)
     return stage_reads(ctx, d_packed, packed_bytes, d_byte_off, d_len, nreads, read_id_offset, cudaMemcpyDeviceToDevice);
+}
+
+// ---- the step before the path: FASTA ingest (fasta_ingest.cuh) ---------------------------------------------------
+// FastaIndex::getmydna (src/FastaIndex.cpp:191-290): the rank's chunk of the file + the .fai records of its reads -> DnaBuffer.
+// The raw chunk crosses PCIe in slices on the second stream; the pack kernel of a slice starts when the slice is there.
+int elba_fe_ingest_fasta(elba_fe_ctx *ctx, const char *chunk, uint64_t chunk_bytes, uint64_t chunk_pos, const uint64_t *records,
+                         uint64_t nreads, int64_t read_id_offset)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (nreads >= 0xFFFFFFF0ull) return fail(ctx, ELBA_FE_ERR_INVALID, "too many reads for one context (local read ids are 32-bit)");
+    if (nreads && !records) return fail(ctx, ELBA_FE_ERR_INVALID, "null FASTA index records");
+    if (chunk_bytes && !chunk) return fail(ctx, ELBA_FE_ERR_INVALID, "null FASTA chunk");
+    CK(cudaSetDevice(ctx->cfg.device));
+    // layout of the arena (DnaBuffer::computebufsize, src/DnaBuffer.cpp:16-20) and of the work items; every record must lie in the chunk
+    std::vector<u64> off(nreads + 1), items(nreads + 1), len(nreads ? nreads : 1);
+    u64 head = 0, nitems = 0; bool ordered = true; u64 prev_end = chunk_pos;
+    for (u64 r = 0; r < nreads; ++r)
+    {
+        const u64 l = records[3 * r], pos = records[3 * r + 1], bases = records[3 * r + 2];
+        off[r] = head; items[r] = nitems; len[r] = l;
+        if (pos < prev_end || pos - chunk_pos > chunk_bytes) ordered = false;      // (an empty read's position is never dereferenced)
+        if (l)
+        {
+            if (bases == 0) return fail(ctx, ELBA_FE_ERR_INVALID, "FASTA index record with zero bases per line");
+            if (pos < chunk_pos) return fail(ctx, ELBA_FE_ERR_INVALID, "FASTA index record starts before the chunk");
+            const u64 last = pos + (l - 1) + (l - 1) / bases;          // file offset of the read's last base
+            if (last < pos || last - chunk_pos >= chunk_bytes) return fail(ctx, ELBA_FE_ERR_INVALID, "FASTA index record ends behind the chunk");
+            prev_end = last + 1;
+        }
+        const u64 nb = (l + 3) / 4;
+        head += nb; nitems += (nb + FI_ITEM_BYTES - 1) / FI_ITEM_BYTES;
+    }
+    off[nreads] = head; items[nreads] = nitems;
+    ctx->phase = 0;
+    ctx->n = (u32)nreads; ctx->packed_bytes = head; ctx->read_id_offset = read_id_offset; ctx->up_n = 0;
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(ctx->packed.ensure(head + 64));
+    CK(ctx->off.ensure(sizeof(u64) * (size_t)(nreads + 1)));
+    CK(ctx->len64.ensure(sizeof(u64) * (size_t)(nreads + 1)));
+    CK(ctx->fa_raw.ensure(chunk_bytes + 64));
+    CK(ctx->fa_rec.ensure(24 * (size_t)std::max<u64>(nreads, 1)));
+    CK(ctx->fa_items.ensure(sizeof(u64) * (size_t)(nreads + 1)));
+    CK(cudaMemcpyAsync(ctx->off.p, off.data(), sizeof(u64) * (nreads + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->fa_items.p, items.data(), sizeof(u64) * (nreads + 1), cudaMemcpyHostToDevice, st));
+    if (nreads)
+    {
+        CK(cudaMemcpyAsync(ctx->len64.p, len.data(), sizeof(u64) * nreads, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->fa_rec.p, records, 24 * nreads, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemsetAsync(ctx->packed.as<uint8_t>() + head, 0, 64, st));
+    FastaView fv; fv.raw = ctx->fa_raw.as<uint8_t>(); fv.rec = ctx->fa_rec.as<u64>(); fv.off = ctx->off.as<u64>(); fv.item_start = ctx->fa_items.as<u64>();
+    fv.chunk_pos = chunk_pos; fv.n = (u32)nreads;
+    // slices end where a read begins (records in file order, the .fai's own order; otherwise one slice)
+    const int S = (ordered && chunk_bytes >= (64ull << 20) && nreads >= 4096) ? elba_fe_ctx::UP_SLICES : 1;
+    std::vector<u64> slice_read(S + 1, nreads);
+    slice_read[0] = 0;
+    for (int i = 1; i < S; ++i)
+    {
+        const u64 want = chunk_pos + chunk_bytes / S * (u64)i;          // the first read that starts at or behind this file offset
+        u64 lo = slice_read[i - 1], hi = nreads;
+        while (lo < hi) { const u64 mid = (lo + hi) / 2; if (records[3 * mid + 1] < want) lo = mid + 1; else hi = mid; }
+        slice_read[i] = lo;
+    }
+    CK(cudaEventRecord(ctx->ev_fork, st));                   // the previous pass has finished with the old chunk before it is overwritten
+    CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+    for (int i = 0; i < S; ++i)
+    {
+        const u64 r0 = slice_read[i], r1 = slice_read[i + 1];
+        const u64 p0 = (i == 0 || r0 >= nreads) ? (i == 0 ? 0 : chunk_bytes) : records[3 * r0 + 1] - chunk_pos;
+        const u64 p1 = (i == S - 1 || r1 >= nreads) ? chunk_bytes : records[3 * r1 + 1] - chunk_pos;
+        if (p1 > p0) CK(cudaMemcpyAsync(ctx->fa_raw.as<uint8_t>() + p0, chunk + p0, p1 - p0, cudaMemcpyHostToDevice, ctx->aux));
+        CK(cudaEventRecord(ctx->up_ev[i], ctx->aux));
+        CK(cudaStreamWaitEvent(st, ctx->up_ev[i], 0));
+        const u64 i0 = items[r0], i1 = items[r1];
+        if (i1 > i0)
+        {
+            const u32 g = (u32)std::min<u64>((i1 - i0 + 7) / 8, (u64)grid_for(ctx, 8));
+            k_fasta_pack<<<g, 256, 0, st>>>(fv, i0, i1, ctx->packed.as<uint8_t>()); CKL(); LAUNCHED(ctx);
+        }
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+    int rc = prepare_reads(ctx);                              // synchronises: the caller's chunk and records are free again
+    if (rc) return rc;
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->tm.upload_ms = ms;
+    return 0;
+}
+
+int elba_fe_reads_size(elba_fe_ctx *ctx, uint64_t *nreads, uint64_t *packed_bytes)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 1) return fail(ctx, ELBA_FE_ERR_STATE, "no reads resident");
+    if (nreads) *nreads = ctx->n; if (packed_bytes) *packed_bytes = ctx->packed_bytes;
+    return 0;
+}
+
+// the resident DnaBuffer back to the host (the stages behind the path still read it there: src/main.cpp:150,289)
+int elba_fe_get_reads(elba_fe_ctx *ctx, uint8_t *packed, uint64_t *byte_off, uint64_t *len)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 1) return fail(ctx, ELBA_FE_ERR_STATE, "no reads resident");
+    CK(cudaSetDevice(ctx->cfg.device));
+    { int rcw = wait_reads(ctx); if (rcw) return rcw; }
+    cudaEvent_t a = ctx->ev[0], b = ctx->ev[1];
+    CK(cudaEventRecord(a, ctx->stream));
+    if (packed && ctx->packed_bytes) CK(cudaMemcpyAsync(packed, ctx->packed.p, ctx->packed_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (byte_off && ctx->n) CK(cudaMemcpyAsync(byte_off, ctx->off.p, 8 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (len && ctx->n) CK(cudaMemcpyAsync(len, ctx->len64.p, 8 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, a, b); ctx->tm.download_ms = ms;
+    return 0;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1616,7 +1733,7 @@ int elba_fe_spgemm(elba_fe_ctx *ctx)
     }
     CK(cudaEventRecord(ctx->ev[7], st));
     mark(ctx, "spgemm"); trace_flush(ctx, "spgemm");
-    ctx->phase = 4;
+    ctx->phase = 4; ctx->dc_built = false;
     return 0;
 }
 
@@ -1871,6 +1988,69 @@ int elba_fe_device_A(elba_fe_ctx *ctx, const int64_t **rowptr, const uint32_t **
     if (!ctx) return ELBA_FE_ERR_INVALID;
     if (ctx->phase < 3) return fail(ctx, ELBA_FE_ERR_STATE, "A not built");
     if (rowptr) *rowptr = ctx->a_rowptr.as<int64_t>(); if (col) *col = ctx->a_col.as<u32>(); if (pos) *pos = ctx->a_pos.as<u32>();
+    return 0;
+}
+
+// ---- B by column, doubly compressed (dcsc.cuh): the layout the reference's consumer walks (src/PairwiseAlignment.cpp:16-56) ----
+int elba_fe_B_dcsc(elba_fe_ctx *ctx, uint64_t *nzc)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (ctx->phase < 4) return fail(ctx, ELBA_FE_ERR_STATE, "B not built");
+    CK(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->stream;
+    const u64 nnz = ctx->sz.nnzB; const u32 N = ctx->b_rows;
+    if (nnz >= 0xFFFFFFF0ull) return fail(ctx, ELBA_FE_ERR_INVALID, "B block with more than 2^32 nonzeros");
+    if (!ctx->dc_built)
+    {
+        int rc;
+        CK(ctx->dc_key.ensure(4 * (nnz + 1))); CK(ctx->dc_key2.ensure(4 * (nnz + 1))); CK(ctx->dc_val.ensure(8 * (nnz + 1))); CK(ctx->dc_val2.ensure(8 * (nnz + 1)));
+        CK(ctx->dc_head.ensure(8 * (nnz + 1)));
+        CK(ctx->dc_ir.ensure(8 * (nnz + 1))); CK(ctx->dc_num.ensure(4 * (nnz + 1))); CK(ctx->dc_seeds.ensure(16 * (nnz + 1)));
+        CK(ctx->dc_jc.ensure(8 * (nnz + 1))); CK(ctx->dc_cp.ensure(8 * (nnz + 2)));
+        u64 h_nzc = 0;
+        if (nnz)
+        {
+            // the widest column id of the block decides the sorted bits
+            int64_t ncols = (int64_t)N;
+            if (ctx->comm.nranks > 1) { int64_t o, l; elba_fe_block_extent((int64_t)ctx->N_total, ctx->comm.grid_cols, ctx->comm.rank % ctx->comm.grid_cols, &o, &l); ncols = l; }
+            k_dcsc_keys<<<nblk(nnz, 256), 256, 0, st>>>(ctx->b_rowptr.as<int64_t>(), ctx->b_col.as<u32>(), N, nnz, ctx->dc_key.as<u32>(), ctx->dc_val.as<u64>()); CKL(); LAUNCHED(ctx);
+            if ((rc = sort_pairs_u32_u64(ctx, ctx->dc_key.as<u32>(), ctx->dc_key2.as<u32>(), ctx->dc_val.as<u64>(), ctx->dc_val2.as<u64>(), nnz, 0, bits_for((u64)std::max<int64_t>(ncols, 2))))) return rc;
+            k_dcsc_heads<<<nblk(nnz + 1, 256), 256, 0, st>>>(ctx->dc_key2.as<u32>(), nnz, ctx->dc_head.as<u64>()); CKL(); LAUNCHED(ctx);
+            if ((rc = exclusive_scan_inplace(ctx, ctx->dc_head.as<u64>(), nnz + 1))) return rc;
+            k_dcsc_write<<<nblk(nnz + 1, 256), 256, 0, st>>>(ctx->dc_key2.as<u32>(), ctx->dc_val2.as<u64>(), ctx->dc_head.as<u64>(), nnz, ctx->b_num.as<int32_t>(),
+                ctx->b_seeds.as<uint4>(), ctx->dc_jc.as<int64_t>(), ctx->dc_cp.as<int64_t>(), ctx->dc_ir.as<int64_t>(), ctx->dc_num.as<int32_t>(), ctx->dc_seeds.as<uint4>()); CKL(); LAUNCHED(ctx);
+            CK(cudaMemcpyAsync(&h_nzc, ctx->dc_head.as<u64>() + nnz, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        else CK(cudaMemsetAsync(ctx->dc_cp.p, 0, 8, st));
+        ctx->dc_nzc = h_nzc; ctx->dc_built = true;
+    }
+    if (nzc) *nzc = ctx->dc_nzc;
+    return 0;
+}
+
+int elba_fe_get_B_dcsc(elba_fe_ctx *ctx, int64_t *jc, int64_t *cp, int64_t *ir, int32_t *numshared, uint32_t *seeds)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    int rc = elba_fe_B_dcsc(ctx, nullptr);
+    if (rc) return rc;
+    cudaEvent_t a = ctx->ev[0], b = ctx->ev[1];
+    CK(cudaEventRecord(a, ctx->stream));
+    D2H(jc, ctx->dc_jc.p, 8 * ctx->dc_nzc); D2H(cp, ctx->dc_cp.p, 8 * (ctx->dc_nzc + 1)); D2H(ir, ctx->dc_ir.p, 8 * ctx->sz.nnzB);
+    D2H(numshared, ctx->dc_num.p, 4 * ctx->sz.nnzB); D2H(seeds, ctx->dc_seeds.p, 16 * ctx->sz.nnzB);
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, a, b); ctx->tm.download_ms = ms;
+    return 0;
+}
+
+int elba_fe_device_B_dcsc(elba_fe_ctx *ctx, const int64_t **jc, const int64_t **cp, const int64_t **ir, const int32_t **numshared, const uint32_t **seeds)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    int rc = elba_fe_B_dcsc(ctx, nullptr);
+    if (rc) return rc;
+    if (jc) *jc = ctx->dc_jc.as<int64_t>(); if (cp) *cp = ctx->dc_cp.as<int64_t>(); if (ir) *ir = ctx->dc_ir.as<int64_t>();
+    if (numshared) *numshared = ctx->dc_num.as<int32_t>(); if (seeds) *seeds = ctx->dc_seeds.as<u32>();
     return 0;
 }
 

@@ -64,6 +64,7 @@ ABI_SYMBOLS = (
     "elba_fe_timings", "elba_fe_reset_timings", "elba_fe_align", "elba_fe_get_alignments",
     "elba_fe_comm_get_id", "elba_fe_comm_init", "elba_fe_comm_set_grid", "elba_fe_comm_info", "elba_fe_block_extent", "elba_fe_sizes_global",
     "elba_fe_digests", "elba_fe_device_count",
+    "elba_fe_ingest_fasta", "elba_fe_reads_size", "elba_fe_get_reads", "elba_fe_B_dcsc", "elba_fe_get_B_dcsc", "elba_fe_device_B_dcsc",
 )
 
 _lib = None
@@ -148,6 +149,23 @@ class Context:
         self.nreads = nreads
         self._ck(self.L.elba_fe_set_reads_device(self.h, C.c_void_p(buf_ptr), C.c_uint64(nbytes), C.c_void_p(off_ptr), C.c_void_p(len_ptr),
                                                  C.c_uint64(nreads), C.c_int64(read_id_offset)))
+
+    def ingest_fasta(self, chunk, chunk_pos: int, records: np.ndarray, read_id_offset: int = 0):
+        """FastaIndex::getmydna on the device (src/FastaIndex.cpp:191-290): `chunk` = the bytes [chunk_pos, chunk_pos + len(chunk))
+        of the FASTA file (bytes / uint8 array), `records` = (nreads, 3) uint64 .fai records (len, pos, bases)."""
+        rec = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, 3)
+        raw = np.frombuffer(chunk, dtype=np.uint8) if isinstance(chunk, (bytes, bytearray, memoryview)) else np.ascontiguousarray(chunk, dtype=np.uint8)
+        self.nreads = len(rec)
+        self._ck(self.L.elba_fe_ingest_fasta(self.h, _p(raw) if raw.size else None, C.c_uint64(raw.size), C.c_uint64(chunk_pos),
+                                             _p(rec) if len(rec) else None, C.c_uint64(len(rec)), C.c_int64(read_id_offset)))
+
+    def reads(self) -> DnaBuffer:
+        """The resident DnaBuffer back on the host (arena, offsets, lengths)."""
+        n, nb = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.elba_fe_reads_size(self.h, C.byref(n), C.byref(nb)))
+        buf, off, lens = np.zeros(nb.value, np.uint8), np.zeros(n.value, np.uint64), np.zeros(n.value, np.uint64)
+        self._ck(self.L.elba_fe_get_reads(self.h, _p(buf), _p(off), _p(lens)))
+        return DnaBuffer(buf, off.astype(np.uint64), lens.astype(np.uint64))
 
     def set_stream(self, cuda_stream: int):
         self._ck(self.L.elba_fe_set_stream(self.h, C.c_void_p(cuda_stream)))
@@ -240,6 +258,17 @@ class Context:
         num, seeds = np.zeros(s["nnzB"], np.int32), np.zeros((s["nnzB"], 4), np.uint32)
         self._ck(self.L.elba_fe_get_B(self.h, _p(rp), _p(col), _p(num), _p(seeds)))
         return rp, col, num, seeds
+
+    def B_dcsc(self):
+        """B column-major and doubly compressed, CombBLAS' Dcsc arrays (src/PairwiseAlignment.cpp:16-56): (jc, cp, ir, numshared, seeds),
+        local indices of this rank's block, rows ascending within a column."""
+        nzc = C.c_uint64()
+        self._ck(self.L.elba_fe_B_dcsc(self.h, C.byref(nzc)))
+        nnz = self.sizes()["nnzB"]
+        jc, cp, ir = np.zeros(nzc.value, np.int64), np.zeros(nzc.value + 1, np.int64), np.zeros(nnz, np.int64)
+        num, seeds = np.zeros(nnz, np.int32), np.zeros((nnz, 4), np.uint32)
+        self._ck(self.L.elba_fe_get_B_dcsc(self.h, _p(jc), _p(cp), _p(ir), _p(num), _p(seeds)))
+        return jc, cp, ir, num, seeds
 
     def B_triples(self):
         s = self.sizes()

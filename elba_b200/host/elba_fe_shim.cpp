@@ -13,6 +13,10 @@
  *   GetKmerOwner                include/KmerOps.hpp:31        src/KmerOps.cpp:352-359
  *   create_seed_matrix          include/SharedSeeds.hpp:98-99 src/SharedSeeds.cpp:4-10
  *
+ * and, for the step before the path, FastaIndex::getmydna (include/FastaIndex.hpp:31,
+ * src/FastaIndex.cpp:191-290) as elba_fe_getmydna(index); with -DELBA_FE_SHIM_WRAP_GETMYDNA and the linker option
+ * -Wl,--wrap=_ZNK10FastaIndex8getmydnaEv the reference's own call site (src/main.cpp:139) reaches it unchanged.
+ *
  * State between the calls lives in one elba_fe_ctx per rank, found through the address of the object the driver
  * passes back in (the KmerCountMap, then A).  The driver's `kmermap.reset()` (main.cpp:266) and `A.reset()` (:284)
  * therefore need no change; the context is destroyed after create_seed_matrix.
@@ -24,6 +28,7 @@
  */
 #include "KmerOps.hpp"
 #include "SharedSeeds.hpp"
+#include "FastaIndex.hpp"
 #ifdef ELBA_FE_SHIM_ALIGN
 #include "PairwiseAlignment.hpp"      /* also replaces src/PairwiseAlignment.cpp (first version, one rank) */
 #endif
@@ -92,13 +97,14 @@ int GetKmerOwner(const TKmer& kmer, int nprocs)
     return static_cast<int>(owner);
 }
 
-std::unique_ptr<KmerCountMap>
-get_kmer_count_map_keys(const DnaBuffer& myreads, std::shared_ptr<CommGrid> commgrid)
+namespace
 {
-    static_assert(KMER_SIZE <= ELBA_FE_MAX_KMER_SIZE, "libelba_fe counts k-mers of one 64-bit word (TKmer = Kmer<1>)");
+
+/* one context per rank: parameters from the compile-time macros, the rank's GPU, the NCCL communicator over the grid */
+FeState make_state(std::shared_ptr<CommGrid> commgrid)
+{
     MPI_Comm comm = commgrid->GetWorld();
     int myrank = commgrid->GetRank(), nprocs = commgrid->GetSize();
-
     elba_fe_config cfg;
     elba_fe_default_config(&cfg);
     cfg.k = KMER_SIZE; cfg.lower = LOWER_KMER_FREQ; cfg.upper = UPPER_KMER_FREQ; cfg.stride = 1; cfg.seed_count = 2;
@@ -113,28 +119,8 @@ get_kmer_count_map_keys(const DnaBuffer& myreads, std::shared_ptr<CommGrid> comm
         int ndev = elba_fe_device_count();
         cfg.device = ndev > 0 ? local % ndev : 0;
     }
-
     FeState st; st.grid = commgrid;
     fe_check(elba_fe_create(&cfg, &st.ctx), nullptr, "elba_fe_create", comm);
-
-    /* global read ids: the MPI_Exscan of src/KmerOps.cpp:215-216 */
-    size_t numreads = myreads.size();
-    int64_t mine = (int64_t)numreads, before = 0, total = mine;
-    MPI_Exscan(&mine, &before, 1, MPI_INT64_T, MPI_SUM, comm);
-    if (myrank == 0) before = 0;
-    MPI_Allreduce(MPI_IN_PLACE, &total, 1, MPI_INT64_T, MPI_SUM, comm);
-    st.readoffset = before; st.totreads = total;
-
-    /* the arena through DnaBuffer's public accessors only (include/DnaBuffer.hpp:18-23) */
-    std::vector<uint64_t> off(numreads), len(numreads);
-    const uint8_t *base = numreads ? myreads.getbufoffset(0) : nullptr;
-    for (size_t i = 0; i < numreads; ++i)
-    {
-        off[i] = (uint64_t)(myreads.getbufoffset(i) - base);
-        len[i] = (uint64_t)myreads[i].size();
-    }
-    uint64_t nbytes = numreads ? off[numreads - 1] + (uint64_t)myreads[numreads - 1].numbytes() : 0;
-
     if (nprocs > 1)
     {
         /* one NCCL communicator over the grid's ranks; the id travels over MPI */
@@ -143,7 +129,103 @@ get_kmer_count_map_keys(const DnaBuffer& myreads, std::shared_ptr<CommGrid> comm
         MPI_Bcast(&id, (int)sizeof id, MPI_BYTE, 0, comm);
         fe_check(elba_fe_comm_init(st.ctx, &id, myrank, nprocs), st.ctx, "elba_fe_comm_init", comm);
     }
-    fe_check(elba_fe_upload_reads(st.ctx, base, nbytes, off.data(), len.data(), numreads, before), st.ctx, "elba_fe_upload_reads", comm);
+    return st;
+}
+
+/* reads that elba_fe_getmydna left resident on the GPU, keyed by the arena of the DnaBuffer it returned */
+std::map<const void*, FeState> g_ingested;
+
+}
+
+/*
+ * FastaIndex::getmydna (src/FastaIndex.cpp:191-290) with the parse on the device: the rank reads its chunk of the file with
+ * the same collective MPI-IO call and hands it, with its .fai records, to elba_fe_ingest_fasta; the packed arena comes back
+ * into a DnaBuffer for the stages that read it on the host (src/main.cpp:150,289) and STAYS resident for the counting that
+ * follows (get_kmer_count_map_keys below finds it by the arena's address: no second upload).
+ * Binding: `DnaBuffer mydna = elba_fe_getmydna(index);` at src/main.cpp:139, or link with
+ * -Wl,--wrap=_ZNK10FastaIndex8getmydnaEv.
+ */
+DnaBuffer elba_fe_getmydna(const FastaIndex& index)
+{
+    auto commgrid = index.getcommgrid();
+    MPI_Comm comm = commgrid->GetWorld();
+    FeState st = make_state(commgrid);
+    const auto& myrecords = index.getmyrecords();
+    static_assert(sizeof(FastaIndex::Record) == 3 * sizeof(uint64_t), "FastaIndex::Record is {size_t len, pos, bases}");
+
+    MPI_Offset startpos = 0, endpos = 0, filesize = 0;
+    MPI_File fh;
+    MPI_File_open(comm, index.get_fasta_fname().c_str(), MPI_MODE_RDONLY, MPI_INFO_NULL, &fh);
+    MPI_File_get_size(fh, &filesize);
+    if (!myrecords.empty())
+    {
+        startpos = myrecords.front().pos;
+        endpos = myrecords.back().pos + myrecords.back().len + (myrecords.back().len / myrecords.back().bases);
+        if (endpos > filesize) endpos = filesize;
+    }
+    MPI_Offset readbufsize = endpos - startpos;
+    std::unique_ptr<char[]> readbuf(new char[readbufsize > 0 ? readbufsize : 1]);
+    MPI_FILE_READ_AT_ALL(fh, startpos, &readbuf[0], readbufsize, MPI_CHAR, MPI_STATUS_IGNORE);
+    MPI_File_close(&fh);
+
+    st.readoffset = (int64_t)index.getmyreaddispl(); st.totreads = (int64_t)index.gettotrecords();
+    fe_check(elba_fe_ingest_fasta(st.ctx, &readbuf[0], (uint64_t)readbufsize, (uint64_t)startpos,
+                                  reinterpret_cast<const uint64_t*>(myrecords.data()), myrecords.size(), st.readoffset),
+             st.ctx, "elba_fe_ingest_fasta", comm);
+    uint64_t numreads = 0, bufsize = 0;
+    fe_check(elba_fe_reads_size(st.ctx, &numreads, &bufsize), st.ctx, "elba_fe_reads_size", comm);
+    uint8_t *buf = new uint8_t[bufsize ? bufsize : 1];           /* owned by the DnaBuffer (delete[] in its destructor) */
+    fe_check(elba_fe_get_reads(st.ctx, buf, nullptr, nullptr), st.ctx, "elba_fe_get_reads", comm);
+    auto readlens = index.getmyreadlens();
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_ingested[buf] = st;
+    }
+    return DnaBuffer(bufsize, numreads, buf, readlens.data());
+}
+
+#ifdef ELBA_FE_SHIM_WRAP_GETMYDNA
+/* ld --wrap: every reference to FastaIndex::getmydna() const in the other objects resolves here (same calling convention:
+ * hidden result pointer, then `this`) */
+extern "C" DnaBuffer __wrap__ZNK10FastaIndex8getmydnaEv(const FastaIndex *self) { return elba_fe_getmydna(*self); }
+#endif
+
+std::unique_ptr<KmerCountMap>
+get_kmer_count_map_keys(const DnaBuffer& myreads, std::shared_ptr<CommGrid> commgrid)
+{
+    static_assert(KMER_SIZE <= ELBA_FE_MAX_KMER_SIZE, "libelba_fe counts k-mers of one 64-bit word (TKmer = Kmer<1>)");
+    MPI_Comm comm = commgrid->GetWorld();
+    int myrank = commgrid->GetRank();
+    size_t numreads = myreads.size();
+    const uint8_t *base = numreads ? myreads.getbufoffset(0) : nullptr;
+
+    FeState st; bool resident = false;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_ingested.find(base);
+        if (base && it != g_ingested.end()) { st = it->second; g_ingested.erase(it); resident = true; }
+    }
+    if (!resident) st = make_state(commgrid);
+
+    /* global read ids: the MPI_Exscan of src/KmerOps.cpp:215-216 */
+    int64_t mine = (int64_t)numreads, before = 0, total = mine;
+    MPI_Exscan(&mine, &before, 1, MPI_INT64_T, MPI_SUM, comm);
+    if (myrank == 0) before = 0;
+    MPI_Allreduce(MPI_IN_PLACE, &total, 1, MPI_INT64_T, MPI_SUM, comm);
+    st.readoffset = before; st.totreads = total;
+
+    if (!resident)
+    {
+        /* the arena through DnaBuffer's public accessors only (include/DnaBuffer.hpp:18-23) */
+        std::vector<uint64_t> off(numreads), len(numreads);
+        for (size_t i = 0; i < numreads; ++i)
+        {
+            off[i] = (uint64_t)(myreads.getbufoffset(i) - base);
+            len[i] = (uint64_t)myreads[i].size();
+        }
+        uint64_t nbytes = numreads ? off[numreads - 1] + (uint64_t)myreads[numreads - 1].numbytes() : 0;
+        fe_check(elba_fe_upload_reads(st.ctx, base, nbytes, off.data(), len.data(), numreads, before), st.ctx, "elba_fe_upload_reads", comm);
+    }
 
     auto kmermap = std::make_unique<KmerCountMap>();
     {

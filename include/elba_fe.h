@@ -94,6 +94,21 @@ int elba_fe_upload_reads(elba_fe_ctx *ctx, const uint8_t *packed, uint64_t packe
 int elba_fe_set_reads_device(elba_fe_ctx *ctx, const uint8_t *d_packed, uint64_t packed_bytes,
                              const uint64_t *d_byte_off, const uint64_t *d_len, uint64_t nreads, int64_t read_id_offset);
 
+/* ---- the step before the path: FASTA ingest on the device ------------------------------------
+ * Replaces FastaIndex::getmydna (src/FastaIndex.cpp:191-290: one core per rank copies every record line by line and
+ * packs it with DnaSeq::compress, src/DnaSeq.cpp:7-29).  chunk = the bytes [chunk_pos, chunk_pos + chunk_bytes) of the
+ * FASTA file in host memory (what MPI_File_read_at_all delivers, :236); records = the rank's .fai records exactly as
+ * FastaIndex::getmyrecords() holds them (include/FastaIndex.hpp:10: nreads x {size_t len, pos, bases}; base i of a read
+ * is the byte at pos + i + i / bases).  The arena it leaves resident is byte-for-byte the reference's DnaBuffer
+ * (code table include/DnaSeq.hpp:136-154; N/n -> A; lower case accepted); afterwards the context is in the same state
+ * as after elba_fe_upload_reads.  A record that leaves the chunk is ELBA_FE_ERR_INVALID (the reference reads past it). */
+int elba_fe_ingest_fasta(elba_fe_ctx *ctx, const char *chunk, uint64_t chunk_bytes, uint64_t chunk_pos,
+                         const uint64_t *records /* nreads x 3 */, uint64_t nreads, int64_t read_id_offset);
+/* the resident DnaBuffer: its sizes, then arena + tables to the host for the stages that still read it there
+ * (DnaBuffer(bufsize, numreads, buf, readlens), src/DnaBuffer.cpp:5-14); any pointer may be NULL */
+int elba_fe_reads_size(elba_fe_ctx *ctx, uint64_t *nreads, uint64_t *packed_bytes);
+int elba_fe_get_reads(elba_fe_ctx *ctx, uint8_t *packed, uint64_t *byte_off /*nreads*/, uint64_t *len /*nreads*/);
+
 /* ---- the path ------------------------------------------------------------------------------- */
 /* get_kmer_count_map_keys + get_kmer_count_map_values (src/KmerOps.cpp:18-350):
  * reliable k-mers {x : lower <= count(x) <= upper}, exact instance counts, column id = rank of x. */
@@ -172,6 +187,15 @@ int elba_fe_get_B_triples(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t 
 /* device pointers of the same arrays (zero-copy hand-off to a device consumer); any may be NULL */
 int elba_fe_device_B(elba_fe_ctx *ctx, const int64_t **rowptr, const uint32_t **col, const int32_t **numshared, const uint32_t **seeds);
 int elba_fe_device_A(elba_fe_ctx *ctx, const int64_t **rowptr, const uint32_t **col, const uint32_t **pos);
+
+/* B column-major and doubly compressed: the arrays of CombBLAS' Dcsc<int64_t, SharedSeeds> exactly as the
+ * consumer walks them (src/PairwiseAlignment.cpp:16-56: nzc, cp[nzc+1], jc[nzc], ir[nnz], numx[nnz]; row ids ascending
+ * within a column; LOCAL row / column indices of this rank's block), made on the device: a host that builds
+ * SpDCCols(nrow, ncol, Dcsc*) copies them in as they are, no tuple sort.  elba_fe_B_dcsc builds (once per B) and
+ * returns the number of nonempty columns; get_ copies to caller-allocated arrays, device_ hands out the pointers. */
+int elba_fe_B_dcsc(elba_fe_ctx *ctx, uint64_t *nzc);
+int elba_fe_get_B_dcsc(elba_fe_ctx *ctx, int64_t *jc, int64_t *cp, int64_t *ir, int32_t *numshared, uint32_t *seeds);
+int elba_fe_device_B_dcsc(elba_fe_ctx *ctx, const int64_t **jc, const int64_t **cp, const int64_t **ir, const int32_t **numshared, const uint32_t **seeds);
 
 /* ---- the consumer of B (next row of the hot path; first version, one GPU) ------------------------------------------ */
 /* X-drop seed-and-extend of B's nonzeros: PairwiseAlignment (src/PairwiseAlignment.cpp:5-106) keeps the strict upper

@@ -358,6 +358,41 @@ int eo_pack(const char *s, uint64_t len, uint8_t *mem)
     return 0;
 }
 
+/* FASTA ingest: FastaIndex::getmydna, src/FastaIndex.cpp:254-278, + DnaSeq::compress, src/DnaSeq.cpp:7-29.
+ * chunk = the bytes [chunk_pos, chunk_pos + chunk_bytes) of the FASTA file; rec = the .fai records of the reads, 3 words
+ * each: len, pos (file offset of the first base), bases (bases per line; every line is followed by ONE separator byte,
+ * :265-266).  Base i of a read sits at pos + i + i / bases.  A character outside ACGTN/acgtn carries code 4
+ * (include/DnaSeq.hpp:136-154) and `uint8_t shift = code << (6 - 2 * i)` (src/DnaSeq.cpp:20-22) then spills into the
+ * previous base of the byte: reproduced bit for bit.  Returns the arena size, or -1 if a record leaves the chunk. */
+int64_t eo_fasta_pack(const char *chunk, uint64_t chunk_bytes, uint64_t chunk_pos, const uint64_t *rec, uint64_t nreads, uint8_t *packed)
+{
+    uint64_t head = 0;
+    for (uint64_t r = 0; r < nreads; ++r)
+    {
+        const uint64_t len = rec[3 * r], pos = rec[3 * r + 1], bases = rec[3 * r + 2];
+        const uint64_t nbytes = (len + 3) / 4;
+        if (len)
+        {
+            if (bases == 0 || pos < chunk_pos) return -1;
+            const uint64_t last = pos + (len - 1) + (len - 1) / bases;
+            if (last - chunk_pos >= chunk_bytes) return -1;
+        }
+        for (uint64_t b = 0; b < nbytes; ++b)
+        {
+            uint8_t byte = 0;
+            for (int i = 0; i < 4 && 4 * b + i < len; ++i)
+            {
+                const uint64_t j = 4 * b + i;
+                const int c = char_code(chunk[pos - chunk_pos + j + j / bases]);
+                byte |= (uint8_t)(c << (6 - 2 * i));
+            }
+            packed[head + b] = byte;
+        }
+        head += nbytes;
+    }
+    return (int64_t)head;
+}
+
 /* ASCII k-mer -> forward value, twin, canonical, hash (Kmer ctor :86-107, GetTwin, GetRep, GetHash) */
 void eo_kmer_info(const char *s, int k, uint64_t *fwd, uint64_t *twin, uint64_t *rep, uint64_t *hash)
 {

@@ -241,10 +241,16 @@ class RefResult:
     secs: dict = field(default_factory=dict)
 
 
-def ref_run(dna, k: int, lower: int, upper: int, nranks: int = 1, fetch: bool = True) -> RefResult:
-    """Run the reference's own KmerOps/SharedSeeds code on `nranks` thread-ranks."""
+def ref_run(dna, k: int, lower: int, upper: int, nranks: int = 1, fetch: bool = True, fasta: str = None) -> RefResult:
+    """Run the reference's own KmerOps/SharedSeeds code on `nranks` thread-ranks; with `fasta` the reads come from the
+    reference's own FastaIndex + getmydna on that file (src/main.cpp:130-139) instead of `dna`."""
     L = ref_lib(k, lower, upper)
-    h = _vp(L.ref_run(_p(dna.buf), _p(dna.lengths), _u64(dna.size()), nranks))
+    if fasta is not None:
+        L.ref_run_fasta.restype = _vp
+        L.ref_run_fasta.argtypes = [_c.c_char_p, _c.c_int]
+        h = _vp(L.ref_run_fasta(fasta.encode(), nranks))
+    else:
+        h = _vp(L.ref_run(_p(dna.buf), _p(dna.lengths), _u64(dna.size()), nranks))
     try:
         sz = np.zeros(8, np.int64)
         L.ref_sizes(h, _p(sz))
@@ -277,10 +283,12 @@ def shim_path(k: int, lower: int, upper: int) -> str:
     return os.path.join(HERE, "_ref", f"libelba_shim_k{k}_l{lower}_u{upper}.so")
 
 
-def shim_run(dna, k: int, lower: int, upper: int) -> RefResult:
+def shim_run(dna, k: int, lower: int, upper: int, fasta: str = None) -> RefResult:
     """The reference's driver sequence (src/main.cpp:191-282, restated in ref_wrap.cpp::ref_run) over the PRODUCT's drop-in
     shim (elba_b200/host/elba_fe_shim.cpp) and libelba_fe.so, with the reference's own headers: executes the boundary.
-    Needs a B200; the library is built where /root/reference exists (oracle/Makefile target `shim`) and travels prebuilt."""
+    Needs a B200; the library is built where /root/reference exists (oracle/Makefile target `shim`) and travels prebuilt.
+    With `fasta` the sequence starts at FastaIndex(fasta).getmydna(), which the shim library's link (--wrap) sends to
+    elba_fe_getmydna: the parse runs on the device and the reads stay resident for the counting."""
     key = ("shim", k, lower, upper)
     if key not in _ref_libs:
         L = _c.CDLL(shim_path(k, lower, upper))
@@ -289,7 +297,7 @@ def shim_run(dna, k: int, lower: int, upper: int) -> RefResult:
     saved = _ref_libs.get((k, lower, upper))
     _ref_libs[(k, lower, upper)] = _ref_libs[key]
     try:
-        return ref_run(dna, k, lower, upper, nranks=1)
+        return ref_run(dna, k, lower, upper, nranks=1, fasta=fasta)
     finally:
         if saved is None:
             del _ref_libs[(k, lower, upper)]
@@ -374,3 +382,43 @@ def ref_xdrop(dna, k: int, lower: int, upper: int, rows, cols, seedq, seedt, mat
                       _p(np.ascontiguousarray(seedq, np.uint32)), _p(np.ascontiguousarray(seedt, np.uint32)), _u64(n),
                       _i32(mat), _i32(mis), _i32(gap), _i32(dropoff), _p(out))
     return out
+
+
+# ---- FASTA ingest (src/FastaIndex.cpp:98-176,191-290, src/DnaSeq.cpp:7-29) -------------------------------
+def fasta_pack(chunk: bytes, chunk_pos: int, rec: np.ndarray) -> np.ndarray:
+    """The restatement: rec = (nreads, 3) uint64 .fai records (len, pos, bases) -> the packed arena of those reads."""
+    rec = np.ascontiguousarray(rec, dtype=np.uint64).reshape(-1, 3)
+    out = np.zeros(int(((rec[:, 0] + np.uint64(3)) // np.uint64(4)).sum()) if len(rec) else 0, np.uint8)
+    L = lib()
+    L.eo_fasta_pack.restype = _i64
+    L.eo_fasta_pack.argtypes = [_c.c_char_p, _u64, _u64, _vp, _u64, _vp]
+    n = L.eo_fasta_pack(chunk, len(chunk), chunk_pos, _p(rec), len(rec), _p(out))
+    if n < 0:
+        raise ValueError("a record leaves the chunk")
+    assert n == out.size
+    return out
+
+
+def ref_fasta(path: str, nranks: int = 1, klu=(17, 2, 8)):
+    """The reference's own FastaIndex ctor + getmydna on `nranks` thread-ranks.  Returns (displ [nranks + 1],
+    [(records (n, 3) uint64, packed arena uint8)] per rank)."""
+    L = ref_lib(*klu)
+    L.ref_fasta_run.restype = _vp
+    L.ref_fasta_run.argtypes = [_c.c_char_p, _c.c_int]
+    L.ref_fasta_sizes.argtypes = [_vp, _vp, _vp]
+    L.ref_fasta_get.argtypes = [_vp, _c.c_int, _vp, _vp]
+    L.ref_fasta_free.argtypes = [_vp]
+    h = L.ref_fasta_run(path.encode(), nranks)
+    try:
+        displ = np.zeros(nranks + 1, np.int64)
+        nbytes = np.zeros(nranks, np.int64)
+        L.ref_fasta_sizes(h, _p(displ), _p(nbytes))
+        out = []
+        for r in range(nranks):
+            rec = np.zeros((int(displ[r + 1] - displ[r]) if r + 1 < nranks else int(displ[nranks] - displ[r]), 3), np.uint64)
+            buf = np.zeros(int(nbytes[r]), np.uint8)
+            L.ref_fasta_get(h, r, _p(rec), _p(buf))
+            out.append((rec, buf))
+        return displ, out
+    finally:
+        L.ref_fasta_free(h)

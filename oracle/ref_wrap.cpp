@@ -41,6 +41,7 @@
 #include "DnaBuffer.hpp"
 #include "Overlap.hpp"
 #include "XDropAligner.hpp"
+#include "FastaIndex.hpp"
 #include <cstring>
 #include <numeric>
 #include <algorithm>
@@ -167,12 +168,15 @@ void ref_bloom_copy(void *b, uint8_t *out) { std::memcpy(out, ((Bloom*)b)->bf, (
  * thread-ranks: get_kmer_count_map_keys -> get_kmer_count_map_values ->
  * create_kmer_matrix -> copy + Transpose -> create_seed_matrix.
  */
-void *ref_run(const uint8_t *packed, const uint64_t *lens, uint64_t nreads, int nranks)
+static void *run_impl(const uint8_t *packed, const uint64_t *lens, uint64_t nreads, int nranks, const char *fasta)
 {
     RefResult *res = new RefResult; res->nranks = nranks;
-    std::vector<uint64_t> start = partition_reads(lens, nreads, nranks);
-    std::vector<uint64_t> byteoff(nreads + 1, 0);
-    for (uint64_t i = 0; i < nreads; ++i) byteoff[i+1] = byteoff[i] + DnaSeq::bytesneeded(lens[i]);
+    std::vector<uint64_t> start, byteoff(nreads + 1, 0);
+    if (!fasta)
+    {
+        start = partition_reads(lens, nreads, nranks);
+        for (uint64_t i = 0; i < nreads; ++i) byteoff[i+1] = byteoff[i] + DnaSeq::bytesneeded(lens[i]);
+    }
 
     fake_mpi::World world(nranks);
     fake_mpi::g_world = &world;
@@ -186,11 +190,18 @@ void *ref_run(const uint8_t *packed, const uint64_t *lens, uint64_t nreads, int 
     {
         fake_mpi::t_rank = rank;
         auto commgrid = std::make_shared<CommGrid>(MPI_COMM_WORLD, 0, 0);
-        uint64_t r0 = start[rank], r1 = start[rank+1];
-        size_t bufsize = byteoff[r1] - byteoff[r0];
-        uint8_t *buf = new uint8_t[bufsize ? bufsize : 1]; std::memcpy(buf, packed + byteoff[r0], bufsize);
-        std::vector<size_t> l(lens + r0, lens + r1);
-        DnaBuffer mydna(bufsize, r1 - r0, buf, l.data());
+        /* the reads: a block of the caller's arena, or (src/main.cpp:130-139) FastaIndex index(fasta, commgrid); index.getmydna() */
+        std::unique_ptr<FastaIndex> index;
+        if (fasta) index = std::make_unique<FastaIndex>(fasta, commgrid);
+        auto from_arena = [&]()
+        {
+            uint64_t r0 = start[rank], r1 = start[rank+1];
+            size_t bufsize = byteoff[r1] - byteoff[r0];
+            uint8_t *buf = new uint8_t[bufsize ? bufsize : 1]; std::memcpy(buf, packed + byteoff[r0], bufsize);
+            std::vector<size_t> l(lens + r0, lens + r1);
+            return DnaBuffer(bufsize, r1 - r0, buf, l.data());
+        };
+        DnaBuffer mydna = fasta ? index->getmydna() : from_arena();
         double *tt = &t[rank * 6];
 
         MPI_Barrier(MPI_COMM_WORLD); double t0 = now(), ta = t0;
@@ -262,6 +273,10 @@ void *ref_run(const uint8_t *packed, const uint64_t *lens, uint64_t nreads, int 
     return res;
 }
 
+void *ref_run(const uint8_t *packed, const uint64_t *lens, uint64_t nreads, int nranks) { return run_impl(packed, lens, nreads, nranks, nullptr); }
+/* the same from a FASTA file + its .fai: FastaIndex -> getmydna -> the five functions (src/main.cpp:130-139,191-282) */
+void *ref_run_fasta(const char *fasta, int nranks) { return run_impl(nullptr, nullptr, 0, nranks, fasta); }
+
 void ref_free(void *h) { delete (RefResult*)h; }
 void ref_sizes(void *h, int64_t *out /*[8]*/)
 {
@@ -308,6 +323,56 @@ void ref_xdrop_batch(const uint8_t *packed, const uint64_t *off, const uint64_t 
         r[4] = o.score; r[5] = o.rc; r[6] = o.passed; r[7] = o.containedQ; r[8] = o.containedT;
         r[9] = o.direction; r[10] = o.directionT; r[11] = o.suffix; r[12] = o.suffixT;
     }
+}
+
+/*
+ * The step before the hot path: FastaIndex(fasta, commgrid) + FastaIndex::getmydna()
+ * (src/FastaIndex.cpp:98-176,191-290, compiled unmodified) on `nranks` thread-ranks.  Per rank: the .fai records it was
+ * handed (len, pos, bases), and the DnaBuffer arena it parsed.
+ */
+struct RefFasta { std::vector<std::vector<uint64_t>> rec; std::vector<std::vector<uint8_t>> buf; std::vector<int64_t> displ; };
+
+void *ref_fasta_run(const char *path, int nranks)
+{
+    RefFasta *res = new RefFasta; res->rec.resize(nranks); res->buf.resize(nranks); res->displ.assign(nranks + 1, 0);
+    fake_mpi::World world(nranks);
+    fake_mpi::g_world = &world;
+    auto body = [&](int rank)
+    {
+        fake_mpi::t_rank = rank;
+        auto commgrid = std::make_shared<CommGrid>(MPI_COMM_WORLD, 0, 0);
+        FastaIndex index(path, commgrid);
+        DnaBuffer mydna = index.getmydna();
+        for (const auto &r : index.getmyrecords()) { res->rec[rank].push_back(r.len); res->rec[rank].push_back(r.pos); res->rec[rank].push_back(r.bases); }
+        const size_t nb = mydna.getrangebufsize(0, mydna.size());
+        res->buf[rank].assign(mydna.getbufoffset(0), mydna.getbufoffset(0) + nb);
+        res->displ[rank] = (int64_t)index.getmyreaddispl();
+        if (rank == 0) res->displ[nranks] = (int64_t)index.gettotrecords();
+        MPI_Barrier(MPI_COMM_WORLD);
+    };
+    if (nranks == 1) body(0);
+    else
+    {
+        std::vector<std::thread> th;
+        for (int r = 0; r < nranks; ++r) th.emplace_back(body, r);
+        for (auto& x : th) x.join();
+    }
+    fake_mpi::g_world = nullptr; fake_mpi::t_rank = 0;
+    return res;
+}
+void ref_fasta_free(void *h) { delete (RefFasta*)h; }
+/* displ[nranks + 1] = first global read id of every rank, then the total; bytes[nranks] = arena bytes of every rank */
+void ref_fasta_sizes(void *h, int64_t *displ, int64_t *bytes)
+{
+    RefFasta *r = (RefFasta*)h;
+    for (size_t i = 0; i < r->displ.size(); ++i) displ[i] = r->displ[i];
+    for (size_t i = 0; i < r->buf.size(); ++i) bytes[i] = (int64_t)r->buf[i].size();
+}
+void ref_fasta_get(void *h, int rank, uint64_t *rec /* 3 per read */, uint8_t *packed)
+{
+    RefFasta *r = (RefFasta*)h;
+    std::memcpy(rec, r->rec[rank].data(), r->rec[rank].size() * 8);
+    std::memcpy(packed, r->buf[rank].data(), r->buf[rank].size());
 }
 
 } // extern "C"

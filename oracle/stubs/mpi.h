@@ -11,12 +11,17 @@
  *
  * Only the MPI-3 subset those files name is provided (SURVEY.md §2.2 lists
  * the call sites): Comm_rank/size, Barrier, Allreduce, Reduce, Exscan,
- * Alltoall, Alltoallv, Gather, Gatherv.
+ * Alltoall, Alltoallv, Gather, Gatherv; and for src/FastaIndex.cpp (the step
+ * before the hot path): Bcast, Scatterv, contiguous derived
+ * datatypes, MPI_File_open / get_size / read_at_all / close over pread(2).
  */
 #ifndef ELBA_ORACLE_FAKE_MPI_H
 #define ELBA_ORACLE_FAKE_MPI_H
 
 #include <pthread.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
 #include <cstdint>
 #include <cstring>
 #include <cstdio>
@@ -57,8 +62,14 @@ inline thread_local int t_rank = 0;
 inline int nranks() { return g_world ? g_world->size : 1; }
 inline void barrier() { if (g_world && g_world->size > 1) pthread_barrier_wait(&g_world->bar); }
 
+/* derived datatypes (MPI_Type_contiguous): ids from 1000 up, sizes in a small table guarded by the callers' own barriers */
+inline size_t g_derived[64];
+inline int g_nderived = 0;
+inline pthread_mutex_t g_derived_mu = PTHREAD_MUTEX_INITIALIZER;
+
 inline size_t dtsize(MPI_Datatype t)
 {
+    if (t >= 1000) return g_derived[(t - 1000) & 63];
     switch (t)
     {
         case MPI_CHAR: case MPI_BYTE: case MPI_UINT8_T: return 1;
@@ -200,6 +211,48 @@ static inline int MPI_Alltoallv(const void *send, const int *scnt, const int *sd
     barrier();
     return 0;
 }
+
+/* root's blocks send[dis[p] .. dis[p] + cnt[p]) to rank p */
+static inline int MPI_Scatterv(const void *send, const int *cnt, const int *dis, MPI_Datatype st, void *recv, int rcount, MPI_Datatype rt, int root, MPI_Comm)
+{
+    using namespace fake_mpi;
+    size_t sz = dtsize(st); (void)rt;
+    if (nranks() == 1) { std::memcpy(recv, (const uint8_t*)send + (size_t)dis[0] * sz, (size_t)rcount * sz); return 0; }
+    g_world->p0[t_rank] = send; g_world->p1[t_rank] = dis;
+    barrier();
+    std::memcpy(recv, (const uint8_t*)g_world->p0[root] + (size_t)((const int*)g_world->p1[root])[t_rank] * sz, (size_t)rcount * sz);
+    barrier();
+    return 0;
+}
+
+static inline int MPI_Type_contiguous(int n, MPI_Datatype old, MPI_Datatype *out)
+{
+    using namespace fake_mpi;
+    pthread_mutex_lock(&g_derived_mu);
+    const int id = g_nderived++ & 63;
+    g_derived[id] = (size_t)n * dtsize(old);
+    pthread_mutex_unlock(&g_derived_mu);
+    *out = 1000 + id;
+    return 0;
+}
+static inline int MPI_Type_commit(MPI_Datatype *) { return 0; }
+static inline int MPI_Type_free(MPI_Datatype *) { return 0; }
+
+/* MPI-IO, read side only: every rank-thread opens the file itself */
+typedef long long MPI_Offset;
+typedef int MPI_File;
+typedef int MPI_Status;
+#define MPI_MODE_RDONLY 2
+#define MPI_STATUS_IGNORE ((MPI_Status*)nullptr)
+static inline int MPI_File_open(MPI_Comm, const char *name, int, int, MPI_File *fh) { *fh = ::open(name, O_RDONLY); return *fh < 0; }
+static inline int MPI_File_get_size(MPI_File fh, MPI_Offset *size) { struct stat sb; if (fstat(fh, &sb)) return 1; *size = (MPI_Offset)sb.st_size; return 0; }
+static inline int MPI_File_read_at_all(MPI_File fh, MPI_Offset off, void *buf, int n, MPI_Datatype t, MPI_Status *)
+{
+    size_t want = (size_t)n * fake_mpi::dtsize(t), got = 0;
+    while (got < want) { ssize_t r = ::pread(fh, (char*)buf + got, want - got, (off_t)(off + (MPI_Offset)got)); if (r <= 0) break; got += (size_t)r; }
+    return got != want;
+}
+static inline int MPI_File_close(MPI_File *fh) { ::close(*fh); *fh = -1; return 0; }
 
 static inline int MPI_Gather(const void *send, int scount, MPI_Datatype st, void *recv, int rcount, MPI_Datatype rt, int root, MPI_Comm)
 {

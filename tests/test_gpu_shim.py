@@ -52,3 +52,24 @@ def test_driver_sequence_through_the_shim(fixtures, golden, key):
     assert np.array_equal(r.b_rowptr, ref.b_rowptr) and np.array_equal(r.b_col, ref.b_col) and np.array_equal(r.b_num, ref.b_num)
     assert digest(r.b_rowptr.astype(np.int64), r.b_col.astype(np.uint32), r.b_num.astype(np.int32)) == g["digests"]["B"]
     assert np.array_equal(r.b_seeds, ref.b_seeds)
+
+
+def test_driver_sequence_from_the_fasta_file_through_the_shim(fixtures, golden, tmp_path):
+    """src/main.cpp:130-139 + :191-282 unchanged: FastaIndex index(fasta, commgrid); DnaBuffer mydna = index.getmydna(); then
+    the five functions.  In the shim library getmydna is the product's (ld --wrap -> elba_fe_getmydna -> elba_fe_ingest_fasta):
+    the FASTA is parsed on the device, the DnaBuffer the driver holds equals the reference's, and counting finds the reads
+    already resident.  Results == the golden digests of the reference's own run on the same reads."""
+    from elba_b200 import fasta as F
+    from oracle import oracle as O
+    g = golden["configs"]["reads_fa_k17_l2_u8"]
+    if not os.path.exists(O.shim_path(g["k"], g["lower"], g["upper"])):
+        pytest.skip("oracle/_ref/libelba_shim_* not built (needs the reference headers)")
+    dna = fixtures(g["fixture"])
+    path = str(tmp_path / "reads.fa")
+    F.write_fasta(path, [dna.read_ascii(i) for i in range(dna.size())], 80)
+    r = O.shim_run(None, g["k"], g["lower"], g["upper"], fasta=path)
+    kmers, counts, acol, aval = _tier1(r)
+    assert digest(kmers, counts) == g["digests"]["kmers"]
+    assert digest(r.a_rowptr.astype(np.int64), acol, aval) == g["digests"]["A"]
+    assert r.nnzB == g["nnzB"] and r.nnzB_pre == g["nnzB_pre"]
+    assert digest(r.b_rowptr.astype(np.int64), r.b_col.astype(np.uint32), r.b_num.astype(np.int32)) == g["digests"]["B"]

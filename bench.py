@@ -299,10 +299,12 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), {a: b / steps for a, b in acc.items()}
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    # one sampler for the job (rank 0's GPU): eight nvidia-smi loops on one box were seen to stall kernel launches for tens of ms
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     ms_res, tm = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     sizes_local = ctx.sizes()
     sizes = ctx.sizes_global()              # whole-job totals (collective)
     digests = ctx.digests()                 # whole-job result digests of the last timed pass (collective)

@@ -104,6 +104,7 @@ struct elba_fe_ctx
     DevBuf t_col, t_num, t_seeds, row_off, row_nnz, bins, small_rows, mid_rows, big_rows, ovf_rows, gscratch, b_rowptr, b_col, b_num, b_seeds;
     u64 b_cap_hint = 0;
     DevBuf cubtmp, hll_regs, bloom;
+    DevBuf xa_buf, xa_off, xa_len;                          // elba_fe_align on several GPUs: arena and read tables of all ranks
     DevBuf fa_raw, fa_rec, fa_items;                       // elba_fe_ingest_fasta: the raw FASTA chunk, its .fai records, first work item of every read
     DevBuf dc_key, dc_key2, dc_val, dc_val2, dc_head, dc_jc, dc_cp, dc_ir, dc_num, dc_seeds; u64 dc_nzc = 0; bool dc_built = false;      // B by column (DCSC)
     // multi-GPU
@@ -323,7 +324,7 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
         &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->at_ptr32, &ctx->at_ent, &ctx->lp_ptr, &ctx->lp_ent, &ctx->sp_col, &ctx->sp_col2, &ctx->sp_val, &ctx->sp_val2, &ctx->tup_cnt, &ctx->tup_cur, &ctx->tuples, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->agpad, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->skm_foff, &ctx->skm_inoff, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
-        &ctx->fa_raw, &ctx->fa_rec, &ctx->fa_items, &ctx->dc_key, &ctx->dc_key2, &ctx->dc_val, &ctx->dc_val2, &ctx->dc_head, &ctx->dc_jc, &ctx->dc_cp, &ctx->dc_ir, &ctx->dc_num, &ctx->dc_seeds,
+        &ctx->xa_buf, &ctx->xa_off, &ctx->xa_len, &ctx->fa_raw, &ctx->fa_rec, &ctx->fa_items, &ctx->dc_key, &ctx->dc_key2, &ctx->dc_val, &ctx->dc_val2, &ctx->dc_head, &ctx->dc_jc, &ctx->dc_cp, &ctx->dc_ir, &ctx->dc_num, &ctx->dc_seeds,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf, &ctx->seeds, &ctx->perm, &ctx->rel_idx, &ctx->rel_idx_s,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
         &ctx->r_key, &ctx->r_key2, &ctx->r_pos, &ctx->r_colptr, &ctx->r_row, &ctx->r_ptr };
@@ -748,6 +749,12 @@ static int multi_setup(elba_fe_ctx *ctx, bool &ok)
     ctx->p2p = ok;
     ctx->setup_sig[0] = sig[0]; ctx->setup_sig[1] = sig[1]; ctx->setup_sig[2] = sig[2]; ctx->setup_valid = true;
     return 0;
+}
+
+static __global__ void k_add_u64(u64 *__restrict__ v, u64 n, u64 add)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += add;
 }
 
 static __global__ void k_remote_records(const u64 *__restrict__ fill, u64 nbg, u32 nb_own, u32 me, u64 *__restrict__ out)
@@ -2059,7 +2066,6 @@ int elba_fe_align(elba_fe_ctx *ctx, int mat, int mis, int gap, int dropoff, uint
 {
     if (!ctx) return ELBA_FE_ERR_INVALID;
     if (ctx->phase < 4) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_align: call elba_fe_spgemm first");
-    if (ctx->comm.nranks > 1) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_align: one GPU only in this version");
     if (mat <= 0 || mis > 0 || gap >= 0 || dropoff < 0) return fail(ctx, ELBA_FE_ERR_INVALID, "elba_fe_align: need mat > 0, mis <= 0, gap < 0, dropoff >= 0");
     CK(cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = ctx->stream;
@@ -2068,13 +2074,50 @@ int elba_fe_align(elba_fe_ctx *ctx, int mat, int mis, int gap, int dropoff, uint
     { int rcw = wait_reads(ctx); if (rcw) return rcw; }
     CK(cudaEventRecord(ctx->xd_e0, st));
     CK(ctx->xd_flag.ensure(8 * (nnz + 2))); CK(ctx->xd_rowof.ensure(4 * (nnz + 1))); CK(ctx->xd_max.ensure(64));
+    int rc;
+    // the reads the pairs of this block name: one GPU: its own.  Several GPUs: block (i, j) needs the reads of R_i and C_j, which
+    // other ranks hold (the reference exchanges them in DistributedFastaData, src/DistributedFastaData.cpp:98-232): the arenas
+    // and read tables of all ranks are all-gathered over NVLink (0.25 B per base) and indexed by global read id.
+    const int W = ctx->comm.nranks;
+    const uint8_t *x_buf = ctx->packed.as<uint8_t>(); const u64 *x_off = ctx->off.as<u64>(); const u32 *x_len = ctx->len32.as<u32>();
+    u64 x_n = ctx->n; u32 row_base = 0, col_base = 0;
+    if (W > 1)
+    {
+        std::vector<u64> nb, nr, ro;
+        if ((rc = allgather_u64(ctx, ctx->packed_bytes, nb))) return rc;
+        if ((rc = allgather_u64(ctx, (u64)ctx->n, nr))) return rc;
+        if ((rc = allgather_u64(ctx, (u64)ctx->read_id_offset, ro))) return rc;
+        u64 Nt = 0, Bt = 0;
+        for (int r = 0; r < W; ++r)
+        {
+            if (ro[r] != ro[0] + Nt) return fail(ctx, ELBA_FE_ERR_INVALID, "elba_fe_align: the ranks must hold consecutive blocks of reads in rank order");
+            Nt += nr[r]; Bt += nb[r];
+        }
+        if (Nt >= 0xFFFFFFF0ull) return fail(ctx, ELBA_FE_ERR_INVALID, "elba_fe_align: too many reads");
+        CK(ctx->xa_buf.ensure(Bt + 64)); CK(ctx->xa_off.ensure(8 * (Nt + 1))); CK(ctx->xa_len.ensure(4 * (Nt + 1)));
+        if ((rc = allgatherv(ctx, ctx->packed.p, ctx->xa_buf.p, nb, 1))) return rc;
+        if ((rc = allgatherv(ctx, ctx->off.p, ctx->xa_off.p, nr, 8))) return rc;
+        if ((rc = allgatherv(ctx, ctx->len32.p, ctx->xa_len.p, nr, 4))) return rc;
+        CK(cudaMemsetAsync(ctx->xa_buf.as<uint8_t>() + Bt, 0, 64, st));
+        u64 r0 = 0, b0 = 0;
+        for (int r = 0; r < W; ++r)
+        {
+            // rank r's offsets count from its own arena: move them behind the arenas of the ranks before it
+            if (nr[r] && b0) { k_add_u64<<<nblk(nr[r], 256), 256, 0, st>>>(ctx->xa_off.as<u64>() + r0, nr[r], b0); CKL(); LAUNCHED(ctx); }
+            r0 += nr[r]; b0 += nb[r];
+        }
+        x_buf = ctx->xa_buf.as<uint8_t>(); x_off = ctx->xa_off.as<u64>(); x_len = ctx->xa_len.as<u32>(); x_n = Nt;
+        row_base = (u32)((u64)ctx->op.row0 - ro[0]); col_base = (u32)((u64)ctx->op.col0 - ro[0]);
+        ctx->panel_bytes += Bt + 12 * Nt - ctx->packed_bytes - 12 * (u64)ctx->n;
+    }
+    const int global_rule = ctx->comm.grid_rows != ctx->comm.grid_cols;
     k_xdrop_select<<<nblk(nnz + 1, 256), 256, 0, st>>>(ctx->b_rowptr.as<int64_t>(), ctx->b_col.as<u32>(), N, nnz, ctx->op.row0, ctx->op.col0,
-        ctx->xd_flag.as<u64>(), ctx->xd_rowof.as<u32>());
+        global_rule, ctx->xd_flag.as<u64>(), ctx->xd_rowof.as<u32>());
     CKL(); LAUNCHED(ctx);
-    int rc = exclusive_scan_inplace(ctx, ctx->xd_flag.as<u64>(), nnz + 1);
+    rc = exclusive_scan_inplace(ctx, ctx->xd_flag.as<u64>(), nnz + 1);
     if (rc) return rc;
     CK(cudaMemsetAsync(ctx->xd_max.p, 0, 64, st));
-    if (ctx->n) { k_max_u32<<<grid_for(ctx, 2), 256, 0, st>>>(ctx->len32.as<u32>(), ctx->n, ctx->xd_max.as<u32>()); CKL(); LAUNCHED(ctx); }
+    if (x_n) { k_max_u32<<<grid_for(ctx, 2), 256, 0, st>>>(x_len, x_n, ctx->xd_max.as<u32>()); CKL(); LAUNCHED(ctx); }
     u64 np = 0; u32 maxlen = 0;
     CK(cudaMemcpyAsync(&np, ctx->xd_flag.as<u64>() + nnz, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&maxlen, ctx->xd_max.p, 4, cudaMemcpyDeviceToHost, st));
@@ -2089,7 +2132,7 @@ int elba_fe_align(elba_fe_ctx *ctx, int mat, int mis, int gap, int dropoff, uint
         const u32 warps_per_cta = 4;
         const u32 grid = (u32)std::min<u64>((np + warps_per_cta - 1) / warps_per_cta, (u64)grid_for(ctx, 8));
         XdropArgs A;
-        A.buf = ctx->packed.as<uint8_t>(); A.off = ctx->off.as<u64>(); A.len = ctx->len32.as<u32>();
+        A.buf = x_buf; A.off = x_off; A.len = x_len; A.row_base = row_base; A.col_base = col_base;
         A.k = ctx->cfg.k; A.mat = mat; A.mis = mis; A.gap = gap; A.drop = dropoff;
         A.prow = ctx->xd_prow.as<u32>(); A.pcol = ctx->xd_pcol.as<u32>(); A.sq = ctx->xd_sq.as<u32>(); A.st = ctx->xd_st.as<u32>(); A.npairs = np;
         A.stride = (u64)maxlen + 4;

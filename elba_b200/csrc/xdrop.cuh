@@ -30,6 +30,7 @@ struct XdropArgs
     const uint8_t *buf; const u64 *off; const u32 *len;        // the 2-bit arena (src/DnaSeq.cpp:7-29)
     int k, mat, mis, gap, drop;
     const u32 *prow, *pcol, *sq, *st; u64 npairs;              // aligned pairs: row read, column read, seed position in each
+    u32 row_base, col_base;                                    // read index of the block's first row / column read in buf / off / len
     int *scratch; u64 stride;                                  // per warp: 3 * stride ints
     int32_t *out;                                              // [npairs][XD_FIELDS]
 };
@@ -43,7 +44,7 @@ struct XRead
 
 // nonzero e of B belongs to row r: rowptr[r] <= e < rowptr[r + 1]
 __global__ void k_xdrop_select(const int64_t *__restrict__ rowptr, const u32 *__restrict__ col, u32 nrows, u64 nnz, int64_t row0, int64_t col0,
-                               u64 *__restrict__ flag, u32 *__restrict__ rowof)
+                               int global_rule, u64 *__restrict__ flag, u32 *__restrict__ rowof)
 {
     const u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (e > nnz) return;
@@ -52,8 +53,10 @@ __global__ void k_xdrop_select(const int64_t *__restrict__ rowptr, const u32 *__
     while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if ((u64)rowptr[mid] <= e) lo = mid; else hi = mid; }
     rowof[e] = lo;
     const int64_t lr = lo, lc = col[e];
-    // src/PairwiseAlignment.cpp:52: upper triangle of the local block, its diagonal only where it lies above the global one
-    flag[e] = ((lr < lc) || (lr <= lc && lr + row0 < lc + col0)) ? 1 : 0;
+    // src/PairwiseAlignment.cpp:52: upper triangle of the local block, its diagonal only where it lies above the global one.
+    // That rule pairs block (i, j) with block (j, i) and so needs a SQUARE grid (the reference only runs on those); on a
+    // pr != pc grid every unordered pair is taken where it lies in the global upper triangle instead.
+    flag[e] = (global_rule ? (lr + row0 < lc + col0) : ((lr < lc) || (lr <= lc && lr + row0 < lc + col0))) ? 1 : 0;
 }
 
 __global__ void k_xdrop_pairs(const u64 *__restrict__ slot, const u32 *__restrict__ rowof, const u32 *__restrict__ col, const u32 *__restrict__ seeds, u64 nnz,
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(128) k_xdrop(XdropArgs A)
     int *b0 = A.scratch + warp * 3 * A.stride, *b1 = b0 + A.stride, *b2 = b1 + A.stride;
     for (u64 p = warp; p < A.npairs; p += nwarps)
     {
-        const u32 rq = A.prow[p], rt = A.pcol[p];
+        const u32 rq = A.prow[p] + A.row_base, rt = A.pcol[p] + A.col_base;
         XRead Q{A.buf + A.off[rq], (int)A.len[rq]}, T{A.buf + A.off[rt], (int)A.len[rt]};
         const int k = A.k, sq = (int)A.sq[p], st = (int)A.st[p];
         int begQ = 0, endQ = 0, begT = 0, endT = 0, score = -1; bool rc = false;

@@ -21,6 +21,7 @@ def main():
     grid = tuple(int(x) for x in sys.argv[5].split("x")) if len(sys.argv) > 5 and sys.argv[5] != "-" else None
     parts = int(sys.argv[6]) if len(sys.argv) > 6 else 0
     base = int(sys.argv[7]) if len(sys.argv) > 7 else 0      # global id of the first read of rank 0 (the ids need not start at 0)
+    do_align = len(sys.argv) > 8 and sys.argv[8] == "align"  # also run the X-drop alignment of every rank's block of B
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -43,7 +44,12 @@ def main():
     digests = ctx.digests()
     trip = (trip[0] - base, trip[1] - base, trip[2], trip[3])
     info = dict(info, row0=info["row0"] - base, col0=info["col0"] - base)
-    payload = dict(rank=rank, info=info, sizes=sizes, digests=digests, kmers=kmers, counts=counts, A=(arp, acol, apos), first=first, n=mine.size(), B=trip, timings=ctx.timings())
+    aligned = None
+    if do_align:
+        ar, ac, af = ctx.align(1, -1, -1, 15)
+        aligned = (ar - base, ac - base, af)
+    payload = dict(rank=rank, info=info, sizes=sizes, digests=digests, kmers=kmers, counts=counts, A=(arp, acol, apos), first=first, n=mine.size(), B=trip,
+                   aligned=aligned, timings=ctx.timings())
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(payload, gathered, dst=0)
     ok = True
@@ -76,6 +82,24 @@ def main():
             assert np.array_equal(brp, ref.b_rowptr) and np.array_equal(bcol, ref.b_col), "pattern of B"
             assert np.array_equal(bnum, ref.b_num), "numshared"
             assert np.array_equal(bseeds, ref.b_seeds), "seeds"
+            if do_align:
+                # every unordered pair of distinct reads of B's pattern is aligned exactly once over the ranks; the 13 fields of
+                # each aligned (row, column) equal the oracle's for that orientation and the seed B holds at (row, column)
+                rows = np.repeat(np.arange(dna.size()), np.diff(ref.b_rowptr))
+                seed_of = {(int(r), int(c)): (int(s[0]), int(s[1])) for r, c, s in zip(rows, ref.b_col, ref.b_seeds)}
+                ar = np.concatenate([g["aligned"][0] for g in gathered]); ac = np.concatenate([g["aligned"][1] for g in gathered])
+                af = np.concatenate([g["aligned"][2] for g in gathered])
+                pairs = sorted((min(int(r), int(c)), max(int(r), int(c))) for r, c in zip(ar, ac))
+                want_pairs = sorted((int(r), int(c)) for r, c in zip(rows, ref.b_col) if r < c)
+                assert pairs == want_pairs, ("aligned pairs", len(pairs), len(want_pairs))
+                if pr != pc:
+                    assert (ar < ac).all(), "non-square grid: the global upper triangle"
+                sq = np.array([seed_of[(int(r), int(c))][0] for r, c in zip(ar, ac)], dtype=np.uint32)
+                st = np.array([seed_of[(int(r), int(c))][1] for r, c in zip(ar, ac)], dtype=np.uint32)
+                want = O.xdrop(dna, k, ar, ac, sq, st, 1, -1, -1, 15)
+                bad = np.where((af != want).any(axis=1))[0]
+                assert len(bad) == 0, ("alignment fields", len(bad), af[bad[:3]].tolist(), want[bad[:3]].tolist())
+                print(f"MULTI-GPU ALIGNMENT OK pairs={len(pairs)} per rank={[len(g['aligned'][0]) for g in gathered]}", flush=True)
             if base == 0:
                 from common import oracle_result_digests
                 want = oracle_result_digests(ref)

@@ -69,3 +69,14 @@ def test_multi_gpu_without_peer_memory(world):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     _launch(world, ["synth:300000,500,12000,0.01", 31, 2, 4, "-", 16], 29699 + world, env={"ELBA_FE_P2P": "0"})
+
+
+@pytest.mark.parametrize("world,grid", [(2, "-"), (2, "2x1"), (4, "2x2"), (8, "-")])
+def test_multi_gpu_xdrop_alignment(world, grid):
+    """elba_fe_align on several GPUs: every rank aligns the nonzeros of its block of B (reads of the other ranks all-gathered
+    over NVLink); square grids select pairs by the reference's block-local rule (src/PairwiseAlignment.cpp:52), the others by
+    the global upper triangle.  Every pair exactly once, 13 fields bit-exact against the oracle, nonzero first read id."""
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _launch(world, ["synth:120000,260,7000,0.05", 21, 2, 6, grid, 0, 0, "align"], 29711 + world)
+    _launch(world, ["reads_fa", 17, 2, 8, grid, 0, 41, "align"], 29721 + world)

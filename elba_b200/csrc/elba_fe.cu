@@ -13,6 +13,7 @@
 #include "digest.cuh"
 #include "fasta_ingest.cuh"
 #include "dcsc.cuh"
+#include "transitive.cuh"
 #include "comm.cuh"
 #include <cub/cub.cuh>
 #include <string>
@@ -104,6 +105,9 @@ struct elba_fe_ctx
     DevBuf t_col, t_num, t_seeds, row_off, row_nnz, bins, small_rows, mid_rows, big_rows, ovf_rows, gscratch, b_rowptr, b_col, b_num, b_seeds;
     u64 b_cap_hint = 0;
     DevBuf cubtmp, hll_regs, bloom;
+    DevBuf tr_in_row, tr_in_col, tr_in_f, tr_key, tr_key2, tr_val, tr_val2, tr_head, tr_okey, tr_row, tr_col, tr_dir, tr_dirT, tr_suf, tr_sufT, tr_src, tr_tr,
+           tr_rowptr, tr_I, tr_T, tr_keep, tr_orow, tr_ocol, tr_of, tr_osrc, tr_otr;      // elba_fe_transitive_reduction
+    u64 tr_out = 0; bool tr_done = false;
     DevBuf xa_buf, xa_off, xa_len;                          // elba_fe_align on several GPUs: arena and read tables of all ranks
     DevBuf fa_raw, fa_rec, fa_items;                       // elba_fe_ingest_fasta: the raw FASTA chunk, its .fai records, first work item of every read
     DevBuf dc_key, dc_key2, dc_val, dc_val2, dc_head, dc_jc, dc_cp, dc_ir, dc_num, dc_seeds; u64 dc_nzc = 0; bool dc_built = false;      // B by column (DCSC)
@@ -324,6 +328,9 @@ int elba_fe_destroy(elba_fe_ctx *ctx)
         &ctx->at_key, &ctx->at_key2, &ctx->at_pos2, &ctx->at_colptr, &ctx->at_row, &ctx->at_pos, &ctx->prod,
         &ctx->t_col, &ctx->t_num, &ctx->t_seeds, &ctx->row_off, &ctx->row_nnz, &ctx->sp_ptr, &ctx->sp_ent, &ctx->at_ptr32, &ctx->at_ent, &ctx->lp_ptr, &ctx->lp_ent, &ctx->sp_col, &ctx->sp_col2, &ctx->sp_val, &ctx->sp_val2, &ctx->tup_cnt, &ctx->tup_cur, &ctx->tuples, &ctx->xd_flag, &ctx->xd_rowof, &ctx->xd_prow, &ctx->xd_pcol, &ctx->xd_sq, &ctx->xd_st, &ctx->xd_nz, &ctx->xd_out, &ctx->xd_scratch, &ctx->xd_max, &ctx->agpad, &ctx->skm_fillin, &ctx->skm_plan, &ctx->skm_stage, &ctx->skm_foff, &ctx->skm_inoff, &ctx->d_roff, &ctx->route_cur, &ctx->rel_gid, &ctx->glob_key, &ctx->glob_cnt, &ctx->glob_gid, &ctx->glob_cnt_in, &ctx->bins, &ctx->small_rows, &ctx->mid_rows, &ctx->big_rows, &ctx->ovf_rows, &ctx->gscratch,
         &ctx->b_rowptr, &ctx->b_col, &ctx->b_num, &ctx->b_seeds, &ctx->cubtmp, &ctx->hll_regs, &ctx->bloom,
+        &ctx->tr_in_row, &ctx->tr_in_col, &ctx->tr_in_f, &ctx->tr_key, &ctx->tr_key2, &ctx->tr_val, &ctx->tr_val2, &ctx->tr_head, &ctx->tr_okey, &ctx->tr_row, &ctx->tr_col,
+        &ctx->tr_dir, &ctx->tr_dirT, &ctx->tr_suf, &ctx->tr_sufT, &ctx->tr_src, &ctx->tr_tr, &ctx->tr_rowptr, &ctx->tr_I, &ctx->tr_T, &ctx->tr_keep, &ctx->tr_orow, &ctx->tr_ocol,
+        &ctx->tr_of, &ctx->tr_osrc, &ctx->tr_otr,
         &ctx->xa_buf, &ctx->xa_off, &ctx->xa_len, &ctx->fa_raw, &ctx->fa_rec, &ctx->fa_items, &ctx->dc_key, &ctx->dc_key2, &ctx->dc_val, &ctx->dc_val2, &ctx->dc_head, &ctx->dc_jc, &ctx->dc_cp, &ctx->dc_ir, &ctx->dc_num, &ctx->dc_seeds,
         &ctx->plan, &ctx->bfill, &ctx->ovf, &ctx->scratch[0], &ctx->scratch[1], &ctx->skm_slab, &ctx->skm_fill, &ctx->skm_ovf, &ctx->seeds, &ctx->perm, &ctx->rel_idx, &ctx->rel_idx_s,
         &ctx->recvbuf, &ctx->recvcnt, &ctx->tmp64, &ctx->rel_all_key, &ctx->rel_all_cnt, &ctx->g_key, &ctx->g_pos, &ctx->pack_key, &ctx->l_rowptr, &ctx->l_col,
@@ -2167,6 +2174,84 @@ int elba_fe_get_alignments(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t
     D2H(row, tmp.p, 8 * np); D2H(col, tmp.as<int64_t>() + np, 8 * np); D2H(fields, ctx->xd_out.p, 4 * (size_t)XD_FIELDS * np);
     CK(cudaStreamSynchronize(ctx->stream));
     tmp.release();
+    return 0;
+}
+
+// ---- transitive reduction of the overlap graph (transitive.cuh): TransitiveReduction(R), src/TransitiveReduction.cpp:3-92 ----
+int elba_fe_transitive_reduction(elba_fe_ctx *ctx, const int64_t *row, const int64_t *col, const int32_t *fields, uint64_t nnz, int64_t nreads,
+                                 int32_t fuzz, uint64_t *nnz_out)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (nreads < 0 || nreads >= 0xFFFFFFF0ll) return fail(ctx, ELBA_FE_ERR_INVALID, "elba_fe_transitive_reduction: bad number of reads");
+    if (nnz >= (1ull << 31)) return fail(ctx, ELBA_FE_ERR_INVALID, "elba_fe_transitive_reduction: more than 2^31 overlaps");
+    if (nnz && (!row || !col || !fields)) return fail(ctx, ELBA_FE_ERR_INVALID, "elba_fe_transitive_reduction: null triples");
+    for (u64 e = 0; e < nnz; ++e)
+    {
+        if (row[e] < 0 || row[e] >= nreads || col[e] < 0 || col[e] >= nreads) return fail(ctx, ELBA_FE_ERR_INVALID, "elba_fe_transitive_reduction: read id out of range");
+        if (fields[4 * e] < -1 || fields[4 * e] > 3 || fields[4 * e + 1] < -1 || fields[4 * e + 1] > 3)
+            return fail(ctx, ELBA_FE_ERR_INVALID, "elba_fe_transitive_reduction: direction outside -1..3 (include/Overlap.hpp:36-44)");
+    }
+    CK(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->stream;
+    ctx->tr_done = false; ctx->tr_out = 0;
+    const u64 m2 = 2 * nnz; const u32 n = (u32)nreads;
+    int rc;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    u64 M = 0;
+    if (nnz)
+    {
+        CK(ctx->tr_in_row.ensure(8 * nnz)); CK(ctx->tr_in_col.ensure(8 * nnz)); CK(ctx->tr_in_f.ensure(16 * nnz));
+        CK(cudaMemcpyAsync(ctx->tr_in_row.p, row, 8 * nnz, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->tr_in_col.p, col, 8 * nnz, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->tr_in_f.p, fields, 16 * nnz, cudaMemcpyHostToDevice, st));
+        CK(ctx->tr_key.ensure(8 * m2)); CK(ctx->tr_key2.ensure(8 * m2)); CK(ctx->tr_val.ensure(4 * m2)); CK(ctx->tr_val2.ensure(4 * m2)); CK(ctx->tr_head.ensure(8 * (m2 + 1)));
+        k_tr_items<<<nblk(nnz, 256), 256, 0, st>>>(ctx->tr_in_row.as<int64_t>(), ctx->tr_in_col.as<int64_t>(), nnz, ctx->tr_key.as<u64>(), ctx->tr_val.as<u32>()); CKL(); LAUNCHED(ctx);
+        if ((rc = sort_pairs(ctx, ctx->tr_key.as<u64>(), ctx->tr_key2.as<u64>(), ctx->tr_val.as<u32>(), ctx->tr_val2.as<u32>(), m2, 0, 32 + bits_for(std::max<u64>(n, 2))))) return rc;
+        k_tr_heads<<<nblk(m2 + 1, 256), 256, 0, st>>>(ctx->tr_key2.as<u64>(), m2, ctx->tr_head.as<u64>()); CKL(); LAUNCHED(ctx);
+        if ((rc = exclusive_scan_inplace(ctx, ctx->tr_head.as<u64>(), m2 + 1))) return rc;
+        CK(cudaMemcpyAsync(&M, ctx->tr_head.as<u64>() + m2, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (M)
+    {
+        CK(ctx->tr_okey.ensure(8 * M)); CK(ctx->tr_row.ensure(4 * M)); CK(ctx->tr_col.ensure(4 * M)); CK(ctx->tr_dir.ensure(4 * M)); CK(ctx->tr_dirT.ensure(4 * M));
+        CK(ctx->tr_suf.ensure(4 * M)); CK(ctx->tr_sufT.ensure(4 * M)); CK(ctx->tr_src.ensure(4 * M)); CK(ctx->tr_tr.ensure(M)); CK(ctx->tr_rowptr.ensure(8 * ((u64)n + 2)));
+        CK(ctx->tr_I.ensure(M)); CK(ctx->tr_T.ensure(M)); CK(ctx->tr_keep.ensure(8 * (M + 1)));
+        k_tr_entries<<<nblk(m2, 256), 256, 0, st>>>(ctx->tr_key2.as<u64>(), ctx->tr_val2.as<u32>(), ctx->tr_head.as<u64>(), m2, nnz, ctx->tr_in_f.as<int32_t>(),
+            ctx->tr_okey.as<u64>(), ctx->tr_row.as<u32>(), ctx->tr_col.as<u32>(), ctx->tr_dir.as<int32_t>(), ctx->tr_dirT.as<int32_t>(), ctx->tr_suf.as<int32_t>(), ctx->tr_sufT.as<int32_t>(),
+            ctx->tr_src.as<u32>(), ctx->tr_tr.as<uint8_t>()); CKL(); LAUNCHED(ctx);
+        k_segment_ptr<<<nblk((u64)n + 1, 256), 256, 0, st>>>(ctx->tr_okey.as<u64>(), M, n, 32, ctx->tr_rowptr.as<int64_t>()); CKL(); LAUNCHED(ctx);
+        TrGraph g; g.rowptr = ctx->tr_rowptr.as<int64_t>(); g.row = ctx->tr_row.as<u32>(); g.col = ctx->tr_col.as<u32>(); g.dir = ctx->tr_dir.as<int32_t>(); g.dirT = ctx->tr_dirT.as<int32_t>();
+        g.suf = ctx->tr_suf.as<int32_t>(); g.sufT = ctx->tr_sufT.as<int32_t>(); g.m = M; g.n = n;
+        CK(cudaMemsetAsync(ctx->tr_T.p, 0, M, st));
+        k_tr_mark<<<nblk(M, 128), 128, 0, st>>>(g, fuzz, ctx->tr_I.as<uint8_t>()); CKL(); LAUNCHED(ctx);
+        k_tr_symmetric<<<nblk(M, 256), 256, 0, st>>>(g, ctx->tr_I.as<uint8_t>(), ctx->tr_T.as<uint8_t>()); CKL(); LAUNCHED(ctx);
+        k_tr_keep<<<nblk(M + 1, 256), 256, 0, st>>>(g, ctx->tr_T.as<uint8_t>(), ctx->tr_keep.as<u64>()); CKL(); LAUNCHED(ctx);
+        if ((rc = exclusive_scan_inplace(ctx, ctx->tr_keep.as<u64>(), M + 1))) return rc;
+        u64 S = 0;
+        CK(cudaMemcpyAsync(&S, ctx->tr_keep.as<u64>() + M, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const u64 S1 = std::max<u64>(S, 1);
+        CK(ctx->tr_orow.ensure(8 * S1)); CK(ctx->tr_ocol.ensure(8 * S1)); CK(ctx->tr_of.ensure(16 * S1)); CK(ctx->tr_osrc.ensure(8 * S1)); CK(ctx->tr_otr.ensure(S1));
+        k_tr_output<<<nblk(M, 256), 256, 0, st>>>(g, ctx->tr_T.as<uint8_t>(), ctx->tr_keep.as<u64>(), ctx->tr_src.as<u32>(), ctx->tr_tr.as<uint8_t>(),
+            ctx->tr_orow.as<int64_t>(), ctx->tr_ocol.as<int64_t>(), ctx->tr_of.as<int32_t>(), ctx->tr_osrc.as<u64>(), ctx->tr_otr.as<uint8_t>()); CKL(); LAUNCHED(ctx);
+        ctx->tr_out = S;
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->tm.transitive_ms = ms;
+    ctx->tr_done = true;
+    if (nnz_out) *nnz_out = ctx->tr_out;
+    return 0;
+}
+
+int elba_fe_get_string_graph(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t *fields, uint64_t *src, uint8_t *transposed)
+{
+    if (!ctx) return ELBA_FE_ERR_INVALID;
+    if (!ctx->tr_done) return fail(ctx, ELBA_FE_ERR_STATE, "elba_fe_get_string_graph: call elba_fe_transitive_reduction first");
+    const u64 S = ctx->tr_out;
+    D2H(row, ctx->tr_orow.p, 8 * S); D2H(col, ctx->tr_ocol.p, 8 * S); D2H(fields, ctx->tr_of.p, 16 * S); D2H(src, ctx->tr_osrc.p, 8 * S); D2H(transposed, ctx->tr_otr.p, S);
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

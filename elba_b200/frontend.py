@@ -49,7 +49,7 @@ class Timings(C.Structure):
     _fields_ = [("upload_ms", C.c_float), ("count_ms", C.c_float), ("build_ms", C.c_float), ("spgemm_ms", C.c_float),
                 ("download_ms", C.c_float), ("count_kernel_ms", C.c_float), ("spgemm_kernel_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("partition_ms", C.c_float), ("lookup_ms", C.c_float), ("exchange_ms", C.c_float),
-                ("exchange_mbytes", C.c_float), ("panel_mbytes", C.c_float), ("align_ms", C.c_float), ("reserved", C.c_float * 2)]
+                ("exchange_mbytes", C.c_float), ("panel_mbytes", C.c_float), ("align_ms", C.c_float), ("transitive_ms", C.c_float), ("reserved", C.c_float * 1)]
 
     def as_dict(self):
         return {n: (int(getattr(self, n)) if n == "kernel_launches" else float(getattr(self, n))) for n, _ in self._fields_ if n != "reserved"}
@@ -64,6 +64,7 @@ ABI_SYMBOLS = (
     "elba_fe_timings", "elba_fe_reset_timings", "elba_fe_align", "elba_fe_get_alignments",
     "elba_fe_comm_get_id", "elba_fe_comm_init", "elba_fe_comm_set_grid", "elba_fe_comm_info", "elba_fe_block_extent", "elba_fe_sizes_global",
     "elba_fe_digests", "elba_fe_device_count",
+    "elba_fe_transitive_reduction", "elba_fe_get_string_graph",
     "elba_fe_ingest_fasta", "elba_fe_reads_size", "elba_fe_get_reads", "elba_fe_B_dcsc", "elba_fe_get_B_dcsc", "elba_fe_device_B_dcsc",
 )
 
@@ -288,6 +289,22 @@ class Context:
         out = np.zeros((n.value, len(self.ALIGN_FIELDS)), np.int32)
         self._ck(self.L.elba_fe_get_alignments(self.h, _p(rows), _p(cols), _p(out)))
         return rows, cols, out
+
+    TR_FIELDS = ("direction", "directionT", "suffix", "suffixT")
+
+    def transitive_reduction(self, nreads: int, rows, cols, fields, fuzz: int = 1000):
+        """TransitiveReduction(R) (src/TransitiveReduction.cpp:3-92) on the device.  R = triples (row, col, fields[nnz, 4] =
+        direction, directionT, suffix, suffixT).  Returns the string graph S row-major: (rows, cols, fields[nnzS, 4], src, transposed)."""
+        rows, cols = np.ascontiguousarray(rows, np.int64), np.ascontiguousarray(cols, np.int64)
+        fields = np.ascontiguousarray(fields, np.int32).reshape(-1, 4)
+        n = C.c_uint64()
+        self._ck(self.L.elba_fe_transitive_reduction(self.h, _p(rows) if len(rows) else None, _p(cols) if len(rows) else None, _p(fields) if len(rows) else None,
+                                                     C.c_uint64(len(rows)), C.c_int64(nreads), C.c_int32(fuzz), C.byref(n)))
+        m = n.value
+        orow, ocol, of = np.zeros(m, np.int64), np.zeros(m, np.int64), np.zeros((m, 4), np.int32)
+        osrc, otr = np.zeros(m, np.uint64), np.zeros(m, np.uint8)
+        self._ck(self.L.elba_fe_get_string_graph(self.h, _p(orow), _p(ocol), _p(of), _p(osrc), _p(otr)))
+        return orow, ocol, of, osrc, otr
 
     def hll(self):
         regs, est = np.zeros(4096, np.uint8), C.c_double()

@@ -29,6 +29,9 @@
 #include "KmerOps.hpp"
 #include "SharedSeeds.hpp"
 #include "FastaIndex.hpp"
+#ifdef ELBA_FE_SHIM_TR
+#include "TransitiveReduction.hpp"    /* also replaces src/TransitiveReduction.cpp (first version: every rank reduces the whole graph) */
+#endif
 #ifdef ELBA_FE_SHIM_ALIGN
 #include "PairwiseAlignment.hpp"      /* also replaces src/PairwiseAlignment.cpp (first version, one rank) */
 #endif
@@ -101,7 +104,7 @@ namespace
 {
 
 /* one context per rank: parameters from the compile-time macros, the rank's GPU, the NCCL communicator over the grid */
-FeState make_state(std::shared_ptr<CommGrid> commgrid)
+FeState make_state(std::shared_ptr<CommGrid> commgrid, bool with_comm = true)
 {
     MPI_Comm comm = commgrid->GetWorld();
     int myrank = commgrid->GetRank(), nprocs = commgrid->GetSize();
@@ -121,7 +124,7 @@ FeState make_state(std::shared_ptr<CommGrid> commgrid)
     }
     FeState st; st.grid = commgrid;
     fe_check(elba_fe_create(&cfg, &st.ctx), nullptr, "elba_fe_create", comm);
-    if (nprocs > 1)
+    if (nprocs > 1 && with_comm)
     {
         /* one NCCL communicator over the grid's ranks; the id travels over MPI */
         elba_fe_comm_id id;
@@ -380,5 +383,83 @@ PairwiseAlignment(DistributedFastaData& dfd, CT<SharedSeeds>::PSpParMat& Bmat, i
     CT<int64_t>::PDistVec dcols(cols, st.grid);
     CT<Overlap>::PDistVec dvals(overlaps, st.grid);
     return std::make_unique<CT<Overlap>::PSpParMat>(st.totreads, st.totreads, drows, dcols, dvals, false);
+}
+#endif
+
+#ifdef ELBA_FE_SHIM_TR
+/*
+ * TransitiveReduction (include/TransitiveReduction.hpp:17, src/TransitiveReduction.cpp:3-92) on the device
+ * (elba_fe_transitive_reduction).  The overlap matrix is small next to everything before it, so every rank gathers the
+ * triples of all blocks (walked exactly as src/PairwiseAlignment.cpp:16-33 walks B), reduces the whole graph on its GPU
+ * (replicas, no device collective) and hands the constructor the entries of S that stem from ITS OWN triples; the
+ * (rows, cols, vals) constructor redistributes them (src/PairwiseAlignment.cpp:97-103 builds R the same way).  The
+ * Overlap payload of a mirror-image entry is Overlap::Transpose of the source entry (include/Overlap.hpp:46-74).
+ */
+Overlap opmin(const Overlap& e1, const Overlap& e2)       /* src/TransitiveReduction.cpp:94-102: declared in the header, kept for other users */
+{
+    Overlap e = Overlap();
+    for (int i = 0; i < 4; ++i) e.suffix_paths[i] = std::min(e1.suffix_paths[i], e2.suffix_paths[i]);
+    return e;
+}
+
+std::unique_ptr<CT<Overlap>::PSpParMat> TransitiveReduction(CT<Overlap>::PSpParMat R)
+{
+    auto commgrid = R.getcommgrid();
+    MPI_Comm comm = commgrid->GetWorld();
+    int myrank = commgrid->GetRank(), nprocs = commgrid->GetSize();
+    const int64_t nrow = R.getnrow(), ncol = R.getncol();
+
+    int64_t roff = 0, nr = 0, coff = 0, nc = 0;
+    elba_fe_block_extent(nrow, commgrid->GetGridRows(), commgrid->GetRankInProcCol(), &roff, &nr);
+    elba_fe_block_extent(ncol, commgrid->GetGridCols(), commgrid->GetRankInProcRow(), &coff, &nc);
+    std::vector<int64_t> rows, cols; std::vector<int32_t> f; std::vector<const Overlap*> mine;
+    auto dcsc = R.seqptr()->GetDCSC();
+    if (dcsc != nullptr)
+        for (int64_t i = 0; i < dcsc->nzc; ++i)
+            for (int64_t j = dcsc->cp[i]; j < dcsc->cp[i+1]; ++j)
+            {
+                const Overlap& o = dcsc->numx[j];
+                rows.push_back(dcsc->ir[j] + roff); cols.push_back(dcsc->jc[i] + coff);
+                f.push_back(o.direction); f.push_back(o.directionT); f.push_back(o.suffix); f.push_back(o.suffixT);
+                mine.push_back(&o);
+            }
+
+    /* the whole graph on every rank */
+    std::vector<int> cnt(nprocs, 0), dis(nprocs + 1, 0);
+    int mycnt = (int)rows.size();
+    std::vector<int64_t> arows, acols; std::vector<int32_t> af;
+    if (nprocs > 1)
+    {
+        MPI_Allgather(&mycnt, 1, MPI_INT, cnt.data(), 1, MPI_INT, comm);
+        for (int r = 0; r < nprocs; ++r) dis[r + 1] = dis[r] + cnt[r];
+        arows.resize(dis[nprocs]); acols.resize(dis[nprocs]); af.resize(4 * (size_t)dis[nprocs]);
+        std::vector<int> cnt4(nprocs), dis4(nprocs);
+        for (int r = 0; r < nprocs; ++r) { cnt4[r] = 4 * cnt[r]; dis4[r] = 4 * dis[r]; }
+        MPI_Allgatherv(rows.data(), mycnt, MPI_INT64_T, arows.data(), cnt.data(), dis.data(), MPI_INT64_T, comm);
+        MPI_Allgatherv(cols.data(), mycnt, MPI_INT64_T, acols.data(), cnt.data(), dis.data(), MPI_INT64_T, comm);
+        MPI_Allgatherv(f.data(), 4 * mycnt, MPI_INT, af.data(), cnt4.data(), dis4.data(), MPI_INT, comm);
+    }
+    else { cnt[0] = mycnt; dis[1] = mycnt; arows = rows; acols = cols; af = f; }
+
+    FeState st = make_state(commgrid, false);
+    uint64_t ns = 0;
+    fe_check(elba_fe_transitive_reduction(st.ctx, arows.data(), acols.data(), af.data(), arows.size(), nrow, FUZZ, &ns), st.ctx, "elba_fe_transitive_reduction", comm);
+    std::vector<int64_t> srow(ns), scol(ns); std::vector<int32_t> sf(4 * ns); std::vector<uint64_t> ssrc(ns); std::vector<uint8_t> str(ns);
+    fe_check(elba_fe_get_string_graph(st.ctx, srow.data(), scol.data(), sf.data(), ssrc.data(), str.data()), st.ctx, "elba_fe_get_string_graph", comm);
+    elba_fe_destroy(st.ctx);
+
+    std::vector<int64_t> orow, ocol; std::vector<Overlap> oval;
+    const uint64_t lo = (uint64_t)dis[myrank], hi = (uint64_t)dis[myrank + 1];
+    for (uint64_t e = 0; e < ns; ++e)
+    {
+        if (ssrc[e] < lo || ssrc[e] >= hi) continue;          /* another rank holds that entry's payload */
+        const Overlap& o = *mine[ssrc[e] - lo];
+        orow.push_back(srow[e]); ocol.push_back(scol[e]);
+        oval.push_back(str[e] ? Overlap::Transpose()(o) : o);
+    }
+    CT<int64_t>::PDistVec drows(orow, commgrid);
+    CT<int64_t>::PDistVec dcols(ocol, commgrid);
+    CT<Overlap>::PDistVec dvals(oval, commgrid);
+    return std::make_unique<CT<Overlap>::PSpParMat>(nrow, ncol, drows, dcols, dvals, false);
 }
 #endif

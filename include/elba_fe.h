@@ -208,6 +208,20 @@ int elba_fe_align(elba_fe_ctx *ctx, int mat, int mis, int gap, int dropoff, uint
  * the reference's Overlap (include/Overlap.hpp:25-31) that extend_overlap sets */
 int elba_fe_get_alignments(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t *fields);
 
+/* ---- behind the consumer: transitive reduction of the overlap graph (first version, one GPU) ----------
+ * TransitiveReduction(R) (src/TransitiveReduction.cpp:3-92; functors include/TransitiveReduction.hpp:19-110).  R comes as nnz
+ * triples with distinct coordinates (the matrix src/PairwiseAlignment.cpp:97-103 builds, after the prunes of
+ * src/main.cpp:305-311): global read ids in [0, nreads) and four ints per entry = Overlap's direction, directionT, suffix,
+ * suffixT (include/Overlap.hpp:27-29), the only fields the algorithm reads.  fuzz = FUZZ (include/TransitiveReduction.hpp:15:
+ * 1000).  The string graph S (symmetric: every surviving overlap in both orientations) stays on the device;
+ * get_string_graph returns it row-major: coordinates, the four fields as they stand at that coordinate, src = index of the
+ * input triple the entry came from and transposed = 1 where it is that triple's mirror image (the host applies
+ * Overlap::Transpose, include/Overlap.hpp:46-74, to the rest of the payload).  The matrix is small: every rank may run it
+ * on the whole R (replicas only, no collective). */
+int elba_fe_transitive_reduction(elba_fe_ctx *ctx, const int64_t *row, const int64_t *col, const int32_t *fields /* nnz x 4 */, uint64_t nnz,
+                                 int64_t nreads, int32_t fuzz, uint64_t *nnz_out);
+int elba_fe_get_string_graph(elba_fe_ctx *ctx, int64_t *row, int64_t *col, int32_t *fields /* nnz_out x 4 */, uint64_t *src, uint8_t *transposed);
+
 /* ---- the reference's sizing sketches, bit-exact (not needed for the result when lower >= 2) ----------- */
 /* HyperLogLog over the canonical k-mers of the uploaded reads exactly as KmerEstimateHandler drives it
  * (include/KmerOps.hpp:58-69, src/HyperLogLog.cpp:40-76): registers[4096] and estimate(). */
@@ -235,7 +249,8 @@ typedef struct {
     float exchange_mbytes;  /* MB this rank sent in it */
     float panel_mbytes;     /* MB this rank received as routed seed triples and in the all-gather of A's row blocks */
     float align_ms;         /* elba_fe_align: pair selection + the X-drop kernel */
-    float reserved[2];
+    float transitive_ms;    /* elba_fe_transitive_reduction */
+    float reserved[1];
 } elba_fe_timings_t;
 int elba_fe_timings(elba_fe_ctx *ctx, elba_fe_timings_t *out);
 int elba_fe_reset_timings(elba_fe_ctx *ctx);

@@ -33,6 +33,7 @@
 #include <vector>
 #include <algorithm>
 #include <numeric>
+#include <limits>
 #include <unordered_map>
 #include <chrono>
 #include <thread>
@@ -391,6 +392,83 @@ int64_t eo_fasta_pack(const char *chunk, uint64_t chunk_bytes, uint64_t chunk_po
         head += nbytes;
     }
     return (int64_t)head;
+}
+
+/* Transitive reduction of the overlap graph: TransitiveReduction(R), src/TransitiveReduction.cpp:3-92, with the
+ * functors of include/TransitiveReduction.hpp:19-110 and Overlap::Transpose / arrows (include/Overlap.hpp:36-74).
+ * Input: nnz triples (row, col, {direction, directionT, suffix, suffixT}) with distinct coordinates (the matrix
+ * PairwiseAlignment builds, upper triangular in the reference).  What the reference's loop computes:
+ *   R  += transpose(R) with query/target fields swapped (:16-20); an entry both hold keeps R's value (operator+ returns lhs)
+ *   N   = R (x) R under MinPlusSR (:49): N(i,j).suffix_paths[2 t1 + h2] = min over k of R(i,k).suffix + R(k,j).suffix, over the
+ *         k whose arrows chain (t2 != h1; entries with direction -1 have no arrows)
+ *   I   = { (i,j) in R and N : direction != -1 and suffix + FUZZ >= N.suffix_paths[direction] } (:60-62), made symmetric (:70-74)
+ *   T  += I (:76).  T starts as ONE explicit entry at (0,0) (:27-28: nrow copies of the coordinate (0,0)).
+ *   The second round multiplies P = N, whose values are default Overlaps (direction -1: no arrows), so it adds nothing and
+ *   the loop ends (:43-82) - restated as the single squaring it is.
+ *   S   = the entries of R that T does not hold (:86, notB), minus direction -1 (:88).
+ * Output (row-major, columns ascending): row, col, the four fields as they stand at that coordinate, src = index of the input
+ * triple the entry came from, transposed = 1 if it is that triple's mirror image.  Returns the number of entries. */
+uint64_t eo_transitive_reduction(int64_t n, uint64_t nnz, const int64_t *rows, const int64_t *cols, const int32_t *fields, int32_t fuzz,
+                                 int64_t *orow, int64_t *ocol, int32_t *ofields, uint64_t *osrc, uint8_t *otrans)
+{
+    struct E { int64_t r, c; int32_t dir, dirT, suf, sufT; uint64_t src; uint8_t tr; };
+    std::vector<E> e; e.reserve(2 * nnz);
+    for (uint64_t i = 0; i < nnz; ++i)
+    {
+        const int32_t *f = fields + 4 * i;
+        e.push_back({rows[i], cols[i], f[0], f[1], f[2], f[3], i, 0});
+        e.push_back({cols[i], rows[i], f[1], f[0], f[3], f[2], i, 1});       /* Overlap::Transpose */
+    }
+    std::sort(e.begin(), e.end(), [](const E& a, const E& b) { if (a.r != b.r) return a.r < b.r; if (a.c != b.c) return a.c < b.c; return a.tr < b.tr; });
+    std::vector<E> R; R.reserve(e.size());
+    for (size_t i = 0; i < e.size(); ++i) if (i == 0 || e[i].r != e[i-1].r || e[i].c != e[i-1].c) R.push_back(e[i]);       /* R's own entry wins */
+    std::vector<uint64_t> rp((size_t)n + 1, 0);
+    for (const E& x : R) rp[(size_t)x.r + 1]++;
+    for (int64_t i = 0; i < n; ++i) rp[i + 1] += rp[i];
+    auto find = [&](int64_t r, int64_t c) -> int64_t
+    {
+        uint64_t lo = rp[r], hi = rp[r + 1];
+        while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (R[mid].c < c) lo = mid + 1; else hi = mid; }
+        return (lo < rp[r + 1] && R[lo].c == c) ? (int64_t)lo : -1;
+    };
+    const int INF = std::numeric_limits<int>::max();
+    std::vector<uint8_t> I(R.size(), 0);
+    for (int64_t i = 0; i < n; ++i)
+        for (uint64_t p = rp[i]; p < rp[i + 1]; ++p)
+        {
+            const E& x = R[p];
+            if (x.dir == -1) continue;                                        /* GreaterThanSR */
+            int best = INF;                                                   /* N(i, x.c).suffix_paths[x.dir] */
+            for (uint64_t a = rp[i]; a < rp[i + 1]; ++a)
+            {
+                const E& e1 = R[a];
+                if (e1.dir == -1) continue;
+                const int t1 = (e1.dir >> 1) & 1, h1 = e1.dir & 1;
+                const int64_t b = find(e1.c, x.c);
+                if (b < 0) continue;
+                const E& e2 = R[b];
+                if (e2.dir == -1) continue;
+                const int t2 = (e2.dir >> 1) & 1, h2 = e2.dir & 1;
+                if (t2 == h1) continue;
+                if (2 * t1 + h2 != x.dir) continue;
+                best = std::min(best, e1.suf + e2.suf);
+            }
+            if (best != INF && x.suf + fuzz >= best) I[p] = 1;
+        }
+    std::vector<uint8_t> T(I);
+    for (int64_t i = 0; i < n; ++i)
+        for (uint64_t p = rp[i]; p < rp[i + 1]; ++p)
+            if (I[p]) { int64_t q = find(R[p].c, i); if (q >= 0) T[q] = 1; }     /* I += transpose(I); only coordinates R holds matter for :86 */
+    uint64_t out = 0;
+    for (size_t p = 0; p < R.size(); ++p)
+    {
+        const E& x = R[p];
+        if (T[p] || (x.r == 0 && x.c == 0) || x.dir == -1) continue;
+        if (orow) { orow[out] = x.r; ocol[out] = x.c; ofields[4 * out] = x.dir; ofields[4 * out + 1] = x.dirT; ofields[4 * out + 2] = x.suf; ofields[4 * out + 3] = x.sufT;
+                    osrc[out] = x.src; otrans[out] = x.tr; }
+        ++out;
+    }
+    return out;
 }
 
 /* ASCII k-mer -> forward value, twin, canonical, hash (Kmer ctor :86-107, GetTwin, GetRep, GetHash) */

@@ -422,3 +422,51 @@ def ref_fasta(path: str, nranks: int = 1, klu=(17, 2, 8)):
         return displ, out
     finally:
         L.ref_fasta_free(h)
+
+
+# ---- transitive reduction of the overlap graph (src/TransitiveReduction.cpp:3-92) -----------------------
+TR_FIELDS = ("direction", "directionT", "suffix", "suffixT")
+
+
+def transitive_reduction(n: int, rows, cols, fields, fuzz: int = 1000):
+    """The restatement: R as triples (row, col, [direction, directionT, suffix, suffixT]) -> the string graph S as
+    (row, col, fields[nnzS, 4], src, transposed), row-major.  FUZZ = 1000: include/TransitiveReduction.hpp:15."""
+    rows, cols = np.ascontiguousarray(rows, np.int64), np.ascontiguousarray(cols, np.int64)
+    fields = np.ascontiguousarray(fields, np.int32).reshape(-1, 4)
+    L = lib()
+    L.eo_transitive_reduction.restype = _u64
+    L.eo_transitive_reduction.argtypes = [_i64, _u64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]
+    cap = 2 * len(rows)
+    orow, ocol, of = np.zeros(cap, np.int64), np.zeros(cap, np.int64), np.zeros((cap, 4), np.int32)
+    osrc, otr = np.zeros(cap, np.uint64), np.zeros(cap, np.uint8)
+    m = L.eo_transitive_reduction(n, len(rows), _p(rows), _p(cols), _p(fields), fuzz, _p(orow), _p(ocol), _p(of), _p(osrc), _p(otr))
+    return orow[:m], ocol[:m], of[:m], osrc[:m], otr[:m]
+
+
+def ref_transitive_reduction(n: int, rows, cols, fields, klu=(17, 2, 8), shim: bool = False):
+    """The reference's own TransitiveReduction.cpp (oracle/_ref; CombBLAS restated in oracle/stubs): (row, col, fields[nnzS, 4]).
+    shim=True: the same driver code over the PRODUCT's drop-in TransitiveReduction (elba_b200/host/elba_fe_shim.cpp ->
+    elba_fe_transitive_reduction; needs a B200)."""
+    rows, cols = np.ascontiguousarray(rows, np.int64), np.ascontiguousarray(cols, np.int64)
+    fields = np.ascontiguousarray(fields, np.int32).reshape(-1, 4)
+    if shim:
+        key = ("shim",) + tuple(klu)
+        if key not in _ref_libs:
+            _ref_libs[key] = _c.CDLL(shim_path(*klu))
+        L = _ref_libs[key]
+    else:
+        L = ref_lib(*klu)
+    L.ref_transitive_reduction.restype = _vp
+    L.ref_transitive_reduction.argtypes = [_i64, _u64, _vp, _vp, _vp]
+    L.ref_tr_size.restype = _u64
+    L.ref_tr_size.argtypes = [_vp]
+    L.ref_tr_get.argtypes = [_vp, _vp, _vp, _vp]
+    L.ref_tr_free.argtypes = [_vp]
+    h = L.ref_transitive_reduction(n, len(rows), _p(rows), _p(cols), _p(fields))
+    try:
+        m = L.ref_tr_size(h)
+        orow, ocol, of = np.zeros(m, np.int64), np.zeros(m, np.int64), np.zeros((m, 4), np.int32)
+        L.ref_tr_get(h, _p(orow), _p(ocol), _p(of))
+        return orow, ocol, of
+    finally:
+        L.ref_tr_free(h)

@@ -42,6 +42,7 @@
 #include "Overlap.hpp"
 #include "XDropAligner.hpp"
 #include "FastaIndex.hpp"
+#include "TransitiveReduction.hpp"
 #include <cstring>
 #include <numeric>
 #include <algorithm>
@@ -374,5 +375,47 @@ void ref_fasta_get(void *h, int rank, uint64_t *rec /* 3 per read */, uint8_t *p
     std::memcpy(rec, r->rec[rank].data(), r->rec[rank].size() * 8);
     std::memcpy(packed, r->buf[rank].data(), r->buf[rank].size());
 }
+
+/*
+ * Transitive reduction of the overlap graph: TransitiveReduction(R), src/TransitiveReduction.cpp:3-92,
+ * compiled unmodified.  R = nnz triples (row, col, Overlap) of which only direction, directionT, suffix, suffixT matter to the
+ * algorithm (include/TransitiveReduction.hpp:19-110); the string graph S comes back as triples with the same four fields.
+ */
+struct RefTR { std::vector<int64_t> row, col; std::vector<int32_t> f; /* 4 per entry: direction, directionT, suffix, suffixT */ };
+
+void *ref_transitive_reduction(int64_t n, uint64_t nnz, const int64_t *rows, const int64_t *cols, const int32_t *fields /* 4 per entry */)
+{
+    RefTR *res = new RefTR;
+    auto commgrid = std::make_shared<CommGrid>(MPI_COMM_WORLD, 0, 0);
+    std::vector<int64_t> r(rows, rows + nnz), c(cols, cols + nnz);
+    std::vector<Overlap> v; v.reserve(nnz);
+    for (uint64_t e = 0; e < nnz; ++e)
+    {
+        Overlap o;
+        o.direction = (int8_t)fields[4 * e]; o.directionT = (int8_t)fields[4 * e + 1]; o.suffix = fields[4 * e + 2]; o.suffixT = fields[4 * e + 3];
+        o.passed = true;
+        v.push_back(o);
+    }
+    CT<int64_t>::PDistVec drows(r, commgrid), dcols(c, commgrid);
+    CT<Overlap>::PDistVec dvals(v, commgrid);
+    CT<Overlap>::PSpParMat R(n, n, drows, dcols, dvals, false);       /* as src/PairwiseAlignment.cpp:97-103 builds it */
+    auto S = TransitiveReduction(R);
+    const auto &st = *S->st;
+    for (int64_t i = 0; i < st.m; ++i)
+        for (int64_t p = st.rowptr[i]; p < st.rowptr[i + 1]; ++p)
+        {
+            const Overlap &o = st.val[p];
+            res->row.push_back(i); res->col.push_back(st.col[p]);
+            res->f.push_back(o.direction); res->f.push_back(o.directionT); res->f.push_back(o.suffix); res->f.push_back(o.suffixT);
+        }
+    return res;
+}
+uint64_t ref_tr_size(void *h) { return ((RefTR*)h)->row.size(); }
+void ref_tr_get(void *h, int64_t *row, int64_t *col, int32_t *fields)
+{
+    RefTR *r = (RefTR*)h;
+    std::memcpy(row, r->row.data(), 8 * r->row.size()); std::memcpy(col, r->col.data(), 8 * r->col.size()); std::memcpy(fields, r->f.data(), 4 * r->f.size());
+}
+void ref_tr_free(void *h) { delete (RefTR*)h; }
 
 } // extern "C"

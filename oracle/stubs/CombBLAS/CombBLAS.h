@@ -28,6 +28,14 @@
  *        seeds, see DESIGN.md.
  *   Prune(pred)                                src/SharedSeeds.cpp:8
  *
+ * and, for src/TransitiveReduction.cpp, what that file names:
+ *   getcommgrid(), FullyDistVec(grid, n, init), SpParMat(m, n, rows, cols, scalar value, false), Apply(unary op),
+ *   operator+= (union of the patterns; where both hold an entry the values are combined with NT's operator+,
+ *   CombBLAS Dcsc::operator+=), the converting copy SpParMat<NT> -> SpParMat<NNT> (T += I adds a bool matrix to an int
+ *   one), operator==, and EWiseApply<RETT, RETDER>(A, B, op, notB, defaultBVal): with notB == false the result holds
+ *   op(A(i,j), B(i,j)) on the INTERSECTION of the patterns; with notB == true it holds op(A(i,j), defaultBVal) on the
+ *   entries of A that B does NOT hold (CombBLAS ParFriends.h / Friends.h EWiseApply, restated from its documentation).
+ *
  * "Ranks" are the threads of oracle/stubs/mpi.h; a distributed matrix is one
  * shared, immutable global store that every rank's handle points at.
  */
@@ -49,6 +57,10 @@
 #include <cassert>
 #include <cmath>
 
+/* the reference's functors name these unqualified (include/TransitiveReduction.hpp:19-77); CombBLAS' headers make them visible */
+using std::unary_function;
+using std::binary_function;
+
 namespace combblas {
 
 class CommGrid
@@ -58,6 +70,8 @@ public:
     int GetRank() const { return fake_mpi::t_rank; }
     int GetSize() const { return fake_mpi::nranks(); }
     MPI_Comm GetWorld() const { return world; }
+    int GetGridRows() const { return (int)std::lround(std::sqrt((double)GetSize())); }
+    int GetGridCols() const { return (int)std::lround(std::sqrt((double)GetSize())); }
     int GetRankInProcRow() const { int q = (int)std::lround(std::sqrt((double)GetSize())); return GetRank() % q; }
     int GetRankInProcCol() const { int q = (int)std::lround(std::sqrt((double)GetSize())); return GetRank() / q; }
 private:
@@ -72,6 +86,8 @@ class FullyDistVec
 {
 public:
     FullyDistVec(const std::vector<NT>& v, std::shared_ptr<CommGrid> g) : arr(v), grid(g) {}
+    /* a vector of globallen copies of initval, spread over the ranks: here rank 0 holds all of it */
+    FullyDistVec(std::shared_ptr<CommGrid> g, IT globallen, NT initval) : arr(fake_mpi::t_rank == 0 ? (size_t)globallen : 0, initval), grid(g) {}
     std::vector<NT> arr;
     std::shared_ptr<CommGrid> grid;
 };
@@ -134,6 +150,109 @@ public:
     }
 
     SpParMat(const SpParMat& o) : st(o.st) {} /* stores are immutable: sharing == copying */
+    SpParMat& operator=(const SpParMat& o) { st = o.st; return *this; }
+
+    /* every listed (row, col) holds `val` (duplicates collapse) */
+    SpParMat(IT m, IT n, const FullyDistVec<IT,IT>& rows, const FullyDistVec<IT,IT>& cols, const NT& val, bool SumDuplicates)
+        : SpParMat(m, n, rows, cols, FullyDistVec<IT,NT>(std::vector<NT>(rows.arr.size(), val), rows.grid), SumDuplicates) {}
+
+    std::shared_ptr<CommGrid> getcommgrid() const { return std::make_shared<CommGrid>(MPI_COMM_WORLD, 0, 0); }
+
+    /* values replaced by op(value) */
+    template <class Op>
+    void Apply(Op op)
+    {
+        using namespace fake_mpi;
+        std::shared_ptr<store_t> mine;
+        if (nranks() > 1) barrier();
+        if (t_rank == 0)
+        {
+            mine = std::make_shared<store_t>(*st);
+            for (auto& v : mine->val) { NT x = v; v = op(x); }
+        }
+        share(mine);
+    }
+
+    /* union of the patterns; an entry both hold becomes lhs + rhs */
+    SpParMat& operator+=(const SpParMat& rhs)
+    {
+        using namespace fake_mpi;
+        std::shared_ptr<store_t> mine;
+        if (nranks() > 1) barrier();
+        if (t_rank == 0)
+        {
+            const store_t &a = *st, &b = *rhs.st;
+            assert(a.m == b.m && a.n == b.n);
+            mine = std::make_shared<store_t>();
+            mine->m = a.m; mine->n = a.n; mine->rowptr.assign(a.m + 1, 0);
+            for (IT r = 0; r < a.m; ++r)
+            {
+                IT p = a.rowptr[r], pe = a.rowptr[r+1], q = b.rowptr[r], qe = b.rowptr[r+1];
+                while (p < pe || q < qe)
+                {
+                    if (q >= qe || (p < pe && a.col[p] < b.col[q])) { mine->col.push_back(a.col[p]); mine->val.push_back(a.val[p]); ++p; }
+                    else if (p >= pe || b.col[q] < a.col[p]) { mine->col.push_back(b.col[q]); mine->val.push_back(b.val[q]); ++q; }
+                    else { mine->col.push_back(a.col[p]); mine->val.push_back((NT)(a.val[p] + b.val[q])); ++p; ++q; }
+                    mine->rowptr[r+1]++;
+                }
+            }
+            std::partial_sum(mine->rowptr.begin(), mine->rowptr.end(), mine->rowptr.begin());
+        }
+        share(mine);
+        return *this;
+    }
+
+    /* the same pattern with the values converted (CombBLAS: template conversion operator of SpParMat) */
+    template <class NNT, class NDER>
+    operator SpParMat<IT,NNT,NDER>() const
+    {
+        using namespace fake_mpi;
+        typedef Store<IT,NNT> nstore;
+        std::shared_ptr<nstore> mine;
+        if (nranks() > 1) barrier();
+        if (t_rank == 0)
+        {
+            mine = std::make_shared<nstore>();
+            mine->m = st->m; mine->n = st->n; mine->rowptr = st->rowptr; mine->col = st->col;
+            mine->val.reserve(st->val.size());
+            for (const auto& v : st->val) mine->val.push_back(static_cast<NNT>(v));
+        }
+        SpParMat<IT,NNT,NDER> C;
+        C.share(mine);
+        return C;
+    }
+
+    /* the local block, column-major and doubly compressed, as src/PairwiseAlignment.cpp:16-33 walks it.  One rank only: the
+     * "block" is the whole matrix (the stores are global here). */
+    struct Dcsc { IT nzc = 0; std::vector<IT> cp, jc, ir; std::vector<NT> numx; };
+    struct Seq
+    {
+        std::shared_ptr<Dcsc> d;
+        Dcsc *GetDCSC() const { return d && d->nzc ? d.get() : nullptr; }
+        IT getnnz() const { return d ? (IT)d->ir.size() : 0; }
+    };
+    std::shared_ptr<Seq> seqptr() const
+    {
+        assert(fake_mpi::nranks() == 1 && "the stand-in's seqptr() serves one rank");
+        auto s = std::make_shared<Seq>(); s->d = std::make_shared<Dcsc>();
+        std::vector<std::tuple<IT,IT,IT>> t;      /* (col, row, position) */
+        for (IT r = 0; r < st->m; ++r) for (IT p = st->rowptr[r]; p < st->rowptr[r+1]; ++p) t.emplace_back(st->col[p], r, p);
+        std::sort(t.begin(), t.end());
+        s->d->cp.push_back(0);
+        for (size_t i = 0; i < t.size(); ++i)
+        {
+            if (i == 0 || std::get<0>(t[i]) != std::get<0>(t[i-1])) { if (i) s->d->cp.push_back((IT)i); s->d->jc.push_back(std::get<0>(t[i])); }
+            s->d->ir.push_back(std::get<1>(t[i])); s->d->numx.push_back(st->val[std::get<2>(t[i])]);
+        }
+        s->d->nzc = (IT)s->d->jc.size();
+        if (!t.empty()) s->d->cp.push_back((IT)t.size());
+        return s;
+    }
+
+    bool operator==(const SpParMat& rhs) const
+    {
+        return st->m == rhs.st->m && st->n == rhs.st->n && st->rowptr == rhs.st->rowptr && st->col == rhs.st->col && st->val == rhs.st->val;
+    }
 
     IT getnrow() const { return st->m; }
     IT getncol() const { return st->n; }
@@ -243,6 +362,39 @@ SpParMat<IU,NUO,UDERO> Mult_AnXBn_DoubleBuff(SpParMat<IU,NU1,UDERA>& A, SpParMat
         }
     }
     SpParMat<IU,NUO,UDERO> C;
+    C.share(mine);
+    return C;
+}
+
+/* element-wise op over two matrices of the same shape: see the header comment for the two modes */
+template <typename RETT, typename RETDER, typename IU, typename NU1, typename NU2, typename UDERA, typename UDERB, typename BinOp>
+SpParMat<IU,RETT,RETDER> EWiseApply(const SpParMat<IU,NU1,UDERA>& A, const SpParMat<IU,NU2,UDERB>& B, BinOp op, bool notB, const NU2& defaultBVal)
+{
+    using namespace fake_mpi;
+    typedef Store<IU,RETT> ostore;
+    std::shared_ptr<ostore> mine;
+    if (nranks() > 1) barrier();
+    if (t_rank == 0)
+    {
+        const auto &a = *A.st; const auto &b = *B.st;
+        assert(a.m == b.m && a.n == b.n);
+        mine = std::make_shared<ostore>();
+        mine->m = a.m; mine->n = a.n; mine->rowptr.assign(a.m + 1, 0);
+        for (IU r = 0; r < a.m; ++r)
+        {
+            IU q = b.rowptr[r], qe = b.rowptr[r+1];
+            for (IU p = a.rowptr[r]; p < a.rowptr[r+1]; ++p)
+            {
+                while (q < qe && b.col[q] < a.col[p]) ++q;
+                const bool both = q < qe && b.col[q] == a.col[p];
+                NU1 x = a.val[p];
+                if (!notB && both) { NU2 y = b.val[q]; mine->col.push_back(a.col[p]); mine->val.push_back((RETT)op(x, y)); mine->rowptr[r+1]++; }
+                else if (notB && !both) { NU2 y = defaultBVal; mine->col.push_back(a.col[p]); mine->val.push_back((RETT)op(x, y)); mine->rowptr[r+1]++; }
+            }
+        }
+        std::partial_sum(mine->rowptr.begin(), mine->rowptr.end(), mine->rowptr.begin());
+    }
+    SpParMat<IU,RETT,RETDER> C;
     C.share(mine);
     return C;
 }

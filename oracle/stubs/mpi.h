@@ -266,6 +266,30 @@ static inline int MPI_Gather(const void *send, int scount, MPI_Datatype st, void
     return 0;
 }
 
+static inline int MPI_Allgather(const void *send, int scount, MPI_Datatype st, void *recv, int rcount, MPI_Datatype rt, MPI_Comm)
+{
+    using namespace fake_mpi;
+    size_t sb = (size_t)scount * dtsize(st); (void)rcount; (void)rt;
+    if (nranks() == 1) { std::memcpy(recv, send, sb); return 0; }
+    g_world->p0[t_rank] = send;
+    barrier();
+    for (int p = 0; p < nranks(); ++p) std::memcpy((uint8_t*)recv + p * sb, g_world->p0[p], sb);
+    barrier();
+    return 0;
+}
+
+static inline int MPI_Allgatherv(const void *send, int scount, MPI_Datatype st, void *recv, const int *rcnt, const int *rdis, MPI_Datatype rt, MPI_Comm)
+{
+    using namespace fake_mpi;
+    size_t sz = dtsize(st); (void)rt;
+    if (nranks() == 1) { std::memcpy((uint8_t*)recv + (size_t)rdis[0] * sz, send, (size_t)scount * sz); return 0; }
+    g_world->p0[t_rank] = send;
+    barrier();
+    for (int p = 0; p < nranks(); ++p) std::memcpy((uint8_t*)recv + (size_t)rdis[p] * sz, g_world->p0[p], (size_t)rcnt[p] * sz);
+    barrier();
+    return 0;
+}
+
 static inline int MPI_Gatherv(const void *send, int scount, MPI_Datatype st, void *recv, const int *rcnt, const int *rdis, MPI_Datatype rt, int root, MPI_Comm)
 {
     using namespace fake_mpi;

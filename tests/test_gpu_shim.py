@@ -73,3 +73,30 @@ def test_driver_sequence_from_the_fasta_file_through_the_shim(fixtures, golden, 
     assert digest(r.a_rowptr.astype(np.int64), acol, aval) == g["digests"]["A"]
     assert r.nnzB == g["nnzB"] and r.nnzB_pre == g["nnzB_pre"]
     assert digest(r.b_rowptr.astype(np.int64), r.b_col.astype(np.uint32), r.b_num.astype(np.int32)) == g["digests"]["B"]
+
+
+def test_transitive_reduction_through_the_shim(fixtures):
+    """TransitiveReduction(R) (include/TransitiveReduction.hpp:17) with src/TransitiveReduction.cpp replaced by the shim's version
+    (elba_fe_transitive_reduction on the device): R is built by the reference-side triple constructor, walked through
+    seqptr()->GetDCSC() as the reference's consumer does, and S comes back as an SpParMat<Overlap> - equal, entry for entry
+    and field for field, to what the reference's own file returns on the CPU."""
+    from oracle import oracle as O
+    from tr_inputs import overlap_graph, random_graph
+    klu = (17, 2, 8)
+    if not os.path.exists(O.shim_path(*klu)):
+        pytest.skip("oracle/_ref/libelba_shim_* not built (needs the reference headers)")
+    dna = fixtures("reads_fa")
+    n, rows, cols, f = overlap_graph(dna, 17, 2, 8)
+    got = O.ref_transitive_reduction(n, rows, cols, f, klu, shim=True)
+    want = O.transitive_reduction(n, rows, cols, f)
+    assert all(np.array_equal(a, b) for a, b in zip(got, want[:3]))
+    if O.ref_available(*klu):
+        ref = O.ref_transitive_reduction(n, rows, cols, f, klu)
+        assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    rng = np.random.default_rng(3)
+    for trial in range(10):
+        n = int(rng.integers(2, 30))
+        rows, cols, f = random_graph(rng, n, density=0.5)
+        got = O.ref_transitive_reduction(n, rows, cols, f, klu, shim=True)
+        want = O.transitive_reduction(n, rows, cols, f)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want[:3])), trial

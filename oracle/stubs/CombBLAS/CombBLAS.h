@@ -231,10 +231,14 @@ public:
         Dcsc *GetDCSC() const { return d && d->nzc ? d.get() : nullptr; }
         IT getnnz() const { return d ? (IT)d->ir.size() : 0; }
     };
+    /* CombBLAS hands out the matrix's own local block: it must live as long as the matrix does (callers keep raw Dcsc pointers) */
+    mutable std::shared_ptr<Seq> seq_cache; mutable const void *seq_of = nullptr;
     std::shared_ptr<Seq> seqptr() const
     {
         assert(fake_mpi::nranks() == 1 && "the stand-in's seqptr() serves one rank");
+        if (seq_cache && seq_of == (const void*)st.get()) return seq_cache;
         auto s = std::make_shared<Seq>(); s->d = std::make_shared<Dcsc>();
+        seq_cache = s; seq_of = (const void*)st.get();
         std::vector<std::tuple<IT,IT,IT>> t;      /* (col, row, position) */
         for (IT r = 0; r < st->m; ++r) for (IT p = st->rowptr[r]; p < st->rowptr[r+1]; ++p) t.emplace_back(st->col[p], r, p);
         std::sort(t.begin(), t.end());

@@ -287,7 +287,7 @@ int elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out)
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, cfg->device);
     if (e != cudaSuccess) return fail(nullptr, ELBA_FE_ERR_CUDA, cudaGetErrorString(e));
-    if (prop.major != 10) return fail(nullptr, ELBA_FE_ERR_NO_DEVICE, "device is not sm_100 (this library carries sm_100a code only)");
+    if (prop.major != 10 || prop.minor != 0) return fail(nullptr, ELBA_FE_ERR_NO_DEVICE, "device is not sm_100 (this library carries sm_100a code only)");
     ctx = new elba_fe_ctx;
     ctx->cfg = *cfg;
     ctx->sm_count = prop.multiProcessorCount;

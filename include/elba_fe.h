@@ -72,6 +72,8 @@ typedef struct elba_fe_ctx elba_fe_ctx;
 
 /* ---- lifetime ------------------------------------------------------------------ */
 void        elba_fe_default_config(elba_fe_config *cfg);     /* k=31 L=15 U=35 (Makefile:1-3), stride 1, seeds 2 */
+/* create: needs a compute-capability 10.0 device (the library carries sm_100a code only).  Side effect on the process:
+ * cudaLimitMaxL2FetchGranularity is set to 32 bytes for the device (sector-random table probes and 32-byte records). */
 int         elba_fe_create(const elba_fe_config *cfg, elba_fe_ctx **out);
 int         elba_fe_destroy(elba_fe_ctx *ctx);
 const char *elba_fe_last_error(const elba_fe_ctx *ctx);      /* ctx may be NULL: error of the last failed create */
@@ -86,8 +88,12 @@ int         elba_fe_set_stream(elba_fe_ctx *ctx, void *cuda_stream);
  * byte_off: offset of read i's first byte in the arena (DnaBuffer::getbufoffset(i) - getbufoffset(0))
  * len:      bases in read i (DnaSeq::size())
  * read_id_offset: global id of local read 0 (the MPI_Exscan of src/KmerOps.cpp:215-216)
- * _host copies from host memory (pinned or pageable) on the context's stream;
- * _device adopts pointers already resident in HBM (no copy; caller keeps them alive).
+ * upload_reads copies from host memory (pinned or pageable): the read tables on the context's stream, a large arena in
+ * slices on a second stream so that parsing starts while it arrives (the caller's buffers must stay valid until the
+ * next call that synchronises: elba_fe_count / elba_fe_run do).
+ * set_reads_device takes pointers already resident in HBM and COPIES them device-to-device into the context's own padded,
+ * 4-byte-aligned arena (the parse kernels read whole 32-bit words past a read's last byte); the caller's buffers are
+ * free again when the call returns.
  */
 int elba_fe_upload_reads(elba_fe_ctx *ctx, const uint8_t *packed, uint64_t packed_bytes,
                          const uint64_t *byte_off, const uint64_t *len, uint64_t nreads, int64_t read_id_offset);

@@ -10,7 +10,7 @@
 //   warp       = one item (found by a binary search over item_start, the same for all lanes: broadcast loads);
 //                in every step the 32 lanes produce 32 consecutive output bytes from 128 consecutive bases
 //                (129-130 consecutive input bytes with a line break inside): both sides coalesced
-//   lane       = 4 bases -> one byte; the line-break offset i / bases is one 32-bit division per lane and step
+//   lane       = 4 bases -> one byte; the lane carries (line, column) of its position from step to step
 #pragma once
 #include "common.cuh"
 
@@ -42,8 +42,17 @@ struct FastaView
 // items [item_begin, item_end) -> arena bytes.  A character outside the table carries code 4; the reference then ORs
 // uint8_t(4 << (6 - 2 i)) into the byte (src/DnaSeq.cpp:20-22), which for i > 0 sets the LOW bit of the base before it
 // and for i = 0 vanishes: reproduced, so that the arena equals the reference's byte for byte on any input.
+//
+// Measured first (profiles/r2_v21_ncu_k_fasta_pack_summary.txt): with one 32-bit division per output byte and a compare chain
+// per character the kernel issued 41 thread instructions per base (426 GB/s of text, 0.07 of HBM).  Now: the code table sits
+// in shared memory (one LDS per character), and a lane keeps (line, column) of its position and advances it by the 128 bases
+// a warp step covers (one division per lane and WORK ITEM, not per byte); lines of fewer than 4 bases and reads of 2^32 bases
+// or more take the general per-byte path.
 __global__ void __launch_bounds__(256) k_fasta_pack(FastaView fv, u64 item_begin, u64 item_end, uint8_t *__restrict__ arena)
 {
+    __shared__ uint8_t s_code[256];
+    s_code[threadIdx.x & 255] = (uint8_t)fasta_code(threadIdx.x & 255);
+    __syncthreads();
     const u32 lane = threadIdx.x & 31;
     const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
     for (u64 it = item_begin + (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5); it < item_end; it += nwarps)
@@ -58,13 +67,34 @@ __global__ void __launch_bounds__(256) k_fasta_pack(FastaView fv, u64 item_begin
         const u64 bend = min(nbytes, b0 + FI_ITEM_BYTES);
         uint8_t *__restrict__ out = arena + __ldg(fv.off + r);
         const uint8_t *__restrict__ in = fv.raw + pos;
+        if (bases >= 4 && ((len | bases) >> 32) == 0)
+        {
+            // at most one line break inside the 4 bases of a lane
+            const u32 B = (u32)bases, L = (u32)len;
+            const u32 sq = 128u / B, sr = 128u - sq * B;                           // what 128 bases add to (line, column)
+            u32 i0 = (u32)(b0 + lane) << 2;                                        // first base of my byte
+            u32 q = i0 / B, rem = i0 - q * B;                                      // its line and its column in the line
+#pragma unroll 1
+            for (u64 b = b0 + lane; b < bend; b += 32)
+            {
+                const uint8_t *__restrict__ p = in + ((u64)i0 + q);               // the byte of base i0
+                const u32 nb = min(4u, L - i0);
+                const u32 t = B - rem;                                             // bases of mine before the line ends (>= 1)
+                u32 byte = (u32)s_code[__ldg(p)] << 6;
+                if (nb > 1) byte |= ((u32)s_code[__ldg(p + 1 + (1u >= t ? 1 : 0))] << 4) & 0xFFu;
+                if (nb > 2) byte |= ((u32)s_code[__ldg(p + 2 + (2u >= t ? 1 : 0))] << 2) & 0xFFu;
+                if (nb > 3) byte |= (u32)s_code[__ldg(p + 3 + (3u >= t ? 1 : 0))];
+                out[b] = (uint8_t)byte;
+                i0 += 128u; q += sq; rem += sr;
+                if (rem >= B) { rem -= B; ++q; }
+            }
+            continue;
+        }
 #pragma unroll 1
         for (u64 b = b0 + lane; b < bend; b += 32)
         {
             const u64 i0 = b << 2;                                                 // first base of this byte
-            u64 q, rem;                                                            // i0 = q * bases + rem
-            if (((i0 | bases) >> 32) == 0) { q = (u32)i0 / (u32)bases; rem = (u32)i0 - (u32)q * (u32)bases; }
-            else { q = i0 / bases; rem = i0 - q * bases; }
+            const u64 q = i0 / bases; u64 rem = i0 - q * bases;                    // i0 = q * bases + rem
             u64 p = i0 + q;                                                        // input byte of base i0
             const u32 nb = (u32)min((u64)4, len - i0);
             u32 byte = 0;
@@ -73,8 +103,7 @@ __global__ void __launch_bounds__(256) k_fasta_pack(FastaView fv, u64 item_begin
             {
                 if (j < nb)
                 {
-                    const u32 code = fasta_code(__ldg(in + p));
-                    byte |= (code << (6 - 2 * j)) & 0xFFu;
+                    byte |= ((u32)s_code[__ldg(in + p)] << (6 - 2 * j)) & 0xFFu;
                     ++p; if (++rem == bases) { rem = 0; ++p; }                     // the line ends: skip its separator
                 }
             }

@@ -102,3 +102,50 @@ def test_gloo_world2_bootstrap_partition_and_merge():
         firsts, counts = [a[0] for a in allt], [a[1] for a in allt]
         assert firsts[0] == 0 and firsts[1] == counts[0] and sum(counts) == 227
         assert nnz == 227 * world and rows_ok and cols_sorted
+
+
+def _fasta_worker(rank, world, port, path, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from elba_b200 import fasta as F
+    from oracle import oracle as O
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # what every rank of the multi-GPU ingest does on the host: its own index block, its own chunk of the file
+    idx = F.FastaIndex(path, rank, world)
+    start, end = idx.chunk_extent()
+    chunk = idx.read_chunk()
+    arena = O.fasta_pack(chunk.tobytes(), start, idx.getmyrecords())        # the checker stands in for the device call here
+    t = torch.tensor([idx.getmyreaddispl(), idx.getmyreadcount(), start, end, arena.size], dtype=torch.int64)
+    allt = [torch.zeros(5, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allt, t)
+    parts = [None] * world
+    dist.all_gather_object(parts, arena)
+    q.put((rank, [x.tolist() for x in allt], np.concatenate(parts)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_fasta_index_blocks_and_chunks(fixtures, tmp_path):
+    """Two ranks ingest their blocks of one FASTA file (src/FastaIndex.cpp:98-176,191-290): consecutive read blocks, chunks that
+    do not overlap, and the arenas of the ranks, put end to end, are the arena of the whole file."""
+    import torch.multiprocessing as mp
+    from elba_b200 import fasta as F
+    dna = fixtures("reads_fa").slice(0, 90)
+    path = str(tmp_path / "reads.fa")
+    F.write_fasta(path, [dna.read_ascii(i) for i in range(dna.size())], 70)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, 29741
+    procs = [ctx.Process(target=_fasta_worker, args=(r, world, port, path, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((r for r in (q.get(timeout=180) for _ in range(world))), key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, allt, whole in res:
+        displ, count, start, end, nbytes = zip(*allt)
+        assert displ[0] == 0 and displ[1] == count[0] and sum(count) == 90
+        assert start[0] < end[0] <= start[1] < end[1] <= os.path.getsize(path)
+        assert sum(nbytes) == dna.buf.size and np.array_equal(whole, dna.buf)

@@ -203,11 +203,15 @@ int elba_fe_B_dcsc(elba_fe_ctx *ctx, uint64_t *nzc);
 int elba_fe_get_B_dcsc(elba_fe_ctx *ctx, int64_t *jc, int64_t *cp, int64_t *ir, int32_t *numshared, uint32_t *seeds);
 int elba_fe_device_B_dcsc(elba_fe_ctx *ctx, const int64_t **jc, const int64_t **cp, const int64_t **ir, const int32_t **numshared, const uint32_t **seeds);
 
-/* ---- the consumer of B (next row of the hot path; first version, one GPU) ------------------------------------------ */
+/* ---- the consumer of B (next row of the hot path; first version of the kernel) --------------------------------------- */
 /* X-drop seed-and-extend of B's nonzeros: PairwiseAlignment (src/PairwiseAlignment.cpp:5-106) keeps the strict upper
  * triangle of the local block (:52) and runs Overlap(len, seeds[0]).extend_overlap on each (:90-91; src/Overlap.cpp:20-73;
  * xdrop_aligner + classify_alignment, src/XDropAligner.cpp:7-282).  mat / mis / gap / dropoff: src/main.cpp:53-56
- * (1, -1, -1, 15).  *npairs = number of aligned pairs. */
+ * (1, -1, -1, 15).  *npairs = number of aligned pairs of THIS rank.
+ * Several GPUs: COLLECTIVE (every rank calls it): rank (i, j) aligns the nonzeros of its block of B; the reads of the other
+ * ranks it needs are all-gathered over NVLink inside the call (the reference: DistributedFastaData, src/DistributedFastaData.cpp:
+ * 98-232).  Pairs are selected by the reference's block-local rule (:52) on a square grid and by the global upper triangle
+ * (row < column) on the others, where the block-local rule would lose pairs: every unordered pair exactly once either way. */
 #define ELBA_FE_ALIGN_FIELDS 13   /* begQ endQ begT endT score rc passed containedQ containedT direction directionT suffix suffixT */
 int elba_fe_align(elba_fe_ctx *ctx, int mat, int mis, int gap, int dropoff, uint64_t *npairs);
 /* the aligned pairs in B's row-major order: global row / column read ids and ELBA_FE_ALIGN_FIELDS ints each = the fields of

@@ -286,8 +286,11 @@ def main():
         return s
 
     def timed(fn, steps, warmup):
+        import gc
         for _ in range(warmup):
             fn()
+        gc.collect()
+        gc.disable()            # a generation-2 collection of the interpreter on one rank stalls every rank at the next collective
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.reset_timings()
@@ -299,6 +302,7 @@ def main():
                 acc[a] = acc.get(a, 0.0) + b
         e1.record()
         barrier()
+        gc.enable()
         ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)   # device time, CUDA events on the launching stream
         if dist is not None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
